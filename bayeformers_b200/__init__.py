@@ -1,0 +1,62 @@
+"""bayeformers_b200 -- B200-native drop-in for the variational-layer hot path of
+yliess86/BayeFormers.
+
+    from bayeformers_b200 import to_bayesian
+    import bayeformers_b200.nn as bnn
+
+mirrors `from bayeformers import to_bayesian` / `import bayeformers.nn as bnn`.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Dict, Optional
+
+import torch
+import torch.nn as tnn
+
+from . import nn, runtime  # noqa: F401  (bayeformers_b200.nn is part of the public surface)
+from .nn import TORCH2BAYE, TORCH2BAYE_ALL
+from .nn.model import Model
+from .nn.parameters.base import Parameter
+from .nn.parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE
+from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
+from .runtime import manual_seed, mc_samples, set_gemm_dtype, set_kl_grad
+
+__all__ = ["to_bayesian", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype", "set_kl_grad"]
+
+
+def to_bayesian(model: tnn.Module, initialization: Optional[Initialization] = DEFAULT_UNIFORM,
+                prior: Optional[Parameter] = DEFAULT_SCALED_GAUSSIAN_MIXTURE, delta: float = None,
+                freeze: bool = False, *, layers: Optional[Dict[type, type]] = None, gemm_dtype=None,
+                kl_grad: Optional[bool] = None) -> Model:
+    """Deep-copy `model` and swap every convertible child for its Bayesian
+    equivalent; returns the copy wrapped in `bnn.Model`.
+
+    Same positional contract as the reference
+    (/root/reference/bayeformers/__init__.py:19-63): exact-class matching (so
+    subclasses and the root module are left alone, quirk Q7), `delta` switches
+    MOPED initialisation on, `freeze` stops gradients to mu.
+
+    Keyword-only extensions (defaults = reference behaviour):
+      layers      registry to use; default `TORCH2BAYE` (nn.Linear only, like the
+                  reference).  Pass `bnn.TORCH2BAYE_ALL` to convert Embedding and
+                  LayerNorm as well.
+      gemm_dtype  "fp32" (reference precision) or "bf16" (tcgen05 tensor cores)
+      kl_grad     True lets the KL term (log q - log p) back-propagate; the
+                  reference silently drops it (linear.py:99-102)
+    """
+    registry = TORCH2BAYE if layers is None else layers
+    dt = None if gemm_dtype is None else runtime._as_dtype(gemm_dtype)
+
+    def replace(parent: tnn.Module) -> None:
+        for name, child in parent.named_children():
+            if child.__class__ in registry:
+                baye = registry[child.__class__].from_frequentist(child, initialization, prior, delta, freeze)
+                baye.gemm_dtype, baye.kl_grad = dt, kl_grad
+                setattr(parent, name, baye)
+            else:
+                replace(child)
+
+    new_model = deepcopy(model)
+    replace(new_model)
+    return Model(model=new_model)

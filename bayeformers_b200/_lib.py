@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI library (include/bayeformers_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or a call
+fails, the product raises.  The library is a plain `extern "C"` .so (no torch
+types in any signature); PyTorch only supplies device pointers and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbayeformers_b200.so")
+
+BF_F32, BF_BF16 = 0, 1
+BF_PRIOR_MIXTURE, BF_PRIOR_GAUSSIAN, BF_PRIOR_NONE = 0, 1, 2
+
+# name -> (restype, argtypes); mirrors include/bayeformers_b200.h one to one
+SIGNATURES = {
+    "bf_abi_version": (c_int32, []),
+    "bf_last_error": (c_char_p, []),
+    "bf_device_is_sm100": (c_int32, []),
+    "bf_philox_normal": (c_int32, [c_void_p, c_int64, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p]),
+    "bf_sample_kl_workspace_bytes": (c_int64, [c_int64, c_int32]),
+    "bf_sample_kl_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
+                                   c_int64, c_int32, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_int32,
+                                   c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "bf_sample_kl_bwd": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                   c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_int32, c_uint64,
+                                   c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "bf_linear_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                c_int32, c_int32, c_void_p]),
+    "bf_linear_dgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
+                                  c_int32, c_void_p]),
+    "bf_linear_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
+                                  c_void_p]),
+    "bf_linear_wgrad_fused_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "bf_linear_wgrad_fused": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
+                                        c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
+                                        c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
+                                        c_int32, c_void_p, c_void_p]),
+    "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the library.  Raises NativeLibraryError when it has
+    not been built -- there is no Python/CPU substitute for the kernels."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m bayeformers_b200.build` "
+            "(the variational-layer kernels are CUDA-only; no fallback exists)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bf_abi_version() != 1:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.bf_abi_version()} vs binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().bf_last_error()
+        raise NativeLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,512 @@
+// Fused Philox sample + log q + log p (forward) and its stand-alone backward.
+//
+// Reference arithmetic being replaced (paths relative to /root/reference):
+//   bayeformers/nn/parameters/gaussian.py:90-101    Gaussian.sample
+//   bayeformers/nn/parameters/gaussian.py:103-116   Gaussian.log_prob (posterior q, MOPED prior p)
+//   bayeformers/nn/parameters/gaussian.py:160-171   ScaledGaussianMixture.log_prob
+//   bayeformers/nn/layers/linear.py:97-102          their call site in Linear.forward
+//
+// One pass over (mu, rho[, prior]) produces S weight samples and the 2*S
+// scalar reductions.  HBM traffic per element: 8 B read (+8 B for a Gaussian
+// prior, +0 when prior_mu aliases mu... still 4 B rho_p) and S*b_w written;
+// eps lives only in registers.  Reductions are deterministic: per-thread
+// sequential -> warp shuffle tree -> block tree -> fixed-order final pass by
+// the last block to finish (no float atomics).
+#include "bf_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxSC = 8;  // samples handled per launch (accumulators stay in registers)
+
+struct SampleKlParams {
+    const float* mu;
+    const float* rho;
+    const float* prior_mu;
+    const float* prior_rho;
+    const float* eps_in;  // [S_total * n] or null
+    void* w_out;          // [S_total][w_stride] or null
+    float* logq_out;      // [S_total]
+    float* logp_out;
+    float* partials;      // [2*SC][gridDim.x]
+    unsigned int* counter;
+    int64_t n;
+    int64_t w_stride;
+    int s0;  // first sample of this launch
+    int accumulate;
+    uint32_t k0, k1, step, tensor_id;
+    BfMixture mix;
+};
+
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&lo);
+    v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(p), v);
+}
+template <typename T>
+__device__ __forceinline__ void store1(T* p, float a);
+template <>
+__device__ __forceinline__ void store1<float>(float* p, float a) { *p = a; }
+template <>
+__device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float a) { *p = __float2bfloat16_rn(a); }
+
+// one element, one sample: returns w and adds the two log-prob terms
+template <int PRIOR>
+__device__ __forceinline__ float element_terms(float mu, float sigma, float neg_c_minus_logsig, float inv_two_var,
+                                               float eps, float pmu, float p_const, float p_inv_two_var,
+                                               const BfMixture& mix, float& q_acc, float& p_acc) {
+    // w = mu + eps*sigma with the reference's two roundings (no fma contraction)
+    const float w = __fadd_rn(mu, __fmul_rn(eps, sigma));
+    const float d = __fsub_rn(w, mu);
+    q_acc += neg_c_minus_logsig - __fmul_rn(d, d) * inv_two_var;
+    if (PRIOR == BF_PRIOR_MIXTURE) {
+        p_acc += bf_mixture_logp(w, mix);
+    } else if (PRIOR == BF_PRIOR_GAUSSIAN) {
+        const float dp = __fsub_rn(w, pmu);
+        p_acc += p_const - __fmul_rn(dp, dp) * p_inv_two_var;
+    }
+    return w;
+}
+
+template <int PRIOR, typename WT, int SC, bool VEC>
+__global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlParams p) {
+    float q_acc[SC], p_acc[SC];
+#pragma unroll
+    for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
+
+    WT* const w_out = reinterpret_cast<WT*>(p.w_out);
+    const int64_t n = p.n;
+    const int64_t nquad = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        const int64_t i0 = q << 2;
+        const bool full = VEC && (i0 + 4 <= n);
+        float mu[4], rho[4], pmu[4], prho[4];
+        if (full) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+            mu[0] = a.x, mu[1] = a.y, mu[2] = a.z, mu[3] = a.w;
+            rho[0] = b.x, rho[1] = b.y, rho[2] = b.z, rho[3] = b.w;
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
+                pmu[0] = c.x, pmu[1] = c.y, pmu[2] = c.z, pmu[3] = c.w;
+                prho[0] = d.x, prho[1] = d.y, prho[2] = d.z, prho[3] = d.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = i0 + j < n;
+                mu[j] = ok ? __ldg(p.mu + i0 + j) : 0.0f;
+                rho[j] = ok ? __ldg(p.rho + i0 + j) : 0.0f;
+                if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                    pmu[j] = ok ? __ldg(p.prior_mu + i0 + j) : 0.0f;
+                    prho[j] = ok ? __ldg(p.prior_rho + i0 + j) : 0.0f;
+                }
+            }
+        }
+        // per-element quantities shared by the S samples
+        float sigma[4], qc[4], qiv[4], pc[4], piv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sigma[j] = bf_softplus(rho[j]);
+            qc[j] = -BF_LOG_SQRT_2PI - logf(sigma[j]);
+            qiv[j] = 1.0f / (2.0f * __fmul_rn(sigma[j], sigma[j]));
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                const float sp = bf_softplus(prho[j]);
+                pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
+                piv[j] = 1.0f / (2.0f * __fmul_rn(sp, sp));
+            } else {
+                pc[j] = piv[j] = 0.0f;
+                pmu[j] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            const int sg = p.s0 + s;
+            float e[4];
+            if (p.eps_in != nullptr) {
+                const float* ep = p.eps_in + (int64_t)sg * n + i0;
+                if (full) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(ep));
+                    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = (i0 + j < n) ? __ldg(ep + j) : 0.0f;
+                }
+            } else {
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
+                e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+            }
+            float w[4];
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j], p.mix,
+                                                q_acc[s], p_acc[s]);
+                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * p.w_stride + i0, w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i0 + j < n) {
+                        w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j],
+                                                    p.mix, q_acc[s], p_acc[s]);
+                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * p.w_stride + i0 + j, w[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- block reduction of the 2*SC accumulators -------------------------
+    __shared__ float red[2 * kMaxSC][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < SC; ++s) {
+        const float a = bf_warp_sum(q_acc[s]);
+        const float b = bf_warp_sum(p_acc[s]);
+        if (lane == 0) {
+            red[2 * s][warp] = a;
+            red[2 * s + 1][warp] = b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * SC) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
+        p.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(p.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- final fixed-order pass (one block): warp w handles value w, w+8, ..
+    for (int v = warp; v < 2 * SC; v += kThreads / 32) {
+        double t = 0.0;
+        const volatile float* row = p.partials + (int64_t)v * gridDim.x;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) t += (double)row[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) {
+            float* dst = ((v & 1) ? p.logp_out : p.logq_out) + p.s0 + (v >> 1);
+            const float r = (float)t;
+            *dst = p.accumulate ? (*dst + r) : r;
+        }
+    }
+    if (threadIdx.x == 0) *p.counter = 0u;  // self-reset for the next launch
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone backward
+// ---------------------------------------------------------------------------
+struct SampleKlBwdParams {
+    const void* grad_w;
+    const float* mu;
+    const float* rho;
+    const float* prior_mu;
+    const float* prior_rho;
+    const float* g_logq;
+    const float* g_logp;
+    const float* eps_in;
+    float* grad_mu;
+    float* grad_rho;
+    int64_t n;
+    int64_t gw_stride;
+    int S;
+    int accumulate;
+    uint32_t k0, k1, step, tensor_id;
+    BfMixture mix;
+};
+
+// 4 consecutive elements starting at i0 (vector access when `full`)
+__device__ __forceinline__ void ld4(const float* p, int64_t i0, int64_t n, bool full, float (&v)[4]) {
+    if (full) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p + i0));
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < n) ? __ldg(p + i0 + j) : 0.0f;
+    }
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, int64_t i0, int64_t n, bool full, float (&v)[4]) {
+    if (full) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p + i0));
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&a.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+        v[0] = __low2float(lo), v[1] = __high2float(lo), v[2] = __low2float(hi), v[3] = __high2float(hi);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < n) ? __bfloat162float(p[i0 + j]) : 0.0f;
+    }
+}
+__device__ __forceinline__ void st4_acc(float* p, int64_t i0, int64_t n, bool full, const float (&v)[4], int acc) {
+    if (full) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (acc) {
+            const float4 a = *reinterpret_cast<const float4*>(p + i0);
+            o.x += a.x, o.y += a.y, o.z += a.z, o.w += a.w;
+        }
+        *reinterpret_cast<float4*>(p + i0) = o;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < n) p[i0 + j] = acc ? p[i0 + j] + v[j] : v[j];
+    }
+}
+
+template <int PRIOR, typename GT, bool KL, bool VEC>
+__global__ void __launch_bounds__(kThreads) sample_kl_bwd_kernel(const SampleKlBwdParams p) {
+    const GT* const gw = reinterpret_cast<const GT*>(p.grad_w);
+    const int64_t n = p.n;
+    const int64_t nquad = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        const int64_t i0 = q << 2;
+        const bool full = VEC && (i0 + 4 <= n);
+        float rho[4], mu[4], pmu[4], sigma[4], inv_pvar[4], am[4], ar[4];
+        ld4(p.rho, i0, n, full, rho);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) am[j] = ar[j] = 0.0f, mu[j] = pmu[j] = sigma[j] = inv_pvar[j] = 0.0f;
+        if (KL) {
+            ld4(p.mu, i0, n, full, mu);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sigma[j] = bf_softplus(rho[j]);
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                float prho[4];
+                ld4(p.prior_mu, i0, n, full, pmu);
+                ld4(p.prior_rho, i0, n, full, prho);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float sp = bf_softplus(prho[j]);
+                    inv_pvar[j] = 1.0f / (sp * sp);
+                }
+            }
+        }
+        for (int s = 0; s < p.S; ++s) {
+            float e[4], g[4];
+            if (p.eps_in != nullptr) {
+                ld4(p.eps_in + (int64_t)s * n, i0, n, full, e);
+            } else {
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)s, p.tensor_id, p.step, p.k0, p.k1);
+                e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+            }
+            if (gw != nullptr) {
+                ld4(gw + (int64_t)s * p.gw_stride, i0, n, full, g);
+            } else {
+                g[0] = g[1] = g[2] = g[3] = 0.0f;
+            }
+            float glq = 0.0f, glp = 0.0f;
+            if (KL) {
+                glq = p.g_logq ? __ldg(p.g_logq + s) : 0.0f;
+                glp = p.g_logp ? __ldg(p.g_logp + s) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float gj = g[j];
+                if (KL) {
+                    const float w = __fadd_rn(mu[j], __fmul_rn(e[j], sigma[j]));
+                    float dp = 0.0f;
+                    if (PRIOR == BF_PRIOR_MIXTURE) dp = bf_mixture_dlogp(w, p.mix);
+                    if (PRIOR == BF_PRIOR_GAUSSIAN) dp = -(w - pmu[j]) * inv_pvar[j];
+                    gj += glp * dp;             // chain through w (both the mu and the sigma*eps path)
+                    ar[j] -= glq / sigma[j];    // d log q / d sigma = -1/sigma
+                }
+                am[j] += gj;
+                ar[j] += gj * e[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ar[j] *= bf_softplus_grad(rho[j]);
+        st4_acc(p.grad_rho, i0, n, full, ar, p.accumulate);
+        if (p.grad_mu != nullptr) st4_acc(p.grad_mu, i0, n, full, am, p.accumulate);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) philox_normal_kernel(float* out, int64_t n, uint32_t k0, uint32_t k1,
+                                                                 uint32_t step, uint32_t tensor_id, uint32_t sample) {
+    const int64_t nquad = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        const float4 v = bf_eps_quad((uint32_t)q, sample, tensor_id, step, k0, k1);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((q << 2) + j < n) out[(q << 2) + j] = e[j];
+    }
+}
+
+inline int grid_for(int64_t nquad, int blocks_per_sm) {
+    const int64_t want = (nquad + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)bf_num_sms() * blocks_per_sm;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+constexpr int kFwdBlocksPerSm = 8;
+
+template <int PRIOR, typename WT, bool VEC>
+int launch_fwd_sc(const SampleKlParams& p, int sc, int grid, cudaStream_t st) {
+    switch (sc) {
+        case 1: sample_kl_fwd_kernel<PRIOR, WT, 1, VEC><<<grid, kThreads, 0, st>>>(p); break;
+        case 2: sample_kl_fwd_kernel<PRIOR, WT, 2, VEC><<<grid, kThreads, 0, st>>>(p); break;
+        case 4: sample_kl_fwd_kernel<PRIOR, WT, 4, VEC><<<grid, kThreads, 0, st>>>(p); break;
+        case 8: sample_kl_fwd_kernel<PRIOR, WT, 8, VEC><<<grid, kThreads, 0, st>>>(p); break;
+        default: return BF_ERR_BAD_ARG;
+    }
+    return 0;
+}
+
+template <int PRIOR, typename WT>
+int launch_fwd_vec(const SampleKlParams& p, int sc, int grid, bool vec, cudaStream_t st) {
+    return vec ? launch_fwd_sc<PRIOR, WT, true>(p, sc, grid, st) : launch_fwd_sc<PRIOR, WT, false>(p, sc, grid, st);
+}
+
+template <int PRIOR>
+int launch_fwd_dtype(const SampleKlParams& p, int sc, int grid, bool vec, int w_dtype, cudaStream_t st) {
+    return w_dtype == BF_BF16 ? launch_fwd_vec<PRIOR, __nv_bfloat16>(p, sc, grid, vec, st)
+                              : launch_fwd_vec<PRIOR, float>(p, sc, grid, vec, st);
+}
+
+inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" int64_t bf_sample_kl_workspace_bytes(int64_t n, int32_t S) {
+    (void)n;
+    (void)S;
+    // [counter, padded to 256 B][2*kMaxSC rows of per-block partials]
+    const int64_t max_grid = (int64_t)bf_num_sms() * kFwdBlocksPerSm;
+    return 256 + (int64_t)2 * kMaxSC * max_grid * (int64_t)sizeof(float);
+}
+
+extern "C" int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
+                                const float* prior_rho, float pi, float sigma1, float sigma2, int64_t n, int32_t S,
+                                uint64_t seed, uint32_t step, uint32_t tensor_id, const float* eps_in, void* w_out,
+                                int32_t w_dtype, int64_t w_stride, float* logq_out, float* logp_out,
+                                int32_t accumulate, void* workspace, void* stream) {
+    BF_CHECK_ARG(mu && rho && logq_out && logp_out && workspace, "null pointer");
+    BF_CHECK_ARG(n >= 0 && S >= 1, "bad n or S");
+    BF_CHECK_ARG(prior_kind == BF_PRIOR_MIXTURE || prior_kind == BF_PRIOR_GAUSSIAN || prior_kind == BF_PRIOR_NONE,
+                 "bad prior_kind");
+    BF_CHECK_ARG(prior_kind != BF_PRIOR_GAUSSIAN || (prior_mu && prior_rho), "gaussian prior needs prior_mu/prior_rho");
+    BF_CHECK_ARG(w_dtype == BF_F32 || w_dtype == BF_BF16, "bad w_dtype");
+    BF_CHECK_ARG(w_out == nullptr || w_stride >= n, "w_stride < n");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    SampleKlParams p{};
+    p.mu = mu, p.rho = rho, p.prior_mu = prior_mu, p.prior_rho = prior_rho, p.eps_in = eps_in;
+    p.w_out = w_out, p.logq_out = logq_out, p.logp_out = logp_out;
+    p.counter = reinterpret_cast<unsigned int*>(workspace);
+    p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+    p.n = n, p.w_stride = w_stride, p.accumulate = accumulate;
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32);
+    p.step = step, p.tensor_id = tensor_id;
+    p.mix = bf_make_mixture(pi, sigma1, sigma2);
+
+    const int64_t nquad = (n + 3) >> 2;
+    const int grid = grid_for(nquad, kFwdBlocksPerSm);
+    const int esz = w_dtype == BF_BF16 ? 2 : 4;
+    bool vec = aligned16(mu) && aligned16(rho) && (eps_in == nullptr || (aligned16(eps_in) && n % 4 == 0));
+    if (prior_kind == BF_PRIOR_GAUSSIAN) vec = vec && aligned16(prior_mu) && aligned16(prior_rho);
+    if (w_out != nullptr) vec = vec && aligned16(w_out) && ((w_stride * esz) % 16 == 0);
+
+    for (int s0 = 0; s0 < S;) {
+        int sc = 1;
+        while (sc * 2 <= kMaxSC && s0 + sc * 2 <= S) sc *= 2;
+        p.s0 = s0;
+        int rc;
+        if (prior_kind == BF_PRIOR_MIXTURE)
+            rc = launch_fwd_dtype<BF_PRIOR_MIXTURE>(p, sc, grid, vec, w_dtype, st);
+        else if (prior_kind == BF_PRIOR_GAUSSIAN)
+            rc = launch_fwd_dtype<BF_PRIOR_GAUSSIAN>(p, sc, grid, vec, w_dtype, st);
+        else
+            rc = launch_fwd_dtype<BF_PRIOR_NONE>(p, sc, grid, vec, w_dtype, st);
+        if (rc) {
+            bf_set_error("bf_sample_kl_fwd: bad sample chunk");
+            return rc;
+        }
+        BF_LAUNCH_OK();
+        s0 += sc;
+    }
+    return 0;
+}
+
+extern "C" int bf_sample_kl_bwd(const void* grad_w, int32_t gw_dtype, int64_t gw_stride, const float* mu,
+                                const float* rho, int32_t prior_kind, const float* prior_mu, const float* prior_rho,
+                                float pi, float sigma1, float sigma2, const float* g_logq, const float* g_logp,
+                                int64_t n, int32_t S, uint64_t seed, uint32_t step, uint32_t tensor_id,
+                                const float* eps_in, float* grad_mu, float* grad_rho, int32_t accumulate,
+                                void* stream) {
+    BF_CHECK_ARG(rho && grad_rho, "null pointer");
+    BF_CHECK_ARG(n >= 0 && S >= 1, "bad n or S");
+    BF_CHECK_ARG(gw_dtype == BF_F32 || gw_dtype == BF_BF16, "bad gw_dtype");
+    const bool kl = (g_logq != nullptr) || (g_logp != nullptr);
+    BF_CHECK_ARG(!kl || mu, "KL gradient needs mu");
+    BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || (prior_mu && prior_rho), "gaussian prior needs arrays");
+    BF_CHECK_ARG(grad_w || kl, "nothing to do");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    SampleKlBwdParams p{};
+    p.grad_w = grad_w, p.mu = mu, p.rho = rho, p.prior_mu = prior_mu, p.prior_rho = prior_rho;
+    p.g_logq = g_logq, p.g_logp = g_logp, p.eps_in = eps_in, p.grad_mu = grad_mu, p.grad_rho = grad_rho;
+    p.n = n, p.gw_stride = gw_stride, p.S = S, p.accumulate = accumulate;
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32);
+    p.step = step, p.tensor_id = tensor_id;
+    p.mix = bf_make_mixture(pi, sigma1, sigma2);
+    const int grid = grid_for((n + 3) >> 2, 8);
+
+    bool vec = aligned16(rho) && aligned16(grad_rho) && (!grad_mu || aligned16(grad_mu)) &&
+               (!eps_in || (aligned16(eps_in) && n % 4 == 0));
+    if (kl) vec = vec && aligned16(mu) && (prior_kind != BF_PRIOR_GAUSSIAN || (aligned16(prior_mu) && aligned16(prior_rho)));
+    if (grad_w) vec = vec && ((reinterpret_cast<uintptr_t>(grad_w) & 15u) == 0) &&
+                      ((gw_stride * (gw_dtype == BF_BF16 ? 2 : 4)) % 16 == 0);
+#define BF_BWD(PRIOR, GT, KLF)                                                       \
+    do {                                                                             \
+        if (vec) sample_kl_bwd_kernel<PRIOR, GT, KLF, true><<<grid, kThreads, 0, st>>>(p);  \
+        else sample_kl_bwd_kernel<PRIOR, GT, KLF, false><<<grid, kThreads, 0, st>>>(p);     \
+    } while (0)
+    const bool bf = gw_dtype == BF_BF16;
+    if (!kl) {
+        if (bf) BF_BWD(BF_PRIOR_NONE, __nv_bfloat16, false);
+        else BF_BWD(BF_PRIOR_NONE, float, false);
+    } else if (prior_kind == BF_PRIOR_MIXTURE) {
+        if (bf) BF_BWD(BF_PRIOR_MIXTURE, __nv_bfloat16, true);
+        else BF_BWD(BF_PRIOR_MIXTURE, float, true);
+    } else if (prior_kind == BF_PRIOR_GAUSSIAN) {
+        if (bf) BF_BWD(BF_PRIOR_GAUSSIAN, __nv_bfloat16, true);
+        else BF_BWD(BF_PRIOR_GAUSSIAN, float, true);
+    } else {
+        if (bf) BF_BWD(BF_PRIOR_NONE, __nv_bfloat16, true);
+        else BF_BWD(BF_PRIOR_NONE, float, true);
+    }
+#undef BF_BWD
+    BF_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bf_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t step, uint32_t tensor_id,
+                                uint32_t sample_id, void* stream) {
+    BF_CHECK_ARG(out && n >= 0, "bad args");
+    if (n == 0) return 0;
+    const int grid = grid_for((n + 3) >> 2, 8);
+    philox_normal_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        out, n, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step, tensor_id, sample_id);
+    BF_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,88 @@
+"""Bayesian LayerNorm (absent from the reference snapshot).
+
+`weight` and `bias` are `Gaussian((H,))`; forward samples both, accumulates
+their log-probs into the layer scalars (weight then bias, as Linear does) and
+applies layer normalisation with the sampled affine.  Under MOPED a
+pretrained-style gamma = 1 gives sigma = delta and beta = 0 gives rho = 0
+(sigma = ln 2) through the reference's -inf -> 0 rule.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Size, Tensor
+
+from ... import ops, runtime
+from ..parameters.base import NoneParameter, Parameter
+from ..parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE, Gaussian, prior_spec_of
+from ..parameters.initializations import DEFAULT_UNIFORM, Initialization
+from .common import BayesianLayer, moped_
+
+
+class LayerNorm(BayesianLayer):
+    def __init__(self, normalized_shape: Union[int, Sequence[int]], eps: float = 1e-5,
+                 elementwise_affine: bool = True, bias: bool = True,
+                 initialization: Optional[Initialization] = DEFAULT_UNIFORM,
+                 prior: Optional[Parameter] = DEFAULT_SCALED_GAUSSIAN_MIXTURE) -> None:
+        super().__init__()
+        if isinstance(normalized_shape, int):
+            normalized_shape = (normalized_shape,)
+        if not elementwise_affine:
+            raise ValueError("a Bayesian LayerNorm needs elementwise_affine=True (there is nothing to sample otherwise)")
+        self.normalized_shape = tuple(normalized_shape)
+        self.eps = eps
+        self.initialization = initialization
+        self.weight = Gaussian(Size(self.normalized_shape), self.initialization)
+        self.weight_prior = prior
+        if bias:
+            self.bias = Gaussian(Size(self.normalized_shape), self.initialization)
+            self.bias_prior = prior
+        else:
+            self.bias = NoneParameter()
+            self.bias_prior = NoneParameter()
+        self._init_scalars()
+
+    def forward(self, input: Tensor) -> Tensor:
+        S = runtime.get_mc_samples()
+        kl_grad = self._kl_grad()
+        wp = prior_spec_of(self.weight_prior)
+        w, logq, logp = ops.SampleKL.apply(self.weight.mu, self.weight.rho, wp.mu, wp.rho, wp,
+                                           self.weight.next_stream(S), S, torch.float32, kl_grad)
+        b = None
+        if isinstance(self.bias, Gaussian):
+            bp = prior_spec_of(self.bias_prior)
+            b, lq_b, lp_b = ops.SampleKL.apply(self.bias.mu, self.bias.rho, bp.mu, bp.rho, bp,
+                                               self.bias.next_stream(S), S, torch.float32, kl_grad)
+            logq, logp = logq + lq_b, logp + lp_b
+        self._publish(logq, logp, S, kl_grad)
+        if S == 1:
+            return F.layer_norm(input, self.normalized_shape, w[0].to(input.dtype),
+                                None if b is None else b[0].to(input.dtype), self.eps)
+        if input.shape[0] % S != 0:
+            raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
+        xn = F.layer_norm(input, self.normalized_shape, None, None, self.eps)
+        lead = [S, input.shape[0] // S] + [1] * (input.dim() - 1 - len(self.normalized_shape))
+        xs = xn.view(S, input.shape[0] // S, *input.shape[1:])
+        shape_w = [S, 1] + [1] * (input.dim() - 1 - len(self.normalized_shape)) + list(self.normalized_shape)
+        y = xs * w.to(input.dtype).view(shape_w)
+        if b is not None:
+            y = y + b.to(input.dtype).view(shape_w)
+        del lead
+        return y.view(input.shape)
+
+    @classmethod
+    def from_frequentist(cls, ln: nn.Module, initialization: Optional[Initialization] = DEFAULT_UNIFORM,
+                         prior: Optional[Parameter] = DEFAULT_SCALED_GAUSSIAN_MIXTURE, delta: float = None,
+                         freeze: bool = False) -> "LayerNorm":
+        if ln.weight is None:
+            raise ValueError("cannot convert a LayerNorm without affine parameters")
+        has_bias = ln.bias is not None
+        baye = cls(ln.normalized_shape, ln.eps, True, has_bias, prior=prior)
+        if delta is not None:
+            baye.weight_prior = moped_(baye.weight, ln.weight, delta, freeze)
+            if has_bias:
+                baye.bias_prior = moped_(baye.bias, ln.bias, delta, freeze)
+        return baye

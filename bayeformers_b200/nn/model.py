@@ -1,0 +1,53 @@
+"""`bnn.Model`: wrapper that exposes the model-level ELBO scalars.
+
+API parity with /root/reference/bayeformers/nn/model.py:16-89: duck-typed
+detection of Bayesian children (both attribute names present), pass-through
+`forward` that calls `self.model.forward` directly (no hooks, quirk Q8), and
+`log_prior()` / `log_variational_posterior()` METHODS returning the sum of the
+children's scalars of the most recent forward, accumulated in module order.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any, List, Optional
+
+import torch
+from torch import Tensor
+from torch.nn import Module
+
+
+def is_module_bayesian(module: Module) -> bool:
+    return hasattr(module, "log_prior") and hasattr(module, "log_variational_posterior")
+
+
+class Model(Module):
+    def __init__(self, model: Optional[Module] = None) -> None:
+        super().__init__()
+        self.model = model
+
+    def forward(self, *args, **kwargs) -> Any:
+        if self.model is None:
+            raise NotImplementedError("Forward pass not implemented yet")
+        return self.model.forward(*args, **kwargs)
+
+    @property
+    def bayesian_children(self) -> List[Module]:
+        return [m for m in self.modules() if is_module_bayesian(m) and m is not self]
+
+    def _total(self, name: str) -> Tensor:
+        children = self.bayesian_children
+        if not children:
+            warnings.warn("No Bayesian Child is present in this model")
+        value = 0.0
+        for child in children:
+            # grad-carrying value when the layer ran with kl_grad=True, else the
+            # reference's detached Parameter
+            live = getattr(child, "live_" + name, None)
+            value = value + (live if live is not None else getattr(child, name))
+        return value
+
+    def log_prior(self) -> Tensor:
+        return self._total("log_prior")
+
+    def log_variational_posterior(self) -> Tensor:
+        return self._total("log_variational_posterior")

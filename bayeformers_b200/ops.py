@@ -1,0 +1,307 @@
+"""torch.autograd.Function wrappers that call the C-ABI kernels.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every
+arithmetic step of the hot path runs in libbayeformers_b200.so.  There is no
+eager/CPU substitute -- non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF_BF16, BF_F32, BF_PRIOR_GAUSSIAN, BF_PRIOR_MIXTURE, BF_PRIOR_NONE
+
+_workspaces: Dict[Tuple, torch.Tensor] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _dt(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return BF_F32
+    if t == torch.bfloat16:
+        return BF_BF16
+    raise TypeError(f"unsupported dtype {t}")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"bayeformers_b200: {what} is on {t.device}; the variational layers run on CUDA (sm_100a) only "
+            "-- there is no CPU path. Move the model and inputs to a B200 device.")
+
+
+def _workspace(kind: str, dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-filled-once scratch, one per (kind, device, stream)."""
+    key = (kind, dev.index, _stream(dev))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1024), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+@dataclass
+class PriorSpec:
+    """What the kernel needs to evaluate log p(w) (and its derivative)."""
+    kind: int = BF_PRIOR_NONE
+    pi: float = 0.5
+    sigma1: float = 1.0
+    sigma2: float = 1.0
+    mu: Optional[torch.Tensor] = None   # BF_PRIOR_GAUSSIAN
+    rho: Optional[torch.Tensor] = None
+
+
+@dataclass
+class StreamSpec:
+    """Identity of one eps draw: (seed, tensor_id, step); `eps` overrides the
+    Philox stream with injected values of shape [S, *param_shape] (parity)."""
+    seed: int = 0
+    tensor_id: int = 0
+    step: int = 0
+    eps: Optional[torch.Tensor] = None
+
+
+def _eps_arg(stream: StreamSpec, S: int, n: int, dev) -> Optional[torch.Tensor]:
+    if stream.eps is None:
+        return None
+    e = stream.eps.to(device=dev, dtype=torch.float32).contiguous()
+    if e.numel() != S * n:
+        raise ValueError(f"injected eps has {e.numel()} elements, expected S*n = {S}*{n}")
+    return e
+
+
+def sample_kl_forward(mu, rho, prior: PriorSpec, stream: StreamSpec, S: int, w_dtype, logq, logp, accumulate: bool,
+                      want_w: bool = True):
+    """w[S, *mu.shape] and logq/logp[S] (+= when accumulate) in one kernel pass."""
+    lib = _lib.load()
+    dev = mu.device
+    n = mu.numel()
+    eps = _eps_arg(stream, S, n, dev)
+    w = torch.empty((S,) + tuple(mu.shape), dtype=w_dtype, device=dev) if want_w else None
+    ws = _workspace("sample_kl", dev, lib.bf_sample_kl_workspace_bytes(n, S))
+    pmu = prior.mu if prior.kind == BF_PRIOR_GAUSSIAN else None
+    prho = prior.rho if prior.kind == BF_PRIOR_GAUSSIAN else None
+    rc = lib.bf_sample_kl_fwd(_ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho), prior.pi, prior.sigma1,
+                              prior.sigma2, n, S, stream.seed, stream.step, stream.tensor_id, _ptr(eps), _ptr(w),
+                              _dt(w_dtype), n, _ptr(logq), _ptr(logp), int(accumulate), _ptr(ws), _stream(dev))
+    _lib.check(rc, "bf_sample_kl_fwd")
+    return w
+
+
+def sample_kl_backward(grad_w, mu, rho, prior: PriorSpec, stream: StreamSpec, S: int, g_logq, g_logp, need_mu: bool):
+    lib = _lib.load()
+    dev = rho.device
+    n = rho.numel()
+    eps = _eps_arg(stream, S, n, dev)
+    g_rho = torch.empty_like(rho, dtype=torch.float32)
+    g_mu = torch.empty_like(rho, dtype=torch.float32) if need_mu else None
+    if grad_w is None and g_logq is None and g_logp is None:
+        g_rho.zero_()
+        if g_mu is not None:
+            g_mu.zero_()
+        return g_mu, g_rho
+    gw_dt = BF_F32
+    if grad_w is not None:
+        grad_w = grad_w.contiguous()
+        gw_dt = _dt(grad_w.dtype)
+    pmu = prior.mu if prior.kind == BF_PRIOR_GAUSSIAN else None
+    prho = prior.rho if prior.kind == BF_PRIOR_GAUSSIAN else None
+    rc = lib.bf_sample_kl_bwd(_ptr(grad_w), gw_dt, n, _ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho),
+                              prior.pi, prior.sigma1, prior.sigma2, _ptr(g_logq), _ptr(g_logp), n, S, stream.seed,
+                              stream.step, stream.tensor_id, _ptr(eps), _ptr(g_mu), _ptr(g_rho), 0, _stream(dev))
+    _lib.check(rc, "bf_sample_kl_bwd")
+    return g_mu, g_rho
+
+
+def _kl_upstream(g, S, dev):
+    if g is None:
+        return torch.zeros(S, dtype=torch.float32, device=dev)
+    return g.to(torch.float32).reshape(S).contiguous()
+
+
+class SampleKL(torch.autograd.Function):
+    """(mu, rho) -> (w[S,...], log q[S], log p[S]) for one variational tensor.
+    Replaces Gaussian.sample + the two log_prob calls of the reference
+    (gaussian.py:90-116,160-171) with one fused pass; backward regenerates eps."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, prior_mu, prior_rho, prior: PriorSpec, stream: StreamSpec, S: int, w_dtype, kl_grad):
+        _require_cuda(mu, "variational parameter")
+        prior = PriorSpec(prior.kind, prior.pi, prior.sigma1, prior.sigma2, prior_mu, prior_rho)
+        dev = mu.device
+        logq = torch.empty(S, dtype=torch.float32, device=dev)
+        logp = torch.empty(S, dtype=torch.float32, device=dev)
+        w = sample_kl_forward(mu.detach(), rho.detach(), prior, stream, S, w_dtype, logq, logp, False)
+        ctx.save_for_backward(mu, rho, prior_mu, prior_rho)
+        ctx.meta = (prior, stream, S, kl_grad)
+        if not kl_grad:
+            ctx.mark_non_differentiable(logq, logp)
+        return w, logq, logp
+
+    @staticmethod
+    def backward(ctx, gw, glq, glp):
+        mu, rho, prior_mu, prior_rho = ctx.saved_tensors
+        prior, stream, S, kl_grad = ctx.meta
+        prior = PriorSpec(prior.kind, prior.pi, prior.sigma1, prior.sigma2, prior_mu, prior_rho)
+        dev = rho.device
+        if kl_grad:
+            glq, glp = _kl_upstream(glq, S, dev), _kl_upstream(glp, S, dev)
+        else:
+            glq = glp = None
+        if gw is not None:
+            gw = gw.reshape(S, -1)
+            if gw.dtype not in (torch.float32, torch.bfloat16):
+                gw = gw.float()
+        g_mu, g_rho = sample_kl_backward(gw, mu.detach(), rho.detach(), prior, stream, S, glq, glp,
+                                         ctx.needs_input_grad[0])
+        return g_mu, g_rho, None, None, None, None, None, None, None
+
+
+@dataclass
+class LinearSpec:
+    S: int
+    gemm_dtype: torch.dtype
+    kl_grad: bool
+    w_prior: PriorSpec
+    b_prior: PriorSpec
+    w_stream: StreamSpec
+    b_stream: StreamSpec = field(default_factory=StreamSpec)
+
+
+def tc_eligible(N: int, K: int) -> bool:
+    """Shapes the TMA-fed tcgen05 path accepts (16-byte global row strides)."""
+    return N % 8 == 0 and K % 8 == 0
+
+
+class BayesLinear(torch.autograd.Function):
+    """y, log q[S], log p[S] = BayesLinear(x, mu/rho of weight and bias, priors).
+
+    Forward : fused sample+KL for W (and b) -> batched-over-S contraction.
+    Backward: dgrad contraction; wgrad contraction whose epilogue regenerates
+              eps and emits dmu / drho directly (bf16 mode), or fp32 wgrad +
+              the stand-alone variational backward (fp32 parity mode).
+    Replaces Linear.forward (linear.py:83-104) and its autograd graph."""
+
+    @staticmethod
+    def forward(ctx, x, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, spec: LinearSpec):
+        _require_cuda(x, "input")
+        _require_cuda(w_mu, "weight")
+        lib = _lib.load()
+        dev = x.device
+        S = spec.S
+        N, K = w_mu.shape
+        rows = x.numel() // K
+        if x.shape[-1] != K or rows % S != 0:
+            raise ValueError(f"input {tuple(x.shape)} incompatible with weight {(N, K)} and mc_samples={S}")
+        M = rows // S
+        use_tc = spec.gemm_dtype == torch.bfloat16 and tc_eligible(N, K)
+        cdt = torch.bfloat16 if use_tc else torch.float32
+        xg = x.detach().reshape(S, M, K).to(cdt).contiguous()
+        has_bias = b_mu is not None
+
+        logq = torch.empty(S, dtype=torch.float32, device=dev)
+        logp = torch.empty(S, dtype=torch.float32, device=dev)
+        w_prior = PriorSpec(spec.w_prior.kind, spec.w_prior.pi, spec.w_prior.sigma1, spec.w_prior.sigma2, wp_mu, wp_rho)
+        W = sample_kl_forward(w_mu.detach(), w_rho.detach(), w_prior, spec.w_stream, S, cdt, logq, logp, False)
+        b = None
+        b_prior = None
+        if has_bias:
+            b_prior = PriorSpec(spec.b_prior.kind, spec.b_prior.pi, spec.b_prior.sigma1, spec.b_prior.sigma2,
+                                bp_mu, bp_rho)
+            b = sample_kl_forward(b_mu.detach(), b_rho.detach(), b_prior, spec.b_stream, S, torch.float32, logq, logp,
+                                  True)
+        out_dtype = x.dtype if (use_tc and x.dtype in (torch.float32, torch.bfloat16)) else torch.float32
+        y = torch.empty((S, M, N), dtype=out_dtype, device=dev)
+        if M > 0:
+            rc = lib.bf_linear_fwd(_ptr(xg), _ptr(W), _ptr(b), _ptr(y), S, M, N, K, _dt(cdt), _dt(out_dtype),
+                                   _stream(dev))
+            _lib.check(rc, "bf_linear_fwd")
+        ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho)
+        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape))
+        if not spec.kl_grad:
+            ctx.mark_non_differentiable(logq, logp)
+        if x.dtype != out_dtype:
+            y = y.to(x.dtype)
+        return y.view(*x.shape[:-1], N), logq, logp
+
+    @staticmethod
+    def backward(ctx, gy, glq, glp):
+        lib = _lib.load()
+        xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho = ctx.saved_tensors
+        spec, use_tc, M, x_dtype, x_shape = ctx.meta
+        S = spec.S
+        N, K = w_mu.shape
+        dev = xg.device
+        cdt = torch.bfloat16 if use_tc else torch.float32
+        st = _stream(dev)
+        if spec.kl_grad:
+            glq, glp = _kl_upstream(glq, S, dev), _kl_upstream(glp, S, dev)
+        else:
+            glq = glp = None
+        w_prior = PriorSpec(spec.w_prior.kind, spec.w_prior.pi, spec.w_prior.sigma1, spec.w_prior.sigma2, wp_mu, wp_rho)
+        has_bias = b_mu is not None
+        need_wmu, need_bmu = ctx.needs_input_grad[1], (has_bias and ctx.needs_input_grad[3])
+
+        g_x = g_wmu = g_wrho = g_bmu = g_brho = None
+        have_gy = gy is not None and M > 0
+        if have_gy:
+            gyc = gy.reshape(S, M, N).to(cdt).contiguous()
+            if ctx.needs_input_grad[0]:
+                dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
+                dx = torch.empty((S, M, K), dtype=dx_dtype, device=dev)
+                rc = lib.bf_linear_dgrad(_ptr(gyc), _ptr(W), _ptr(dx), S, M, N, K, _dt(cdt), _dt(dx_dtype), st)
+                _lib.check(rc, "bf_linear_dgrad")
+                g_x = dx.view(x_shape).to(x_dtype)
+            if has_bias:
+                db = torch.empty((S, N), dtype=torch.float32, device=dev)
+                rc = lib.bf_bias_grad(_ptr(gyc), _dt(cdt), _ptr(db), S, M, N, st)
+                _lib.check(rc, "bf_bias_grad")
+            if use_tc:
+                g_wrho = torch.empty_like(w_rho, dtype=torch.float32)
+                g_wmu = torch.empty_like(w_rho, dtype=torch.float32) if need_wmu else None
+                eps = _eps_arg(spec.w_stream, S, N * K, dev)
+                ws = _workspace("wgrad_turn", dev, lib.bf_linear_wgrad_fused_workspace_bytes(N, K))
+                pk = w_prior.kind
+                rc = lib.bf_linear_wgrad_fused(
+                    _ptr(gyc), _ptr(xg), S, M, N, K, BF_BF16, _ptr(w_mu), _ptr(w_rho), pk,
+                    _ptr(wp_mu if pk == BF_PRIOR_GAUSSIAN else None),
+                    _ptr(wp_rho if pk == BF_PRIOR_GAUSSIAN else None), w_prior.pi, w_prior.sigma1, w_prior.sigma2,
+                    _ptr(glq), _ptr(glp), spec.w_stream.seed, spec.w_stream.step, spec.w_stream.tensor_id, _ptr(eps),
+                    _ptr(g_wmu), _ptr(g_wrho), 0, _ptr(ws), st)
+                _lib.check(rc, "bf_linear_wgrad_fused")
+            else:
+                dW = torch.empty((S, N, K), dtype=torch.float32, device=dev)
+                rc = lib.bf_linear_wgrad(_ptr(gyc), _ptr(xg), _ptr(dW), S, M, N, K, BF_F32, st)
+                _lib.check(rc, "bf_linear_wgrad")
+                g_wmu, g_wrho = sample_kl_backward(dW.view(S, -1), w_mu.detach(), w_rho.detach(), w_prior,
+                                                   spec.w_stream, S, glq, glp, need_wmu)
+        else:
+            g_wmu, g_wrho = sample_kl_backward(None, w_mu.detach(), w_rho.detach(), w_prior, spec.w_stream, S, glq,
+                                               glp, need_wmu)
+            db = None
+        if has_bias:
+            b_prior = PriorSpec(spec.b_prior.kind, spec.b_prior.pi, spec.b_prior.sigma1, spec.b_prior.sigma2,
+                                bp_mu, bp_rho)
+            g_bmu, g_brho = sample_kl_backward(db, b_mu.detach(), b_rho.detach(), b_prior, spec.b_stream, S, glq, glp,
+                                               need_bmu)
+        return g_x, g_wmu, g_wrho, g_bmu, g_brho, None, None, None, None, None
+
+
+def philox_normal(n: int, seed: int, step: int, tensor_id: int, sample_id: int, device) -> torch.Tensor:
+    """eps stream of one (tensor, sample, step) -- for the statistical tests."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    rc = lib.bf_philox_normal(_ptr(out), n, seed, step, tensor_id, sample_id, _stream(dev))
+    _lib.check(rc, "bf_philox_normal")
+    return out

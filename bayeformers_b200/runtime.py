@@ -1,0 +1,93 @@
+"""Process-wide runtime options of the variational layers.
+
+Everything here is an *additive extension* over the reference API; the
+defaults reproduce the reference's behaviour:
+
+  mc_samples = 1      one weight sample per forward (bayeformers/nn/layers/linear.py:97)
+  kl_grad    = False  log-probs detached like the reference's `.data =` (linear.py:99-102)
+  gemm_dtype = fp32   reference precision (bayeformers/nn/parameters/base.py:32)
+
+The eps stream is counter based (Philox4x32-10): eps is a pure function of
+(seed, tensor_id, step, sample_id, element), so backward regenerates it and
+data-parallel replicas draw identical weights with no communication.
+"""
+from __future__ import annotations
+
+import contextlib
+import itertools
+import threading
+from typing import Optional
+
+import torch
+
+_state = threading.local()
+_tensor_ids = itertools.count(1)
+_global = {"seed": None, "kl_grad": False, "gemm_dtype": torch.float32}
+
+
+def next_tensor_id() -> int:
+    """Stream id of a new variational tensor (construction order => identical
+    on every rank that builds the same model)."""
+    return next(_tensor_ids)
+
+
+def manual_seed(seed: int) -> None:
+    """Seed of the eps stream.  Call with the same value on every rank."""
+    _global["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def seed() -> int:
+    """Current seed; if never set it is taken once from torch's default
+    generator, so `torch.manual_seed` also fixes the eps stream."""
+    if _global["seed"] is None:
+        _global["seed"] = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    return _global["seed"]
+
+
+def get_mc_samples() -> int:
+    return getattr(_state, "mc_samples", 1)
+
+
+@contextlib.contextmanager
+def mc_samples(S: int):
+    """Fold S Monte-Carlo samples into the leading (batch) dimension: inside
+    the context a Bayesian layer treats its input as [S*B, ...], uses weight
+    sample s for rows [s*B, (s+1)*B) and reports [S]-shaped log-probs.
+    Bit-identical to the reference's sequential S-loop given the same eps
+    (SURVEY.md section 0, item 3)."""
+    S = int(S)
+    if S < 1:
+        raise ValueError("mc_samples must be >= 1")
+    prev = get_mc_samples()
+    _state.mc_samples = S
+    try:
+        yield
+    finally:
+        _state.mc_samples = prev
+
+
+def set_kl_grad(flag: bool) -> None:
+    _global["kl_grad"] = bool(flag)
+
+
+def get_kl_grad() -> bool:
+    return _global["kl_grad"]
+
+
+def _as_dtype(d) -> torch.dtype:
+    if isinstance(d, torch.dtype):
+        out = d
+    else:
+        out = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16,
+               "bfloat16": torch.bfloat16}[str(d)]
+    if out not in (torch.float32, torch.bfloat16):
+        raise ValueError("gemm_dtype must be fp32 or bf16")
+    return out
+
+
+def set_gemm_dtype(d) -> None:
+    _global["gemm_dtype"] = _as_dtype(d)
+
+
+def get_gemm_dtype() -> torch.dtype:
+    return _global["gemm_dtype"]

@@ -1,0 +1,160 @@
+/*
+ * bayeformers_b200 -- C ABI of the B200-native variational-layer hot path.
+ *
+ * The reference (yliess86/BayeFormers) has no FFI of its own: its operator
+ * surface is the Python module `bayeformers.nn`.  This
+ * header is the boundary a maintainer of the reference would bind to replace
+ * the arithmetic inside
+ *
+ *     bayeformers/nn/parameters/gaussian.py:90-116   Gaussian.sample / log_prob
+ *     bayeformers/nn/parameters/gaussian.py:160-171  ScaledGaussianMixture.log_prob
+ *     bayeformers/nn/layers/linear.py:83-104         Linear.forward (+ its autograd)
+ *
+ * Conventions (all functions):
+ *   - plain C types only: raw DEVICE pointers, sizes as int64_t, the CUDA
+ *     stream as an opaque `void*` (a cudaStream_t);
+ *   - return 0 on success, otherwise a non-zero code (a cudaError_t, or
+ *     BF_ERR_*); `bf_last_error()` gives the text for the calling thread;
+ *   - never allocate device memory, never synchronise the stream, never
+ *     throw; workspaces are caller-provided and sized by the *_workspace_bytes
+ *     queries; the caller keeps every buffer alive until the stream reaches
+ *     the kernel;
+ *   - a workspace must be zero-filled ONCE when it is allocated (it holds a
+ *     self-resetting completion counter) and must not be shared by launches
+ *     that may run concurrently on different streams.
+ *
+ * Philox contract (what "eps" is when `eps_in == NULL`): see oracle/philox_oracle.py
+ * and DESIGN.md.  counter = (flat_index >> 2, sample_id, tensor_id, step),
+ * key = seed; philox4x32-10; two Box-Muller pairs per counter.
+ */
+#ifndef BAYEFORMERS_B200_H_
+#define BAYEFORMERS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_ABI_VERSION 1
+
+/* element types of activation / sampled-weight buffers */
+#define BF_F32 0
+#define BF_BF16 1
+
+/* prior kinds */
+#define BF_PRIOR_MIXTURE 0  /* ScaledGaussianMixture(pi, sigma1, sigma2): gaussian.py:119-171 */
+#define BF_PRIOR_GAUSSIAN 1 /* Gaussian(prior_mu, prior_rho), the MOPED prior: linear.py:147-150 */
+#define BF_PRIOR_NONE 2     /* no prior term (log p contribution 0) */
+
+/* error codes beyond cudaError_t */
+#define BF_ERR_BAD_ARG 10001
+#define BF_ERR_UNSUPPORTED 10002
+#define BF_ERR_DRIVER 10003
+
+int bf_abi_version(void);
+const char* bf_last_error(void);
+/* 1 when the running device is sm_100 (tcgen05 path usable), else 0; <0 on error */
+int bf_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------- *
+ * eps stream, exposed for the statistical tests.
+ * Replaces: eps = self.normal.sample(self.size)   (gaussian.py:100)
+ * out[i] = eps(i | seed, step, tensor_id, sample_id), i in [0, n)
+ * ------------------------------------------------------------------------- */
+int bf_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t step, uint32_t tensor_id,
+                     uint32_t sample_id, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused sample + log q + log p for one variational tensor and S MC samples.
+ * Replaces, per sample: Gaussian.sample (gaussian.py:90-101), Gaussian.log_prob
+ * of the posterior (gaussian.py:103-116) and the prior's log_prob
+ * (gaussian.py:160-171 mixture, or gaussian.py:103-116 on the MOPED prior) as
+ * called from Linear.forward (linear.py:97-102).
+ *
+ *   for s in [0,S):  eps_s = eps_in ? eps_in[s*n + i] : philox(seed, step, tensor_id, s)
+ *                    w_s[i] = mu[i] + eps_s[i] * softplus(rho[i])      -> w_out[s*w_stride + i]
+ *                    logq[s] (+)= sum_i  -log sqrt(2pi) - log sigma_i - (w_s[i]-mu[i])^2 / (2 sigma_i^2)
+ *                    logp[s] (+)= sum_i  log p(w_s[i])
+ *
+ * mu, rho            [n] fp32
+ * prior_mu, prior_rho [n] fp32 (BF_PRIOR_GAUSSIAN only; prior_mu may alias mu)
+ * eps_in             NULL, or [S*n] fp32 injected eps (parity tests)
+ * w_out              [S][w_stride] of w_dtype (BF_F32 / BF_BF16); may be NULL (log-probs only)
+ * logq_out, logp_out [S] fp32; `accumulate` != 0 adds to the existing values
+ *                    (weight then bias, linear.py:99-102)
+ * workspace          bf_sample_kl_workspace_bytes(n, S) bytes, zero-filled once
+ * ------------------------------------------------------------------------- */
+int64_t bf_sample_kl_workspace_bytes(int64_t n, int32_t S);
+int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
+                     const float* prior_rho, float pi, float sigma1, float sigma2, int64_t n, int32_t S,
+                     uint64_t seed, uint32_t step, uint32_t tensor_id, const float* eps_in, void* w_out,
+                     int32_t w_dtype, int64_t w_stride, float* logq_out, float* logp_out, int32_t accumulate,
+                     void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Backward of the above (stand-alone form): eps is RECOMPUTED from the seed.
+ * Replaces what autograd does for gaussian.py:101 (mu + eps*softplus(rho)) and,
+ * when g_logq/g_logp are given, for the two log_prob reductions (the KL
+ * gradient the reference drops through `.data =`, linear.py:99-102).
+ *
+ *   grad_mu[i]  (+)= sum_s grad_w[s][i] + g_logp[s] * dlogp/dw(w_s[i])
+ *   grad_rho[i] (+)= sigmoid(rho[i]) * sum_s ( grad_w[s][i]*eps_s[i]
+ *                        - g_logq[s]/sigma_i + g_logp[s]*dlogp/dw(w_s[i])*eps_s[i] )
+ *
+ * grad_w   [S][gw_stride] of gw_dtype, or NULL (KL terms only)
+ * g_logq, g_logp  device [S] fp32 upstream gradients of the two scalars, or NULL
+ *                 (both NULL == the reference's behaviour: no KL gradient)
+ * grad_mu  [n] fp32 or NULL (frozen mu);  grad_rho [n] fp32
+ * ------------------------------------------------------------------------- */
+int bf_sample_kl_bwd(const void* grad_w, int32_t gw_dtype, int64_t gw_stride, const float* mu, const float* rho,
+                     int32_t prior_kind, const float* prior_mu, const float* prior_rho, float pi, float sigma1,
+                     float sigma2, const float* g_logq, const float* g_logp, int64_t n, int32_t S, uint64_t seed,
+                     uint32_t step, uint32_t tensor_id, const float* eps_in, float* grad_mu, float* grad_rho,
+                     int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * S-sample Linear contractions.  Replaces F.linear(input, weight, bias)
+ * (linear.py:104) and its autograd (mm / addmm backward), batched over the
+ * S Monte-Carlo weight samples.
+ *
+ * dtype == BF_F32 : fp32 FFMA kernels (reference-precision "parity" mode)
+ * dtype == BF_BF16: tcgen05 / TMEM / TMA kernels, bf16 operands, fp32 accumulate
+ *
+ *   fwd   : y[s]  = x[s] (M,K) . w[s]^T (K,N) + bias[s]      y of y_dtype
+ *   dgrad : dx[s] = gy[s] (M,N) . w[s] (N,K)                 dx of dx_dtype
+ *   wgrad : dw[s] = gy[s]^T (N,M) . x[s] (M,K)               dw fp32 [S,N,K]
+ *
+ * bias  [S,N] fp32 or NULL.  All matrices row-major and densely packed.
+ * ------------------------------------------------------------------------- */
+int bf_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t S, int64_t M, int64_t N,
+                  int64_t K, int32_t dtype, int32_t y_dtype, void* stream);
+int bf_linear_dgrad(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N, int64_t K,
+                    int32_t dtype, int32_t dx_dtype, void* stream);
+int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t M, int64_t N, int64_t K,
+                    int32_t dtype, void* stream);
+
+/* wgrad with the variational backward fused into its epilogue: the S weight
+ * gradients never reach HBM.  Per output tile and sample the accumulator is
+ * combined with a regenerated eps tile:
+ *   grad_mu  (+)= sum_s dw[s]                     (skipped when grad_mu == NULL)
+ *   grad_rho (+)= sigmoid(rho) * sum_s dw[s]*eps_s  (+ the KL terms as in bf_sample_kl_bwd)
+ * mu/rho/prior/eps arguments as in bf_sample_kl_bwd, n == N*K.
+ * workspace: bf_linear_wgrad_fused_workspace_bytes(N, K) bytes, zero-filled once
+ * (per-output-tile turn counters, self-resetting). dtype must be BF_BF16. */
+int64_t bf_linear_wgrad_fused_workspace_bytes(int64_t N, int64_t K);
+int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K, int32_t dtype,
+                          const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
+                          const float* prior_rho, float pi, float sigma1, float sigma2, const float* g_logq,
+                          const float* g_logp, uint64_t seed, uint32_t step, uint32_t tensor_id,
+                          const float* eps_in, float* grad_mu, float* grad_rho, int32_t accumulate,
+                          void* workspace, void* stream);
+
+/* column sums of gy over the M rows of each sample: db[s][j] = sum_m gy[s][m][j]
+ * (the bias gradient F.linear's autograd produces).  db fp32 [S,N]. */
+int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYEFORMERS_B200_H_ */

@@ -1,0 +1,183 @@
+"""CPU: the host-side mirror of the reference API (conversion, MOPED, state_dict
+names, RNG consumption) against the golden fixtures, and the C-ABI boundary
+(library loads, exports every symbol include/*.h declares).  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+import bayeformers_b200 as bf
+import bayeformers_b200.nn as bnn
+from bayeformers_b200 import _lib
+
+
+class TinyMLP(torch.nn.Module):  # same architecture as tests/golden/make_golden.py
+    def __init__(self):
+        super().__init__()
+        self.body = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.ReLU(), torch.nn.Linear(16, 8, bias=False))
+        self.head = torch.nn.Linear(8, 3)
+
+    def forward(self, x):
+        return self.head(torch.relu(self.body(x)))
+
+
+@pytest.mark.parametrize("tag,kw", [("plain", {}), ("moped", {"delta": 0.05, "freeze": True}),
+                                    ("moped_unfrozen", {"delta": 0.1})])
+def test_to_bayesian_matches_reference(tag, kw):
+    g = load_golden("to_bayesian.npz")
+    torch.manual_seed(21)
+    m = TinyMLP()
+    for k in g[f"{tag}_freq_keys"]:
+        assert torch.equal(m.state_dict()[str(k)], torch.from_numpy(g[f"{tag}_freq::{k}"]))
+    torch.manual_seed(22)
+    bm = bf.to_bayesian(m, **kw)
+    sd = bm.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g[f"{tag}_keys"]]          # names AND order
+    for k, v in sd.items():
+        ref = torch.from_numpy(g[f"{tag}::{k}"])
+        assert v.shape == ref.shape, k
+        assert torch.equal(v, ref), k                                        # bit-exact mu / rho / priors
+    flags = [f"{n}={int(p.requires_grad)}" for n, p in bm.named_parameters()]
+    assert flags == [str(s) for s in g[f"{tag}_requires_grad"]]
+    # same consumption of torch's global generator as the reference (quirk Q12)
+    assert np.array_equal(torch.get_rng_state().numpy()[:64], g[f"{tag}_rng_after"])
+    assert isinstance(bm, bnn.Model) and len(bm.bayesian_children) == 3
+
+
+def test_to_bayesian_is_not_in_place_and_exact_class_only():
+    class MyLinear(torch.nn.Linear):
+        pass
+
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), MyLinear(4, 4))
+    bm = bf.to_bayesian(net, delta=0.05)
+    assert isinstance(net[0], torch.nn.Linear) and not isinstance(net[0], bnn.Linear)
+    assert isinstance(bm.model[0], bnn.Linear)
+    assert isinstance(bm.model[1], MyLinear)  # subclasses are skipped (quirk Q7)
+    # root module is never replaced
+    root = bf.to_bayesian(torch.nn.Linear(3, 3))
+    assert isinstance(root.model, torch.nn.Linear)
+    with pytest.warns(UserWarning):
+        root.log_prior()
+
+
+def test_moped_rule_and_aliasing():
+    g = load_golden("moped.npz")
+    w = torch.from_numpy(g["w"])
+    for delta in (0.05, 0.1, 0.01):
+        lin = torch.nn.Linear(4, w.shape[0])
+        lin.weight.data = w.clone()
+        lin.bias.data = w[:, 0].clone()
+        layer = bnn.Linear.from_frequentist(lin, delta=delta, freeze=True)
+        assert np.array_equal(layer.weight.rho.detach().numpy().view(np.uint32), g[f"rho_w_{delta}"].view(np.uint32))
+        assert np.array_equal(layer.bias.rho.detach().numpy().view(np.uint32), g[f"rho_b_{delta}"].view(np.uint32))
+        assert torch.equal(layer.weight.mu.data, w)
+        # posterior mu, prior mu and the source weight share storage (quirk Q5)
+        assert layer.weight.mu.data_ptr() == lin.weight.data_ptr() == layer.weight_prior.mu.data_ptr()
+        assert torch.all(layer.weight_prior.rho == 1)
+        assert not layer.weight.mu.requires_grad and layer.weight.rho.requires_grad
+
+
+def test_delta_none_discards_pretrained_weights():
+    lin = torch.nn.Linear(6, 5)
+    torch.manual_seed(3)
+    layer = bnn.Linear.from_frequentist(lin)
+    assert layer.weight_prior is bnn.DEFAULT_SCALED_GAUSSIAN_MIXTURE
+    assert float(layer.weight.mu.abs().max()) <= 0.2 and float(layer.weight.rho.max()) <= -4
+    assert not torch.equal(layer.weight.mu.data, lin.weight.data)
+
+
+def test_api_surface_matches_reference_exports():
+    for name in ["Linear", "Model", "NoneParameter", "Parameter", "DEFAULT_SCALED_GAUSSIAN_MIXTURE", "Gaussian",
+                 "ScaledGaussianMixture", "DEFAULT_UNIFORM", "Initialization", "Uniform", "TORCH2BAYE",
+                 "Embedding", "LayerNorm"]:
+        assert hasattr(bnn, name), name
+    assert bnn.TORCH2BAYE == {torch.nn.Linear: bnn.Linear}
+    p = bnn.DEFAULT_SCALED_GAUSSIAN_MIXTURE
+    assert float(p.pi) == 0.5 and float(p.sigma1) == 1.0 and float(p.sigma2) == np.float32(np.exp(-6))
+    assert bnn.DEFAULT_UNIFORM.mu_range == (-0.2, 0.2) and bnn.DEFAULT_UNIFORM.rho_range == (-5, -4)
+    assert bnn.NoneParameter().sample() is None and bnn.NoneParameter().log_prob(torch.zeros(1)) == 0.0
+    with pytest.raises(NotImplementedError):
+        bnn.Parameter().sample()
+    with pytest.raises(NotImplementedError):
+        bnn.Model()(1)
+    g = bnn.Gaussian(torch.Size((3, 2)))
+    assert g.mu.dtype == torch.float32 and set(dict(g.named_parameters())) == {"mu", "rho", "zero", "one"}
+
+
+def test_compat_log_prob_matches_reference_values():
+    # the torch-op compatibility surface (not the hot path) on the KAT fixtures
+    g = load_golden("gaussian.npz")
+    q = bnn.Gaussian(torch.Size((3,)))
+    q.mu.data, q.rho.data = torch.from_numpy(g["kat_mu"]), torch.from_numpy(g["kat_rho"])
+    assert torch.equal(q.sigma, torch.from_numpy(g["kat_sigma"]))
+    assert torch.equal(q.log_prob(torch.from_numpy(g["kat_w"])).detach(), torch.from_numpy(g["kat_logq"]))
+    m = load_golden("mixture.npz")
+    assert torch.equal(bnn.DEFAULT_SCALED_GAUSSIAN_MIXTURE.log_prob(torch.from_numpy(m["rnd_w"])).detach(),
+                       torch.from_numpy(m["rnd_logp"]))
+    assert bnn.DEFAULT_SCALED_GAUSSIAN_MIXTURE.sample() == 0.0
+
+
+def test_all_layers_registry_converts_embedding_and_layernorm():
+    net = torch.nn.Sequential(torch.nn.Embedding(11, 8, padding_idx=0), torch.nn.LayerNorm(8), torch.nn.Linear(8, 2))
+    bm = bf.to_bayesian(net, delta=0.05, freeze=True, layers=bnn.TORCH2BAYE_ALL)
+    kinds = [type(m).__name__ for m in bm.bayesian_children]
+    assert kinds == ["Embedding", "LayerNorm", "Linear"]
+    ln = bm.model[1]
+    # gamma = 1 -> sigma = delta (to ~1e-5); beta = 0 -> rho = 0 (sigma = ln 2)
+    assert torch.allclose(ln.weight.sigma, torch.full((8,), 0.05), rtol=1e-4)
+    assert torch.all(ln.bias.rho == 0)
+    assert bm.model[0].padding_idx == 0
+
+
+def test_cpu_forward_fails_loudly():
+    layer = bnn.Linear(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.randn(2, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        bnn.Gaussian(torch.Size((4,))).sample()
+
+
+def test_mc_samples_context_and_stream_ids():
+    assert bf.runtime.get_mc_samples() == 1
+    with bf.mc_samples(4):
+        assert bf.runtime.get_mc_samples() == 4
+        with bf.mc_samples(2):
+            assert bf.runtime.get_mc_samples() == 2
+        assert bf.runtime.get_mc_samples() == 4
+    assert bf.runtime.get_mc_samples() == 1
+    a, b = bnn.Gaussian(torch.Size((2,))), bnn.Gaussian(torch.Size((2,)))
+    assert a.tensor_id != b.tensor_id
+    bf.manual_seed(77)
+    s0, s1 = a.next_stream(), a.next_stream()
+    assert (s0.seed, s0.tensor_id) == (77, a.tensor_id) and s1.step == s0.step + 1
+
+    class Fixed:
+        def sample(self, size):
+            return torch.ones(size)
+
+    a.normal = Fixed()
+    assert a.next_stream(3).eps.shape == (3, 2)
+
+
+# ---------------------------------------------------------------- C-ABI boundary
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bayeformers_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from bayeformers_b200.build import build
+    build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bayeformers_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
+    assert _lib.load().bf_abi_version() == 1
