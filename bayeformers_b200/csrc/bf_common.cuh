@@ -74,13 +74,25 @@ __device__ __forceinline__ uint4 bf_philox4x32_10(uint32_t c0, uint32_t c1, uint
     return make_uint4(c0, c1, c2, c3);
 }
 
+// MUFU-only sqrt / reciprocal (no IEEE slow-path branches in the hot loops)
+__device__ __forceinline__ float bf_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float bf_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // two uint32 -> two N(0,1).  u in (0,1], angle in (-pi, pi] so the MUFU
 // sin/cos approximations stay in their accurate range.
 __device__ __forceinline__ void bf_box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // a*2^-32 + 2^-33
     const float f = fmaf((float)b, 4.6566128730773926e-10f, 2.3283064365386963e-10f - 1.0f);  // b*2^-31 + 2^-32 - 1
     // -2 ln u = -2 ln2 * log2 u
-    const float radius = sqrtf(-1.3862943611198906f * __log2f(u));
+    const float radius = bf_sqrt_approx(-1.3862943611198906f * __log2f(u));
     float s, c;
     __sincosf(3.14159265358979323846f * f, &s, &c);
     n0 = radius * c;

@@ -71,6 +71,7 @@ struct Params {
     int accumulate;
     int prior_kind;
     uint32_t k0, k1, step, tensor_id;
+    float prior_const_ipv;  // 1/sigma_p^2 for a Gaussian prior with constant sigma (prior_rho == NULL)
     BfMixture mix;
 };
 
@@ -426,13 +427,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                             float pm[4] = {0, 0, 0, 0}, ipv[4] = {0, 0, 0, 0};
                             if (p.prior_kind == BF_PRIOR_GAUSSIAN) {
                                 const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.prior_mu + flat));
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.prior_rho + flat));
                                 pm[0] = a4.x, pm[1] = a4.y, pm[2] = a4.z, pm[3] = a4.w;
-                                const float pr[4] = {b4.x, b4.y, b4.z, b4.w};
+                                if (p.prior_rho != nullptr) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.prior_rho + flat));
+                                    const float pr[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float sp = bf_softplus(pr[e]);
-                                    ipv[e] = 1.0f / (sp * sp);
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float sp = bf_softplus(pr[e]);
+                                        ipv[e] = 1.0f / (sp * sp);
+                                    }
+                                } else {
+                                    ipv[0] = ipv[1] = ipv[2] = ipv[3] = p.prior_const_ipv;
                                 }
                             }
 #pragma unroll
@@ -632,6 +637,7 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     p.prior_kind = prior_kind;
     p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
     p.mix = bf_make_mixture(pi, sigma1, sigma2);
+    p.prior_const_ipv = 1.0f / (sigma1 * sigma1);
     const bool kl = (g_logq != nullptr) || (g_logp != nullptr);
     const int64_t n_items = tiles * S * splits;
     if (kl) return launch<true, true, EPI_VARGRAD, true>(ma, mb, p, n_items, st);

@@ -79,7 +79,7 @@ extern "C" int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, i
     BF_CHECK_ARG(dtype == BF_BF16, "fused wgrad exists for the bf16 tensor-core path only");
     const bool kl = g_logq || g_logp;
     BF_CHECK_ARG(!kl || mu, "KL gradient needs mu");
-    BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || (prior_mu && prior_rho), "gaussian prior needs arrays");
+    BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || prior_mu, "gaussian prior needs prior_mu");
     return bf_linear_wgrad_fused_bf16(gy, x, S, M, N, K, mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2,
                                       g_logq, g_logp, seed, step, tensor_id, eps_in, grad_mu, grad_rho, accumulate,
                                       reinterpret_cast<int*>(workspace), reinterpret_cast<cudaStream_t>(stream));

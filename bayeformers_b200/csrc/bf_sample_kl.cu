@@ -34,7 +34,9 @@ struct SampleKlParams {
     int64_t w_stride;
     int s0;  // first sample of this launch
     int accumulate;
+    int64_t q0;  // first quad handled by this launch (generic kernel: tail of a vectorised run)
     uint32_t k0, k1, step, tensor_id;
+    float prior_const_c, prior_const_iv;  // Gaussian prior with constant sigma (prior_rho == NULL)
     BfMixture mix;
 };
 
@@ -77,97 +79,11 @@ __device__ __forceinline__ float element_terms(float mu, float sigma, float neg_
     return w;
 }
 
-template <int PRIOR, typename WT, int SC, bool VEC>
-__global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlParams p) {
-    float q_acc[SC], p_acc[SC];
-#pragma unroll
-    for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
-
-    WT* const w_out = reinterpret_cast<WT*>(p.w_out);
-    const int64_t n = p.n;
-    const int64_t nquad = (n + 3) >> 2;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-
-    for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
-        const int64_t i0 = q << 2;
-        const bool full = VEC && (i0 + 4 <= n);
-        float mu[4], rho[4], pmu[4], prho[4];
-        if (full) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
-            mu[0] = a.x, mu[1] = a.y, mu[2] = a.z, mu[3] = a.w;
-            rho[0] = b.x, rho[1] = b.y, rho[2] = b.z, rho[3] = b.w;
-            if (PRIOR == BF_PRIOR_GAUSSIAN) {
-                const float4 c = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
-                const float4 d = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
-                pmu[0] = c.x, pmu[1] = c.y, pmu[2] = c.z, pmu[3] = c.w;
-                prho[0] = d.x, prho[1] = d.y, prho[2] = d.z, prho[3] = d.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = i0 + j < n;
-                mu[j] = ok ? __ldg(p.mu + i0 + j) : 0.0f;
-                rho[j] = ok ? __ldg(p.rho + i0 + j) : 0.0f;
-                if (PRIOR == BF_PRIOR_GAUSSIAN) {
-                    pmu[j] = ok ? __ldg(p.prior_mu + i0 + j) : 0.0f;
-                    prho[j] = ok ? __ldg(p.prior_rho + i0 + j) : 0.0f;
-                }
-            }
-        }
-        // per-element quantities shared by the S samples
-        float sigma[4], qc[4], qiv[4], pc[4], piv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            sigma[j] = bf_softplus(rho[j]);
-            qc[j] = -BF_LOG_SQRT_2PI - logf(sigma[j]);
-            qiv[j] = 1.0f / (2.0f * __fmul_rn(sigma[j], sigma[j]));
-            if (PRIOR == BF_PRIOR_GAUSSIAN) {
-                const float sp = bf_softplus(prho[j]);
-                pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
-                piv[j] = 1.0f / (2.0f * __fmul_rn(sp, sp));
-            } else {
-                pc[j] = piv[j] = 0.0f;
-                pmu[j] = 0.0f;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < SC; ++s) {
-            const int sg = p.s0 + s;
-            float e[4];
-            if (p.eps_in != nullptr) {
-                const float* ep = p.eps_in + (int64_t)sg * n + i0;
-                if (full) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(ep));
-                    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) e[j] = (i0 + j < n) ? __ldg(ep + j) : 0.0f;
-                }
-            } else {
-                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
-                e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
-            }
-            float w[4];
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j], p.mix,
-                                                q_acc[s], p_acc[s]);
-                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * p.w_stride + i0, w[0], w[1], w[2], w[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (i0 + j < n) {
-                        w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j],
-                                                    p.mix, q_acc[s], p_acc[s]);
-                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * p.w_stride + i0 + j, w[j]);
-                    }
-                }
-            }
-        }
-    }
-
+// deterministic reduction tail shared by both forward kernels: per-thread values ->
+// warp shuffle tree -> block tree -> per-block partial -> fixed-order final pass
+// by the last block to arrive (no float atomics)
+template <int SC>
+__device__ __forceinline__ void block_finish(const SampleKlParams& p, float (&q_acc)[SC], float (&p_acc)[SC]) {
     // ---- block reduction of the 2*SC accumulators -------------------------
     __shared__ float red[2 * kMaxSC][kThreads / 32];
     __shared__ bool is_last;
@@ -213,6 +129,198 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlP
     if (threadIdx.x == 0) *p.counter = 0u;  // self-reset for the next launch
 }
 
+template <int PRIOR, typename WT, int SC, bool VEC>
+__global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlParams p) {
+    float q_acc[SC], p_acc[SC];
+#pragma unroll
+    for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
+
+    WT* const w_out = reinterpret_cast<WT*>(p.w_out);
+    const int64_t n = p.n;
+    const int64_t nquad = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    for (int64_t q = p.q0 + (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += stride) {
+        const int64_t i0 = q << 2;
+        const bool full = VEC && (i0 + 4 <= n);
+        float mu[4], rho[4], pmu[4], prho[4];
+        if (full) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+            mu[0] = a.x, mu[1] = a.y, mu[2] = a.z, mu[3] = a.w;
+            rho[0] = b.x, rho[1] = b.y, rho[2] = b.z, rho[3] = b.w;
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
+                pmu[0] = c.x, pmu[1] = c.y, pmu[2] = c.z, pmu[3] = c.w;
+                prho[0] = prho[1] = prho[2] = prho[3] = 0.0f;
+                if (p.prior_rho != nullptr) {
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
+                    prho[0] = d.x, prho[1] = d.y, prho[2] = d.z, prho[3] = d.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = i0 + j < n;
+                mu[j] = ok ? __ldg(p.mu + i0 + j) : 0.0f;
+                rho[j] = ok ? __ldg(p.rho + i0 + j) : 0.0f;
+                if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                    pmu[j] = ok ? __ldg(p.prior_mu + i0 + j) : 0.0f;
+                    prho[j] = (ok && p.prior_rho) ? __ldg(p.prior_rho + i0 + j) : 0.0f;
+                }
+            }
+        }
+        // per-element quantities shared by the S samples
+        float sigma[4], qc[4], qiv[4], pc[4], piv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sigma[j] = bf_softplus(rho[j]);
+            qc[j] = -BF_LOG_SQRT_2PI - logf(sigma[j]);
+            qiv[j] = bf_rcp_approx(2.0f * __fmul_rn(sigma[j], sigma[j]));
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                if (p.prior_rho != nullptr) {
+                    const float sp = bf_softplus(prho[j]);
+                    pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
+                    piv[j] = bf_rcp_approx(2.0f * __fmul_rn(sp, sp));
+                } else {
+                    pc[j] = p.prior_const_c, piv[j] = p.prior_const_iv;
+                }
+            } else {
+                pc[j] = piv[j] = 0.0f;
+                pmu[j] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            const int sg = p.s0 + s;
+            float e[4];
+            if (p.eps_in != nullptr) {
+                const float* ep = p.eps_in + (int64_t)sg * n + i0;
+                if (full) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(ep));
+                    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = (i0 + j < n) ? __ldg(ep + j) : 0.0f;
+                }
+            } else {
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
+                e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+            }
+            float w[4];
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j], p.mix,
+                                                q_acc[s], p_acc[s]);
+                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * p.w_stride + i0, w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i0 + j < n) {
+                        w[j] = element_terms<PRIOR>(mu[j], sigma[j], qc[j], qiv[j], e[j], pmu[j], pc[j], piv[j],
+                                                    p.mix, q_acc[s], p_acc[s]);
+                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * p.w_stride + i0 + j, w[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    block_finish<SC>(p, q_acc, p_acc);
+}
+
+// ---------------------------------------------------------------------------
+// fast path: 16-byte aligned pointers, full quads only (the tail, if any, goes
+// through the generic kernel above with q0 = n/4).  No bounds checks, injected
+// eps resolved at compile time, two independent quads in flight per thread.
+// ---------------------------------------------------------------------------
+struct QuadShared {  // per-element quantities shared by the S samples of a quad
+    float mu[4], sigma[4], qc[4], qiv[4], pmu[4], pc[4], piv[4];
+};
+
+template <int PRIOR>
+__device__ __forceinline__ void load_quad(const SampleKlParams& p, int64_t i0, QuadShared& Q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+    Q.mu[0] = a.x, Q.mu[1] = a.y, Q.mu[2] = a.z, Q.mu[3] = a.w;
+    const float rho[4] = {b.x, b.y, b.z, b.w};
+    float prho[4] = {0.f, 0.f, 0.f, 0.f};
+    if (PRIOR == BF_PRIOR_GAUSSIAN) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
+        Q.pmu[0] = c.x, Q.pmu[1] = c.y, Q.pmu[2] = c.z, Q.pmu[3] = c.w;
+        if (p.prior_rho != nullptr) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
+            prho[0] = d.x, prho[1] = d.y, prho[2] = d.z, prho[3] = d.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        Q.sigma[j] = bf_softplus(rho[j]);
+        Q.qc[j] = -BF_LOG_SQRT_2PI - logf(Q.sigma[j]);
+        Q.qiv[j] = bf_rcp_approx(2.0f * __fmul_rn(Q.sigma[j], Q.sigma[j]));
+        if (PRIOR == BF_PRIOR_GAUSSIAN) {
+            if (p.prior_rho != nullptr) {
+                const float sp = bf_softplus(prho[j]);
+                Q.pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
+                Q.piv[j] = bf_rcp_approx(2.0f * __fmul_rn(sp, sp));
+            } else {  // constant prior sigma (MOPED: rho_p == 1 everywhere), precomputed on the host
+                Q.pc[j] = p.prior_const_c;
+                Q.piv[j] = p.prior_const_iv;
+            }
+        } else {
+            Q.pmu[j] = Q.pc[j] = Q.piv[j] = 0.0f;
+        }
+    }
+}
+
+template <int PRIOR, typename WT, int SC, bool HAS_EPS, int QPT>
+__global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const SampleKlParams p) {
+    float q_acc[SC], p_acc[SC];
+#pragma unroll
+    for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
+    WT* const w_out = reinterpret_cast<WT*>(p.w_out);
+    const int64_t n = p.n;
+    const int64_t nquad = n >> 2;  // full quads only
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+
+    for (int64_t qb = (int64_t)blockIdx.x * kThreads + threadIdx.x; qb < nquad; qb += stride * QPT) {
+        QuadShared Q[QPT];
+        bool live[QPT];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int64_t q = qb + u * stride;
+            live[u] = q < nquad;
+            if (live[u]) load_quad<PRIOR>(p, q << 2, Q[u]);
+        }
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            const int sg = p.s0 + s;
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) {
+                if (!live[u]) continue;
+                const int64_t q = qb + u * stride;
+                const int64_t i0 = q << 2;
+                float e[4];
+                if (HAS_EPS) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)sg * n + i0));
+                    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+                } else {
+                    const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
+                    e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+                }
+                float w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = element_terms<PRIOR>(Q[u].mu[j], Q[u].sigma[j], Q[u].qc[j], Q[u].qiv[j], e[j], Q[u].pmu[j],
+                                                Q[u].pc[j], Q[u].piv[j], p.mix, q_acc[s], p_acc[s]);
+                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * p.w_stride + i0, w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+    block_finish<SC>(p, q_acc, p_acc);
+}
+
 // ---------------------------------------------------------------------------
 // stand-alone backward
 // ---------------------------------------------------------------------------
@@ -232,6 +340,7 @@ struct SampleKlBwdParams {
     int S;
     int accumulate;
     uint32_t k0, k1, step, tensor_id;
+    float prior_const_ipv;  // 1/sigma_p^2 when the Gaussian prior has a constant sigma (prior_rho == NULL)
     BfMixture mix;
 };
 
@@ -289,13 +398,18 @@ __global__ void __launch_bounds__(kThreads) sample_kl_bwd_kernel(const SampleKlB
 #pragma unroll
             for (int j = 0; j < 4; ++j) sigma[j] = bf_softplus(rho[j]);
             if (PRIOR == BF_PRIOR_GAUSSIAN) {
-                float prho[4];
                 ld4(p.prior_mu, i0, n, full, pmu);
-                ld4(p.prior_rho, i0, n, full, prho);
+                if (p.prior_rho != nullptr) {
+                    float prho[4];
+                    ld4(p.prior_rho, i0, n, full, prho);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float sp = bf_softplus(prho[j]);
-                    inv_pvar[j] = 1.0f / (sp * sp);
+                    for (int j = 0; j < 4; ++j) {
+                        const float sp = bf_softplus(prho[j]);
+                        inv_pvar[j] = 1.0f / (sp * sp);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) inv_pvar[j] = p.prior_const_ipv;
                 }
             }
         }
@@ -360,27 +474,36 @@ inline int grid_for(int64_t nquad, int blocks_per_sm) {
 
 constexpr int kFwdBlocksPerSm = 8;
 
-template <int PRIOR, typename WT, bool VEC>
-int launch_fwd_sc(const SampleKlParams& p, int sc, int grid, cudaStream_t st) {
+// ---- generic (scalar, bounds-checked) kernel: one sample per launch --------------
+template <int PRIOR>
+void launch_generic(const SampleKlParams& p, int grid, int w_dtype, cudaStream_t st) {
+    if (w_dtype == BF_BF16)
+        sample_kl_fwd_kernel<PRIOR, __nv_bfloat16, 1, false><<<grid, kThreads, 0, st>>>(p);
+    else
+        sample_kl_fwd_kernel<PRIOR, float, 1, false><<<grid, kThreads, 0, st>>>(p);
+}
+
+// ---- fast kernel: SC samples per launch, QPT quads in flight per thread ----------
+template <int PRIOR, typename WT, bool HAS_EPS>
+int launch_fast_sc(const SampleKlParams& p, int sc, int grid, cudaStream_t st) {
     switch (sc) {
-        case 1: sample_kl_fwd_kernel<PRIOR, WT, 1, VEC><<<grid, kThreads, 0, st>>>(p); break;
-        case 2: sample_kl_fwd_kernel<PRIOR, WT, 2, VEC><<<grid, kThreads, 0, st>>>(p); break;
-        case 4: sample_kl_fwd_kernel<PRIOR, WT, 4, VEC><<<grid, kThreads, 0, st>>>(p); break;
-        case 8: sample_kl_fwd_kernel<PRIOR, WT, 8, VEC><<<grid, kThreads, 0, st>>>(p); break;
+        case 1: sample_kl_fwd_fast_kernel<PRIOR, WT, 1, HAS_EPS, 2><<<grid, kThreads, 0, st>>>(p); break;
+        case 2: sample_kl_fwd_fast_kernel<PRIOR, WT, 2, HAS_EPS, 2><<<grid, kThreads, 0, st>>>(p); break;
+        case 4: sample_kl_fwd_fast_kernel<PRIOR, WT, 4, HAS_EPS, 1><<<grid, kThreads, 0, st>>>(p); break;
+        case 8: sample_kl_fwd_fast_kernel<PRIOR, WT, 8, HAS_EPS, 1><<<grid, kThreads, 0, st>>>(p); break;
         default: return BF_ERR_BAD_ARG;
     }
     return 0;
 }
 
-template <int PRIOR, typename WT>
-int launch_fwd_vec(const SampleKlParams& p, int sc, int grid, bool vec, cudaStream_t st) {
-    return vec ? launch_fwd_sc<PRIOR, WT, true>(p, sc, grid, st) : launch_fwd_sc<PRIOR, WT, false>(p, sc, grid, st);
-}
-
 template <int PRIOR>
-int launch_fwd_dtype(const SampleKlParams& p, int sc, int grid, bool vec, int w_dtype, cudaStream_t st) {
-    return w_dtype == BF_BF16 ? launch_fwd_vec<PRIOR, __nv_bfloat16>(p, sc, grid, vec, st)
-                              : launch_fwd_vec<PRIOR, float>(p, sc, grid, vec, st);
+int launch_fast(const SampleKlParams& p, int sc, int grid, int w_dtype, cudaStream_t st) {
+    const bool eps = p.eps_in != nullptr;
+    if (w_dtype == BF_BF16)
+        return eps ? launch_fast_sc<PRIOR, __nv_bfloat16, true>(p, sc, grid, st)
+                   : launch_fast_sc<PRIOR, __nv_bfloat16, false>(p, sc, grid, st);
+    return eps ? launch_fast_sc<PRIOR, float, true>(p, sc, grid, st)
+               : launch_fast_sc<PRIOR, float, false>(p, sc, grid, st);
 }
 
 inline bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
@@ -400,11 +523,12 @@ extern "C" int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior
                                 uint64_t seed, uint32_t step, uint32_t tensor_id, const float* eps_in, void* w_out,
                                 int32_t w_dtype, int64_t w_stride, float* logq_out, float* logp_out,
                                 int32_t accumulate, void* workspace, void* stream) {
-    BF_CHECK_ARG(mu && rho && logq_out && logp_out && workspace, "null pointer");
+    BF_CHECK_ARG(logq_out && logp_out && workspace, "null pointer");
     BF_CHECK_ARG(n >= 0 && S >= 1, "bad n or S");
+    BF_CHECK_ARG(n == 0 || (mu && rho), "null mu/rho");
     BF_CHECK_ARG(prior_kind == BF_PRIOR_MIXTURE || prior_kind == BF_PRIOR_GAUSSIAN || prior_kind == BF_PRIOR_NONE,
                  "bad prior_kind");
-    BF_CHECK_ARG(prior_kind != BF_PRIOR_GAUSSIAN || (prior_mu && prior_rho), "gaussian prior needs prior_mu/prior_rho");
+    BF_CHECK_ARG(prior_kind != BF_PRIOR_GAUSSIAN || n == 0 || prior_mu, "gaussian prior needs prior_mu");
     BF_CHECK_ARG(w_dtype == BF_F32 || w_dtype == BF_BF16, "bad w_dtype");
     BF_CHECK_ARG(w_out == nullptr || w_stride >= n, "w_stride < n");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -419,31 +543,50 @@ extern "C" int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior
     p.step = step, p.tensor_id = tensor_id;
     p.mix = bf_make_mixture(pi, sigma1, sigma2);
 
-    const int64_t nquad = (n + 3) >> 2;
-    const int grid = grid_for(nquad, kFwdBlocksPerSm);
+    if (prior_kind == BF_PRIOR_GAUSSIAN && prior_rho == nullptr) {
+        // constant prior sigma passed in `sigma1` (see header): fold its terms on the host
+        p.prior_const_c = -BF_LOG_SQRT_2PI - logf(sigma1);
+        p.prior_const_iv = 1.0f / (2.0f * sigma1 * sigma1);
+    }
     const int esz = w_dtype == BF_BF16 ? 2 : 4;
     bool vec = aligned16(mu) && aligned16(rho) && (eps_in == nullptr || (aligned16(eps_in) && n % 4 == 0));
-    if (prior_kind == BF_PRIOR_GAUSSIAN) vec = vec && aligned16(prior_mu) && aligned16(prior_rho);
+    if (prior_kind == BF_PRIOR_GAUSSIAN) vec = vec && aligned16(prior_mu) && (!prior_rho || aligned16(prior_rho));
     if (w_out != nullptr) vec = vec && aligned16(w_out) && ((w_stride * esz) % 16 == 0);
+    const int64_t nq_fast = vec ? (n >> 2) : 0;  // quads the fast kernel takes; the rest is the generic tail
 
-    for (int s0 = 0; s0 < S;) {
-        int sc = 1;
-        while (sc * 2 <= kMaxSC && s0 + sc * 2 <= S) sc *= 2;
-        p.s0 = s0;
-        int rc;
-        if (prior_kind == BF_PRIOR_MIXTURE)
-            rc = launch_fwd_dtype<BF_PRIOR_MIXTURE>(p, sc, grid, vec, w_dtype, st);
-        else if (prior_kind == BF_PRIOR_GAUSSIAN)
-            rc = launch_fwd_dtype<BF_PRIOR_GAUSSIAN>(p, sc, grid, vec, w_dtype, st);
-        else
-            rc = launch_fwd_dtype<BF_PRIOR_NONE>(p, sc, grid, vec, w_dtype, st);
-        if (rc) {
-            bf_set_error("bf_sample_kl_fwd: bad sample chunk");
-            return rc;
+#define BF_BY_PRIOR(CALL)                                                        \
+    (prior_kind == BF_PRIOR_MIXTURE ? CALL<BF_PRIOR_MIXTURE> :                    \
+     prior_kind == BF_PRIOR_GAUSSIAN ? CALL<BF_PRIOR_GAUSSIAN> : CALL<BF_PRIOR_NONE>)
+
+    if (nq_fast > 0) {
+        const int grid = grid_for(nq_fast, kFwdBlocksPerSm);
+        for (int s0 = 0; s0 < S;) {
+            int sc = 1;
+            while (sc * 2 <= kMaxSC && s0 + sc * 2 <= S) sc *= 2;
+            p.s0 = s0, p.q0 = 0, p.accumulate = accumulate;
+            int rc = prior_kind == BF_PRIOR_MIXTURE    ? launch_fast<BF_PRIOR_MIXTURE>(p, sc, grid, w_dtype, st)
+                     : prior_kind == BF_PRIOR_GAUSSIAN ? launch_fast<BF_PRIOR_GAUSSIAN>(p, sc, grid, w_dtype, st)
+                                                       : launch_fast<BF_PRIOR_NONE>(p, sc, grid, w_dtype, st);
+            if (rc) {
+                bf_set_error("bf_sample_kl_fwd: bad sample chunk");
+                return rc;
+            }
+            BF_LAUNCH_OK();
+            s0 += sc;
         }
-        BF_LAUNCH_OK();
-        s0 += sc;
     }
+    if ((nq_fast << 2) < n || n == 0) {
+        const int64_t tail_quads = ((n + 3) >> 2) - nq_fast;
+        const int grid = grid_for(tail_quads, kFwdBlocksPerSm);
+        for (int s0 = 0; s0 < S; ++s0) {
+            p.s0 = s0, p.q0 = nq_fast, p.accumulate = (nq_fast > 0) ? 1 : accumulate;
+            if (prior_kind == BF_PRIOR_MIXTURE) launch_generic<BF_PRIOR_MIXTURE>(p, grid, w_dtype, st);
+            else if (prior_kind == BF_PRIOR_GAUSSIAN) launch_generic<BF_PRIOR_GAUSSIAN>(p, grid, w_dtype, st);
+            else launch_generic<BF_PRIOR_NONE>(p, grid, w_dtype, st);
+            BF_LAUNCH_OK();
+        }
+    }
+#undef BF_BY_PRIOR
     return 0;
 }
 
@@ -458,7 +601,7 @@ extern "C" int bf_sample_kl_bwd(const void* grad_w, int32_t gw_dtype, int64_t gw
     BF_CHECK_ARG(gw_dtype == BF_F32 || gw_dtype == BF_BF16, "bad gw_dtype");
     const bool kl = (g_logq != nullptr) || (g_logp != nullptr);
     BF_CHECK_ARG(!kl || mu, "KL gradient needs mu");
-    BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || (prior_mu && prior_rho), "gaussian prior needs arrays");
+    BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || prior_mu, "gaussian prior needs prior_mu");
     BF_CHECK_ARG(grad_w || kl, "nothing to do");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -469,11 +612,12 @@ extern "C" int bf_sample_kl_bwd(const void* grad_w, int32_t gw_dtype, int64_t gw
     p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32);
     p.step = step, p.tensor_id = tensor_id;
     p.mix = bf_make_mixture(pi, sigma1, sigma2);
+    p.prior_const_ipv = 1.0f / (sigma1 * sigma1);
     const int grid = grid_for((n + 3) >> 2, 8);
 
     bool vec = aligned16(rho) && aligned16(grad_rho) && (!grad_mu || aligned16(grad_mu)) &&
                (!eps_in || (aligned16(eps_in) && n % 4 == 0));
-    if (kl) vec = vec && aligned16(mu) && (prior_kind != BF_PRIOR_GAUSSIAN || (aligned16(prior_mu) && aligned16(prior_rho)));
+    if (kl) vec = vec && aligned16(mu) && (prior_kind != BF_PRIOR_GAUSSIAN || (aligned16(prior_mu) && (!prior_rho || aligned16(prior_rho))));
     if (grad_w) vec = vec && ((reinterpret_cast<uintptr_t>(grad_w) & 15u) == 0) &&
                       ((gw_stride * (gw_dtype == BF_BF16 ? 2 : 4)) % 16 == 0);
 #define BF_BWD(PRIOR, GT, KLF)                                                       \

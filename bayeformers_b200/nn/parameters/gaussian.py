@@ -72,7 +72,19 @@ class Gaussian(Parameter):
         return spec
 
     def prior_spec(self) -> ops.PriorSpec:
-        """This distribution used as a prior over another tensor (MOPED)."""
+        """This distribution used as a prior over another tensor (MOPED).  When
+        rho is one constant (MOPED sets it to 1 everywhere, linear.py:149) the
+        kernels take sigma_p as a scalar instead of reading the array; the check
+        is cached per (storage, version), i.e. one device sync per layer."""
+        key = (self.rho.data_ptr(), self.rho._version, self.rho.device)
+        if getattr(self, "_const_key", None) != key:
+            flat = self.rho.detach().reshape(-1)
+            self._const_sigma = None
+            if flat.numel() > 0 and bool((flat == flat[0]).all()):
+                self._const_sigma = float(F.softplus(flat[0]))
+            self._const_key = key
+        if self._const_sigma is not None:
+            return ops.PriorSpec(kind=BF_PRIOR_GAUSSIAN, sigma1=self._const_sigma, mu=self.mu, rho=None)
         return ops.PriorSpec(kind=BF_PRIOR_GAUSSIAN, mu=self.mu, rho=self.rho)
 
     def sample(self, mc_samples: Optional[int] = None) -> Tensor:

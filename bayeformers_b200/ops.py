@@ -16,6 +16,53 @@ from ._lib import BF_BF16, BF_F32, BF_PRIOR_GAUSSIAN, BF_PRIOR_MIXTURE, BF_PRIOR
 
 _workspaces: Dict[Tuple, torch.Tensor] = {}
 
+# ---- instrumentation (bench.py): kernel-launch counter and optional per-call CUDA-event timing
+stats = {"launches": 0}
+_timing = {"on": False, "records": []}
+
+
+def enable_kernel_timing(flag: bool) -> None:
+    """Bracket every contraction / sample+KL call with CUDA events recorded on
+    the launching stream; `kernel_timing_summary()` turns them into durations."""
+    _timing["on"] = bool(flag)
+    _timing["records"] = []
+
+
+def _timed(name: str, work: float, dev, fn):
+    """Run fn() (which launches on the current stream), counting and optionally timing it."""
+    if not _timing["on"]:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream(dev)
+    e0.record(stream)
+    out = fn()
+    e1.record(stream)
+    _timing["records"].append((name, work, e0, e1))
+    return out
+
+
+def kernel_timing_summary():
+    """{name: {calls, ms, work}} -- call after torch.cuda.synchronize()."""
+    out = {}
+    for name, work, e0, e1 in _timing["records"]:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "work": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+    return out
+
+
+def _fwd_launches(n: int, S: int, aligned: bool) -> int:
+    k, s = 0, S
+    if aligned and n >= 4:
+        while s > 0:  # chunks of 8/4/2/1 samples
+            c = 8 if s >= 8 else (4 if s >= 4 else (2 if s >= 2 else 1))
+            s -= c
+            k += 1
+    if not aligned or n % 4 != 0 or n == 0:
+        k += S
+    return k
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
@@ -91,10 +138,14 @@ def sample_kl_forward(mu, rho, prior: PriorSpec, stream: StreamSpec, S: int, w_d
     ws = _workspace("sample_kl", dev, lib.bf_sample_kl_workspace_bytes(n, S))
     pmu = prior.mu if prior.kind == BF_PRIOR_GAUSSIAN else None
     prho = prior.rho if prior.kind == BF_PRIOR_GAUSSIAN else None
-    rc = lib.bf_sample_kl_fwd(_ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho), prior.pi, prior.sigma1,
-                              prior.sigma2, n, S, stream.seed, stream.step, stream.tensor_id, _ptr(eps), _ptr(w),
-                              _dt(w_dtype), n, _ptr(logq), _ptr(logp), int(accumulate), _ptr(ws), _stream(dev))
+    nbytes = n * (8 + (0 if pmu is None else 4) + (0 if prho is None else 4) +
+                  (S * (2 if w_dtype == torch.bfloat16 else 4) if want_w else 0)) + 8 * S
+    rc = _timed("sample_kl_fwd", float(nbytes), dev, lambda: lib.bf_sample_kl_fwd(
+        _ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho), prior.pi, prior.sigma1,
+        prior.sigma2, n, S, stream.seed, stream.step, stream.tensor_id, _ptr(eps), _ptr(w),
+        _dt(w_dtype), n, _ptr(logq), _ptr(logp), int(accumulate), _ptr(ws), _stream(dev)))
     _lib.check(rc, "bf_sample_kl_fwd")
+    stats["launches"] += _fwd_launches(n, S, mu.data_ptr() % 16 == 0 and rho.data_ptr() % 16 == 0)
     return w
 
 
@@ -116,10 +167,13 @@ def sample_kl_backward(grad_w, mu, rho, prior: PriorSpec, stream: StreamSpec, S:
         gw_dt = _dt(grad_w.dtype)
     pmu = prior.mu if prior.kind == BF_PRIOR_GAUSSIAN else None
     prho = prior.rho if prior.kind == BF_PRIOR_GAUSSIAN else None
-    rc = lib.bf_sample_kl_bwd(_ptr(grad_w), gw_dt, n, _ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho),
-                              prior.pi, prior.sigma1, prior.sigma2, _ptr(g_logq), _ptr(g_logp), n, S, stream.seed,
-                              stream.step, stream.tensor_id, _ptr(eps), _ptr(g_mu), _ptr(g_rho), 0, _stream(dev))
+    nbytes = n * ((0 if grad_w is None else S * grad_w.element_size()) + 8 + (4 if need_mu else 0))
+    rc = _timed("sample_kl_bwd", float(nbytes), dev, lambda: lib.bf_sample_kl_bwd(
+        _ptr(grad_w), gw_dt, n, _ptr(mu), _ptr(rho), prior.kind, _ptr(pmu), _ptr(prho),
+        prior.pi, prior.sigma1, prior.sigma2, _ptr(g_logq), _ptr(g_logp), n, S, stream.seed,
+        stream.step, stream.tensor_id, _ptr(eps), _ptr(g_mu), _ptr(g_rho), 0, _stream(dev)))
     _lib.check(rc, "bf_sample_kl_bwd")
+    stats["launches"] += 1
     return g_mu, g_rho
 
 
@@ -223,9 +277,10 @@ class BayesLinear(torch.autograd.Function):
         out_dtype = x.dtype if (use_tc and x.dtype in (torch.float32, torch.bfloat16)) else torch.float32
         y = torch.empty((S, M, N), dtype=out_dtype, device=dev)
         if M > 0:
-            rc = lib.bf_linear_fwd(_ptr(xg), _ptr(W), _ptr(b), _ptr(y), S, M, N, K, _dt(cdt), _dt(out_dtype),
-                                   _stream(dev))
+            rc = _timed("gemm_fwd_" + ("tc" if use_tc else "f32"), 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_fwd(
+                _ptr(xg), _ptr(W), _ptr(b), _ptr(y), S, M, N, K, _dt(cdt), _dt(out_dtype), _stream(dev)))
             _lib.check(rc, "bf_linear_fwd")
+            stats["launches"] += 1
         ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho)
         ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape))
         if not spec.kl_grad:
@@ -259,30 +314,38 @@ class BayesLinear(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 dx = torch.empty((S, M, K), dtype=dx_dtype, device=dev)
-                rc = lib.bf_linear_dgrad(_ptr(gyc), _ptr(W), _ptr(dx), S, M, N, K, _dt(cdt), _dt(dx_dtype), st)
+                rc = _timed("gemm_dgrad_" + ("tc" if use_tc else "f32"), 2.0 * S * M * N * K, dev,
+                            lambda: lib.bf_linear_dgrad(_ptr(gyc), _ptr(W), _ptr(dx), S, M, N, K, _dt(cdt),
+                                                        _dt(dx_dtype), st))
                 _lib.check(rc, "bf_linear_dgrad")
+                stats["launches"] += 1
                 g_x = dx.view(x_shape).to(x_dtype)
             if has_bias:
                 db = torch.empty((S, N), dtype=torch.float32, device=dev)
-                rc = lib.bf_bias_grad(_ptr(gyc), _dt(cdt), _ptr(db), S, M, N, st)
+                rc = _timed("bias_grad", float(S * M * N * gyc.element_size()), dev,
+                            lambda: lib.bf_bias_grad(_ptr(gyc), _dt(cdt), _ptr(db), S, M, N, st))
                 _lib.check(rc, "bf_bias_grad")
+                stats["launches"] += 1
             if use_tc:
                 g_wrho = torch.empty_like(w_rho, dtype=torch.float32)
                 g_wmu = torch.empty_like(w_rho, dtype=torch.float32) if need_wmu else None
                 eps = _eps_arg(spec.w_stream, S, N * K, dev)
                 ws = _workspace("wgrad_turn", dev, lib.bf_linear_wgrad_fused_workspace_bytes(N, K))
                 pk = w_prior.kind
-                rc = lib.bf_linear_wgrad_fused(
+                rc = _timed("gemm_wgrad_fused_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_wgrad_fused(
                     _ptr(gyc), _ptr(xg), S, M, N, K, BF_BF16, _ptr(w_mu), _ptr(w_rho), pk,
                     _ptr(wp_mu if pk == BF_PRIOR_GAUSSIAN else None),
                     _ptr(wp_rho if pk == BF_PRIOR_GAUSSIAN else None), w_prior.pi, w_prior.sigma1, w_prior.sigma2,
                     _ptr(glq), _ptr(glp), spec.w_stream.seed, spec.w_stream.step, spec.w_stream.tensor_id, _ptr(eps),
-                    _ptr(g_wmu), _ptr(g_wrho), 0, _ptr(ws), st)
+                    _ptr(g_wmu), _ptr(g_wrho), 0, _ptr(ws), st))
                 _lib.check(rc, "bf_linear_wgrad_fused")
+                stats["launches"] += 1
             else:
                 dW = torch.empty((S, N, K), dtype=torch.float32, device=dev)
-                rc = lib.bf_linear_wgrad(_ptr(gyc), _ptr(xg), _ptr(dW), S, M, N, K, BF_F32, st)
+                rc = _timed("gemm_wgrad_f32", 2.0 * S * M * N * K, dev,
+                            lambda: lib.bf_linear_wgrad(_ptr(gyc), _ptr(xg), _ptr(dW), S, M, N, K, BF_F32, st))
                 _lib.check(rc, "bf_linear_wgrad")
+                stats["launches"] += 1
                 g_wmu, g_wrho = sample_kl_backward(dW.view(S, -1), w_mu.detach(), w_rho.detach(), w_prior,
                                                    spec.w_stream, S, glq, glp, need_wmu)
         else:

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the variational-layer hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): Bayesian
+BERT-base sequence classification, `to_bayesian(delta=0.05, freeze=True)`, synthetic
+tokens of length 128, S=4 Monte-Carlo samples, training step = S-sample forward
++ ELBO loss + backward + grad-clip + AdamW (the pattern of
+/root/reference/examples/bert_glue.py:56-73,225-241).  One JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
+
+import torch  # noqa: E402
+
+METRIC = "bayes_bert_base_train_seqs_per_s"
+N_BATCHES = 1000  # the reference divides the KL term by len(train_loader) (bert_glue.py:235)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step (before the S-fold)")
+    ap.add_argument("--samples", type=int, default=4)
+    ap.add_argument("--seq", type=int, default=128)
+    ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--kl-grad", type=int, default=1)
+    ap.add_argument("--ref-batch", type=int, default=2, help="sequences per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs under ncu only: allow < 3 warm-up steps, skip the e2e and CPU legs (numbers invalid)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            p.update(json.load(open(f)))
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+def build_bert(layers: int = 0):
+    from transformers import BertConfig, BertForSequenceClassification
+
+    cfg = BertConfig(num_labels=2)
+    if layers:
+        cfg.num_hidden_layers = layers
+    torch.manual_seed(0)
+    model = BertForSequenceClassification(cfg)
+    with torch.no_grad():  # HF zero-inits biases; perturb so MOPED sees non-degenerate values
+        g = torch.Generator().manual_seed(1)
+        for n, p in model.named_parameters():
+            if n.endswith("bias"):
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+    return model, cfg
+
+
+def flops_per_seq_sample(cfg, T):
+    """fwd+bwd matmul flops of one sequence for ONE MC sample: 6*T*params_linear + attention."""
+    H, L, FF = cfg.hidden_size, cfg.num_hidden_layers, cfg.intermediate_size
+    lin = L * (4 * H * H + 2 * H * FF) + H * H + H * cfg.num_labels
+    return 3 * (2 * T * lin), 3 * (L * 4 * T * T * H)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_steps(args, steps: int, warmup: int):
+    """The reference's CPU path for this workload through the oracle port
+    (oracle/bayes_oracle.py: same torch-CPU operator sequence as
+    bayeformers/nn/layers/linear.py:83-104 inside the S-loop of
+    examples/bert_glue.py:56-73), on all host cores, on a bounded sample of
+    `--ref-batch` sequences per step.  Returns (seq_per_s, s_per_step, cores)."""
+    from oracle import bayes_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, cfg = build_bert(args.layers)
+    torch.manual_seed(2)
+    om = O.oracle_convert(model, delta=0.05, freeze=True).train()
+    B, T, S = args.ref_batch, args.seq, args.samples
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=g)
+    labels = torch.randint(0, 2, (B,), generator=g)
+    params = [p for p in om.parameters() if p.requires_grad]
+    optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8)
+
+    def step():  # same work as the GPU step: S-loop fwd, ELBO, bwd, clip, AdamW (bert_glue.py:230-241)
+        optim.zero_grad(set_to_none=True)
+        O.s_loop_step(om, lambda m: m(input_ids=ids).logits, labels, S, N_BATCHES)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        optim.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return B / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seqs, dt, cores = cpu_reference_steps(args, args.steps, args.warmup)
+    sample = (f"{args.ref_batch} sequences x S={args.samples} per step (bounded sample of the per-GPU batch), "
+              f"oracle port of the reference S-loop, torch CPU fp32, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": seqs, "unit": "seq/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": seqs, "unit": "seq/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": seqs, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "BERT-base to_bayesian(delta=0.05, freeze=True) GLUE-style classification, synthetic tokens, "
+                        "training step (S-sample fwd + ELBO + bwd + clip + AdamW)",
+            "seq_len": args.seq, "mc_samples": args.samples, "batch_per_gpu": args.batch,
+            "global_batch": args.batch * args.gpus, "gemm": args.gemm, "kl_grad": bool(args.kl_grad),
+            "parallelism": f"dp{args.gpus} (batch sharded, identical Philox weights per rank, NCCL grad all-reduce)",
+            "l2": "working set (0.7 GB sampled weights + activations) far exceeds the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    import bayeformers_b200 as bf
+    from bayeformers_b200 import ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    model, cfg = build_bert(args.layers)
+    bf.manual_seed(1234)
+    bm = bf.to_bayesian(model, delta=0.05, freeze=True, gemm_dtype=args.gemm, kl_grad=bool(args.kl_grad)).to(dev).train()
+    if world > 1:
+        parallel.broadcast_seed(0)
+    if args.gemm == "bf16":
+        # activations flow in bf16 from the embeddings on; variational masters (mu, rho) stay fp32
+        bm.model.bert.embeddings.register_forward_hook(lambda m, i, o: o.to(torch.bfloat16))
+    params = [p for p in bm.parameters() if p.requires_grad]
+    optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True)
+    sync = parallel.GradSync(bm)
+
+    B, T, S = args.batch, args.seq, args.samples
+    g = torch.Generator().manual_seed(100 + rank)
+    ids_host = torch.randint(0, cfg.vocab_size, (B, T), generator=g).pin_memory()
+    labels_host = torch.randint(0, 2, (B,), generator=g).pin_memory()
+    ids_dev, labels_dev = ids_host.to(dev), labels_host.to(dev)
+    out_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+
+    def step(ids, labels):
+        optim.zero_grad(set_to_none=True)
+        with bf.mc_samples(S):
+            logits = bm(input_ids=ids.repeat(S, 1)).logits
+        raw = logits.float().view(S, B, -1)
+        nll = torch.nn.functional.cross_entropy(raw.mean(0), labels)
+        lp, lq = bm.log_prior().mean(), bm.log_variational_posterior().mean()
+        loss = (lq - lp) / N_BATCHES + nll
+        loss.backward()
+        sync.finish()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        optim.step()
+        return loss, lp, lq
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_warm = args.warmup if args.profile else max(args.warmup, 3)
+    for _ in range(n_warm):
+        step(ids_dev, labels_dev)
+
+    # ---- timed region 1: inputs resident in HBM (value)
+    ops.enable_kernel_timing(True)
+    launches0 = ops.stats["launches"]
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(ids_dev, labels_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop() if clocks else None
+    launches = ops.stats["launches"] - launches0
+    kern = ops.kernel_timing_summary()
+    ops.enable_kernel_timing(False)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers (e2e)
+    barrier()
+    e0.record()
+    for _ in range(0 if args.profile else args.steps):
+        ids = ids_host.to(dev, non_blocking=True)
+        labels = labels_host.to(dev, non_blocking=True)
+        loss, lp, lq = step(ids, labels)
+        out_host.copy_(torch.stack([loss.detach(), lp.detach().float(), lq.detach().float()]), non_blocking=True)
+        torch.cuda.synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 1e-9) / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B / (ms / 1e3)
+    e2e = world * B / (ms_e2e / 1e3)
+    # ---- roofline of the dominant kernel family (tcgen05 contractions), from the CUDA-event brackets
+    gemm = {k: v for k, v in kern.items() if k.startswith("gemm_")}
+    g_ms = sum(v["ms"] for v in gemm.values())
+    g_flops = sum(v["work"] for v in gemm.values())
+    g_calls = sum(v["calls"] for v in gemm.values())
+    peak_tf = pk["bf16_tflops_sustained"]
+    ach_tf = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "tc::bayes_gemm_kernel (fwd + dgrad + fused wgrad, all layers)",
+                "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": None, "launches_per_step": g_calls / args.steps, "avg_launch_ms": g_ms / max(g_calls, 1),
+                "share_of_step": g_ms / args.steps / ms}
+    sk = kern.get("sample_kl_fwd")
+    roof_sk = None
+    if sk and sk["ms"] > 0:
+        gbs = sk["work"] / (sk["ms"] / 1e3) / 1e9
+        roof_sk = {"bound": "hbm", "kernel": "sample_kl_fwd_fast_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
+                   "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "share_of_step": sk["ms"] / args.steps / ms,
+                   "traffic": None}
+    lin_f, att_f = flops_per_seq_sample(cfg, T)
+    step_tf = (lin_f + att_f) * S * value / 1e12
+    kernels = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+                   "share": v["ms"] / args.steps / ms} for k, v in sorted(kern.items())}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
+        seqs, dt, cores = cpu_reference_steps(args, 2, 1)
+        cpu = {"value": seqs, "unit": "seq/s", "cores": cores, "kind": "port",
+               "sample": f"{args.ref_batch} sequences x S={args.samples}, 1 warm-up + 2 timed steps of the oracle port "
+                         f"of the reference S-loop ({dt:.2f} s/step), torch CPU fp32"}
+
+    line = {"metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args), "roofline": roofline, "roofline_sample_kl": roof_sk,
+            "step_model_tflops": step_tf, "step_frac_of_gemm_roofline": step_tf / peak_tf, "kernels": kernels,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "seq/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": ids_host.numel() * 8 + labels_host.numel() * 8, "d2h_bytes_per_step": 12},
+            "gpu_launches": launches, "clocks": clk,
+            "grad_allreduce_bytes_per_step": sync.bytes_last_step}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

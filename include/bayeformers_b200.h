@@ -78,7 +78,10 @@ int bf_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t step, uint32
  *                    logp[s] (+)= sum_i  log p(w_s[i])
  *
  * mu, rho            [n] fp32
- * prior_mu, prior_rho [n] fp32 (BF_PRIOR_GAUSSIAN only; prior_mu may alias mu)
+ * prior_mu, prior_rho [n] fp32 (BF_PRIOR_GAUSSIAN only; prior_mu may alias mu).
+ *                    prior_rho == NULL means a CONSTANT prior sigma, passed in `sigma1`
+ *                    (MOPED sets rho_p = 1 everywhere: linear.py:149 -> sigma_p = softplus(1));
+ *                    saves 4 B/element of reads and one softplus+log per element
  * eps_in             NULL, or [S*n] fp32 injected eps (parity tests)
  * w_out              [S][w_stride] of w_dtype (BF_F32 / BF_BF16); may be NULL (log-probs only)
  * logq_out, logp_out [S] fp32; `accumulate` != 0 adds to the existing values

@@ -1,0 +1,41 @@
+"""Short, fixed workload for `ncu --set full`: the fused sample+KL kernel at
+config-2 size and the three tcgen05 contractions at the BERT-base FFN shape."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from bayeformers_b200 import _lib, ops
+from bayeformers_b200._lib import BF_BF16, BF_PRIOR_GAUSSIAN, BF_PRIOR_MIXTURE
+import numpy as np
+
+lib = _lib.load()
+DEV = "cuda:0"
+st = torch.cuda.current_stream().cuda_stream
+n, S = 4096 * 4096, 4
+mu = torch.empty(n, device=DEV).uniform_(-0.2, 0.2)
+rho = torch.empty(n, device=DEV).uniform_(-5, -4)
+lq, lp = torch.empty(S, device=DEV), torch.empty(S, device=DEV)
+moped = ops.PriorSpec(BF_PRIOR_GAUSSIAN, sigma1=1.3132616, mu=mu, rho=None)
+mix = ops.PriorSpec(BF_PRIOR_MIXTURE, 0.5, 1.0, float(np.float32(np.exp(-6))))
+for _ in range(2):
+    ops.sample_kl_forward(mu, rho, moped, ops.StreamSpec(1, 2, 3), S, torch.bfloat16, lq, lp, False)
+    ops.sample_kl_forward(mu, rho, mix, ops.StreamSpec(1, 2, 3), 1, torch.float32, lq, lp, False)
+gw = torch.randn(S, n, device=DEV)
+ops.sample_kl_backward(gw, mu, rho, ops.PriorSpec(), ops.StreamSpec(1, 2, 3), S, None, None, False)
+del gw
+S, M, N, K = 4, 4096, 3072, 768
+x = torch.randn(S, M, K, device=DEV).bfloat16(); w = torch.randn(S, N, K, device=DEV).bfloat16()
+gy = torch.randn(S, M, N, device=DEV).bfloat16()
+y = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16); dx = torch.empty(S, M, K, device=DEV, dtype=torch.bfloat16)
+mu2 = torch.randn(N, K, device=DEV) * 0.02; rho2 = torch.full((N, K), -5.0, device=DEV)
+g_rho = torch.empty(N, K, device=DEV)
+ws = torch.zeros(lib.bf_linear_wgrad_fused_workspace_bytes(N, K), dtype=torch.uint8, device=DEV)
+for _ in range(2):
+    lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
+    lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
+    lib.bf_linear_wgrad_fused(gy.data_ptr(), x.data_ptr(), S, M, N, K, BF_BF16, mu2.data_ptr(), rho2.data_ptr(), 2, None, None,
+                              0.5, 1.0, 1.0, None, None, 7, 0, 1, None, None, g_rho.data_ptr(), 0, ws.data_ptr(), st)
+torch.cuda.synchronize()
+print("profile target done")

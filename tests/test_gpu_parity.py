@@ -468,13 +468,15 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
             ws.data_ptr(), st), "wgrad_fused")
 
     fused(0)
-    assert rel_err(g_rho.cpu().numpy(), want_rho.cpu().numpy()) < 2e-6
-    assert rel_err(g_mu.cpu().numpy(), want_mu.cpu().numpy()) < 2e-6
+    # both sides are fp32 sums of the same products in different association orders
+    # (the fused kernel splits the reduction over up to 8 CTAs): 1e-5 is fp32 noise here
+    assert rel_err(g_rho.cpu().numpy(), want_rho.cpu().numpy()) < 1e-5
+    assert rel_err(g_mu.cpu().numpy(), want_mu.cpu().numpy()) < 1e-5
     first = g_rho.clone()
     fused(0)
     assert torch.equal(first, g_rho), "turn-ordered accumulation must be run-to-run deterministic"
     fused(1)  # accumulate into existing gradients
-    assert rel_err(g_rho.cpu().numpy(), 2 * want_rho.cpu().numpy()) < 2e-6
+    assert rel_err(g_rho.cpu().numpy(), 2 * want_rho.cpu().numpy()) < 1e-5
     assert int(ws.view(torch.int32).abs().sum()) == 0  # turn counters reset themselves
 
 
