@@ -22,7 +22,31 @@ from .nn.parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE
 from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
 from .runtime import manual_seed, mc_samples, set_gemm_dtype, set_kl_grad
 
-__all__ = ["to_bayesian", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype", "set_kl_grad"]
+__all__ = ["to_bayesian", "cast_frequentist_", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
+           "set_kl_grad"]
+
+
+def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:
+    """Cast, in place, the floating-point parameters and buffers of every module
+    that is NOT part of a Bayesian layer (embeddings, LayerNorm, ... of the host
+    model) to `dtype`, so activations flow in bf16 when `gemm_dtype="bf16"`.
+    The variational masters (mu, rho, priors) always stay fp32 (quirk Q4)."""
+    from .nn.layers.common import BayesianLayer
+
+    def walk(mod: tnn.Module) -> None:
+        if isinstance(mod, BayesianLayer):
+            return
+        for p in mod._parameters.values():
+            if p is not None and p.is_floating_point():
+                p.data = p.data.to(dtype)
+        for name, b in mod._buffers.items():
+            if b is not None and b.is_floating_point():
+                mod._buffers[name] = b.to(dtype)
+        for child in mod.children():
+            walk(child)
+
+    walk(model)
+    return model
 
 
 def to_bayesian(model: tnn.Module, initialization: Optional[Initialization] = DEFAULT_UNIFORM,

@@ -413,18 +413,19 @@ __global__ void __launch_bounds__(kThreads) sample_kl_bwd_kernel(const SampleKlB
                 }
             }
         }
+        // software prefetch: the grad_w quad of sample s+1 is in flight while sample s is processed
+        float g_next[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gw != nullptr) ld4(gw, i0, n, full, g_next);
         for (int s = 0; s < p.S; ++s) {
             float e[4], g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = g_next[j];
+            if (gw != nullptr && s + 1 < p.S) ld4(gw + (int64_t)(s + 1) * p.gw_stride, i0, n, full, g_next);
             if (p.eps_in != nullptr) {
                 ld4(p.eps_in + (int64_t)s * n, i0, n, full, e);
             } else {
                 const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)s, p.tensor_id, p.step, p.k0, p.k1);
                 e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
-            }
-            if (gw != nullptr) {
-                ld4(gw + (int64_t)s * p.gw_stride, i0, n, full, g);
-            } else {
-                g[0] = g[1] = g[2] = g[3] = 0.0f;
             }
             float glq = 0.0f, glp = 0.0f;
             if (KL) {
@@ -653,4 +654,15 @@ extern "C" int bf_philox_normal(float* out, int64_t n, uint64_t seed, uint32_t s
         out, n, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step, tensor_id, sample_id);
     BF_LAUNCH_OK();
     return 0;
+}
+
+// KL-only variational backward, accumulated on top of existing gradients (used by the
+// fused weight-gradient path, whose tensor-core epilogue handles the data term only).
+int bf_sample_kl_bwd_impl_kl_only(const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
+                                  const float* prior_rho, float pi, float sigma1, float sigma2, const float* g_logq,
+                                  const float* g_logp, int64_t n, int32_t S, uint64_t seed, uint32_t step,
+                                  uint32_t tensor_id, const float* eps_in, float* grad_mu, float* grad_rho,
+                                  cudaStream_t st) {
+    return bf_sample_kl_bwd(nullptr, BF_F32, n, mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2, g_logq,
+                            g_logp, n, S, seed, step, tensor_id, eps_in, grad_mu, grad_rho, 1, st);
 }

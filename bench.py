@@ -212,8 +212,9 @@ def run_ours(args):
     if world > 1:
         parallel.broadcast_seed(0)
     if args.gemm == "bf16":
-        # activations flow in bf16 from the embeddings on; variational masters (mu, rho) stay fp32
-        bm.model.bert.embeddings.register_forward_hook(lambda m, i, o: o.to(torch.bfloat16))
+        # activations flow in bf16 (embeddings / LayerNorm of the host model cast to bf16);
+        # the variational masters (mu, rho, priors) stay fp32
+        bf.cast_frequentist_(bm, torch.bfloat16)
     params = [p for p in bm.parameters() if p.requires_grad]
     optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True)
     sync = parallel.GradSync(bm)

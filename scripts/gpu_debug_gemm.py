@@ -64,23 +64,30 @@ if __name__ == "__main__":
     run(1, 128, 256, 256)
     run(2, 256, 512, 128)
     run(1, 200, 136, 72)
-    # quick timing of the BERT FFN shape
-    S, M, N, K = 4, 8192, 3072, 768
-    x = torch.randn(S, M, K, device=DEV).bfloat16(); w = torch.randn(S, N, K, device=DEV).bfloat16()
-    y = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16)
-    for _ in range(3):
-        lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"fwd S={S} M={M} N={N} K={K}: {ms:.3f} ms  {2*S*M*N*K/ms/1e9:.1f} TFLOP/s")
-    ref = torch.bmm(x, w.transpose(1, 2))
-    e0.record()
-    for _ in range(10):
-        torch.bmm(x, w.transpose(1, 2))
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"cuBLAS bmm same shape: {ms:.3f} ms  {2*S*M*N*K/ms/1e9:.1f} TFLOP/s")
+    # timing of the BERT-base shapes (S=4, B=32 -> M=4096) against cuBLAS bmm on the same bf16 operands
+    def t_ms(fn, it=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(it):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / it
+
+    for (S, M, N, K) in [(4, 4096, 768, 768), (4, 4096, 3072, 768), (4, 4096, 768, 3072), (4, 16384, 3072, 768), (4, 1024, 768, 768)]:
+        x = torch.randn(S, M, K, device=DEV).bfloat16(); w = torch.randn(S, N, K, device=DEV).bfloat16()
+        gy = torch.randn(S, M, N, device=DEV).bfloat16(); b = torch.randn(S, N, device=DEV)
+        y = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16); dx = torch.empty(S, M, K, device=DEV, dtype=torch.bfloat16)
+        rho = torch.full((N, K), -5.0, device=DEV); g_rho = torch.empty(N, K, device=DEV)
+        ws = torch.zeros(lib.bf_linear_wgrad_fused_workspace_bytes(N, K), dtype=torch.uint8, device=DEV)
+        fl = 2 * S * M * N * K / 1e9
+        r = {}
+        r["fwd"] = t_ms(lambda: lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st))
+        r["dgrad"] = t_ms(lambda: lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st))
+        r["wgrad_fused"] = t_ms(lambda: lib.bf_linear_wgrad_fused(gy.data_ptr(), x.data_ptr(), S, M, N, K, BF_BF16, None, rho.data_ptr(), 2, None, None,
+                                                                  0.5, 1.0, 1.0, None, None, 7, 0, 1, None, None, g_rho.data_ptr(), 0, ws.data_ptr(), st))
+        r["cublas_fwd"] = t_ms(lambda: torch.baddbmm(b[:, None, :].bfloat16(), x, w.transpose(1, 2)))
+        r["cublas_dgrad"] = t_ms(lambda: torch.bmm(gy, w))
+        r["cublas_wgrad"] = t_ms(lambda: torch.bmm(gy.transpose(1, 2), x))
+        print(f"S={S} M={M} N={N} K={K}: " + "  ".join(f"{k} {v*1e3:.0f}us {fl/v:.0f}TF" for k, v in r.items()), flush=True)

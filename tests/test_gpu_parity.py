@@ -357,9 +357,16 @@ def test_tiny_bert_s_loop_and_folded_match_reference(mode):
     loss = (lq_s.mean() - lp_s.mean()) / n_batches + nll
     assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     loss.backward()
+    scale = max(float(np.abs(g[f"g_b_rho{i}"]).max()) for i in range(len(layers)))
     for i, l in enumerate(layers):
         assert rel_err(l.weight.rho.grad.cpu().numpy(), g[f"g_w_rho{i}"]) < 2e-4, i
-        assert rel_err(l.bias.rho.grad.cpu().numpy(), g[f"g_b_rho{i}"]) < 2e-4, i
+        want_b = g[f"g_b_rho{i}"]
+        if float(np.abs(want_b).max()) < 1e-9 * scale:
+            # key-projection biases: softmax is shift invariant, the true gradient is 0 and
+            # both sides hold rounding noise (~1e-17)
+            assert float(l.bias.rho.grad.abs().max()) < 1e-7 * scale, i
+        else:
+            assert rel_err(l.bias.rho.grad.cpu().numpy(), want_b) < 2e-4, i
         assert l.weight.mu.grad is None
 
 
