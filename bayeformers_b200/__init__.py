@@ -20,10 +20,11 @@ from .nn.model import Model
 from .nn.parameters.base import Parameter
 from .nn.parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE
 from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
-from .runtime import manual_seed, mc_samples, set_gemm_dtype, set_kl_grad
+from .runtime import (advance_step, disable_device_step, enable_device_step, manual_seed, mc_samples, set_gemm_dtype,
+                      set_kl_grad)
 
 __all__ = ["to_bayesian", "cast_frequentist_", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
-           "set_kl_grad"]
+           "set_kl_grad", "enable_device_step", "disable_device_step", "advance_step"]
 
 
 def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:

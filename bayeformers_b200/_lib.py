@@ -21,6 +21,7 @@ SIGNATURES = {
     "bf_abi_version": (c_int32, []),
     "bf_last_error": (c_char_p, []),
     "bf_device_is_sm100": (c_int32, []),
+    "bf_set_step_counter": (c_int32, [c_void_p]),
     "bf_philox_normal": (c_int32, [c_void_p, c_int64, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p]),
     "bf_sample_kl_workspace_bytes": (c_int64, [c_int64, c_int32]),
     "bf_sample_kl_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
@@ -40,7 +41,8 @@ SIGNATURES = {
                                         c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                         c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
                                         c_int32, c_void_p, c_void_p]),
-    "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "bf_bias_grad_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

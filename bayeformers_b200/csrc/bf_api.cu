@@ -19,6 +19,16 @@ int bf_num_sms() {
     return cached[dev];
 }
 
+namespace {
+const uint32_t* g_step_counter = nullptr;
+}
+const uint32_t* bf_step_counter() { return g_step_counter; }
+
+extern "C" int bf_set_step_counter(const uint32_t* device_counter) {
+    g_step_counter = device_counter;
+    return 0;
+}
+
 extern "C" int bf_abi_version(void) { return BF_ABI_VERSION; }
 
 extern "C" const char* bf_last_error(void) { return g_last_error.c_str(); }

@@ -42,6 +42,8 @@ void bf_set_error(const std::string& msg);
     } while (0)
 
 int bf_num_sms();
+// device-resident step counter (CUDA-graph replays must not redraw the same eps): see bf_set_step_counter
+const uint32_t* bf_step_counter();
 
 // ---------------------------------------------------------------------------
 // constants

@@ -112,34 +112,84 @@ int launch_gemm(const GemmParams& p, int64_t S, cudaStream_t st) {
 }
 
 // ---- bias gradient: db[s][j] = sum_m gy[s][m][j] ---------------------------
+// Two deterministic stages in one launch: every block reduces a slab of rows for 64 columns
+// into a partial; the last block to finish a (sample, column-block) adds the partials in
+// slab order (self-resetting counter, no float atomics).
 constexpr int kColsPerBlock = 64;
 constexpr int kBiasThreads = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const T* __restrict__ gy, float* __restrict__ db,
-                                                                 int64_t M, int64_t N) {
-    const int s = blockIdx.y;
+                                                                 float* __restrict__ partial,
+                                                                 unsigned int* __restrict__ counters, int64_t M,
+                                                                 int64_t N, int64_t rows_per_slab) {
+    const int s = blockIdx.y, slab = blockIdx.z, n_slabs = gridDim.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c0 = (int64_t)blockIdx.x * kColsPerBlock + lane * 2;
     const T* base = gy + (int64_t)s * M * N;
+    const int64_t m_lo = (int64_t)slab * rows_per_slab;
+    const int64_t m_hi = m_lo + rows_per_slab < M ? m_lo + rows_per_slab : M;
     float a0 = 0.0f, a1 = 0.0f;
     const bool ok0 = c0 < N, ok1 = c0 + 1 < N;
-    for (int64_t m = warp; m < M; m += kBiasThreads / 32) {
+    int64_t m = m_lo + warp;
+    for (; m + 3 * (kBiasThreads / 32) < m_hi; m += 4 * (kBiasThreads / 32)) {  // 4 rows in flight per warp
+        float v0[4], v1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T* row = base + (m + u * (kBiasThreads / 32)) * N + c0;
+            v0[u] = ok0 ? bf_ld_as_float(row) : 0.0f;
+            v1[u] = ok1 ? bf_ld_as_float(row + 1) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a0 += v0[u], a1 += v1[u];
+    }
+    for (; m < m_hi; m += kBiasThreads / 32) {
         const T* row = base + m * N + c0;
         if (ok0) a0 += bf_ld_as_float(row);
         if (ok1) a1 += bf_ld_as_float(row + 1);
     }
     __shared__ float red[kBiasThreads / 32][kColsPerBlock];
+    __shared__ bool is_last;
     red[warp][lane * 2] = a0;
     red[warp][lane * 2 + 1] = a1;
     __syncthreads();
+    const int64_t cb = blockIdx.x;
+    const int64_t n_cb = gridDim.x;
     if (threadIdx.x < kColsPerBlock) {
         float t = 0.0f;
 #pragma unroll
         for (int w = 0; w < kBiasThreads / 32; ++w) t += red[w][threadIdx.x];
-        const int64_t c = (int64_t)blockIdx.x * kColsPerBlock + threadIdx.x;
+        partial[(((int64_t)s * n_cb + cb) * n_slabs + slab) * kColsPerBlock + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(counters + s * n_cb + cb, 1u);
+        is_last = (done == (unsigned int)n_slabs - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < kColsPerBlock) {
+        const volatile float* pp = partial + ((int64_t)s * n_cb + cb) * n_slabs * kColsPerBlock + threadIdx.x;
+        float t = 0.0f;
+        for (int k = 0; k < n_slabs; ++k) t += pp[(int64_t)k * kColsPerBlock];
+        const int64_t c = cb * kColsPerBlock + threadIdx.x;
         if (c < N) db[(int64_t)s * N + c] = t;
     }
+    if (threadIdx.x == 0) counters[s * n_cb + cb] = 0u;
+}
+
+inline void bias_grid(int64_t S, int64_t M, int64_t N, int& n_cb, int& n_slabs, int64_t& rows_per_slab) {
+    n_cb = (int)((N + kColsPerBlock - 1) / kColsPerBlock);
+    const int64_t target = (int64_t)bf_num_sms() * 4;
+    int64_t slabs = target / (S * n_cb);
+    const int64_t max_slabs = (M + 63) / 64;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    if (slabs > 65535) slabs = 65535;
+    rows_per_slab = (M + slabs - 1) / slabs;
+    n_slabs = (int)((M + rows_per_slab - 1) / rows_per_slab);
 }
 
 }  // namespace
@@ -177,17 +227,34 @@ int bf_linear_wgrad_f32(const float* gy, const float* x, float* dw, int64_t S, i
     return launch_gemm(p, S, st);
 }
 
+extern "C" int64_t bf_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N) {
+    int n_cb, n_slabs;
+    int64_t rps;
+    bias_grid(S < 1 ? 1 : S, M < 1 ? 1 : M, N < 1 ? 1 : N, n_cb, n_slabs, rps);
+    // [counters: S*n_cb uint32, padded to 256 B][partials: S*n_cb*n_slabs*64 floats]
+    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
+    return cnt + S * n_cb * (int64_t)n_slabs * kColsPerBlock * 4;
+}
+
 extern "C" int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N,
-                            void* stream) {
-    BF_CHECK_ARG(gy && db, "null pointer");
+                            void* workspace, void* stream) {
+    BF_CHECK_ARG(gy && db && workspace, "null pointer");
     BF_CHECK_ARG(gy_dtype == BF_F32 || gy_dtype == BF_BF16, "bad dtype");
     if (S == 0 || N == 0) return 0;
-    dim3 grid((unsigned)((N + kColsPerBlock - 1) / kColsPerBlock), (unsigned)S);
+    int n_cb, n_slabs;
+    int64_t rps;
+    bias_grid(S, M < 1 ? 1 : M, N, n_cb, n_slabs, rps);
+    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + cnt);
+    dim3 grid((unsigned)n_cb, (unsigned)S, (unsigned)n_slabs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (gy_dtype == BF_BF16)
-        bias_grad_kernel<__nv_bfloat16><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gy), db, M, N);
+        bias_grad_kernel<__nv_bfloat16><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gy), db,
+                                                                        partial, counters, M, N, rps);
     else
-        bias_grad_kernel<float><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const float*>(gy), db, M, N);
+        bias_grad_kernel<float><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const float*>(gy), db, partial,
+                                                                counters, M, N, rps);
     BF_LAUNCH_OK();
     return 0;
 }

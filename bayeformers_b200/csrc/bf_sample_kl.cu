@@ -36,6 +36,7 @@ struct SampleKlParams {
     int accumulate;
     int64_t q0;  // first quad handled by this launch (generic kernel: tail of a vectorised run)
     uint32_t k0, k1, step, tensor_id;
+    const uint32_t* step_ptr;  // optional device-resident offset added to `step`
     float prior_const_c, prior_const_iv;  // Gaussian prior with constant sigma (prior_rho == NULL)
     BfMixture mix;
 };
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlP
     for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
 
     WT* const w_out = reinterpret_cast<WT*>(p.w_out);
+    const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
     const int64_t n = p.n;
     const int64_t nquad = (n + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlP
                     for (int j = 0; j < 4; ++j) e[j] = (i0 + j < n) ? __ldg(ep + j) : 0.0f;
                 }
             } else {
-                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, step, p.k0, p.k1);
                 e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
             }
             float w[4];
@@ -239,20 +241,28 @@ struct QuadShared {  // per-element quantities shared by the S samples of a quad
     float mu[4], sigma[4], qc[4], qiv[4], pmu[4], pc[4], piv[4];
 };
 
+struct RawQuad {  // the raw 16-byte loads of one quad, kept in flight across the compute of the previous quad
+    float4 mu, rho, pmu, prho;
+};
+
 template <int PRIOR>
-__device__ __forceinline__ void load_quad(const SampleKlParams& p, int64_t i0, QuadShared& Q) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
-    Q.mu[0] = a.x, Q.mu[1] = a.y, Q.mu[2] = a.z, Q.mu[3] = a.w;
-    const float rho[4] = {b.x, b.y, b.z, b.w};
+__device__ __forceinline__ void load_raw(const SampleKlParams& p, int64_t i0, RawQuad& R) {
+    R.mu = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
+    R.rho = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+    if (PRIOR == BF_PRIOR_GAUSSIAN) {
+        R.pmu = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
+        if (p.prior_rho != nullptr) R.prho = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
+    }
+}
+
+template <int PRIOR>
+__device__ __forceinline__ void derive_quad(const SampleKlParams& p, const RawQuad& R, QuadShared& Q) {
+    Q.mu[0] = R.mu.x, Q.mu[1] = R.mu.y, Q.mu[2] = R.mu.z, Q.mu[3] = R.mu.w;
+    const float rho[4] = {R.rho.x, R.rho.y, R.rho.z, R.rho.w};
     float prho[4] = {0.f, 0.f, 0.f, 0.f};
     if (PRIOR == BF_PRIOR_GAUSSIAN) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
-        Q.pmu[0] = c.x, Q.pmu[1] = c.y, Q.pmu[2] = c.z, Q.pmu[3] = c.w;
-        if (p.prior_rho != nullptr) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
-            prho[0] = d.x, prho[1] = d.y, prho[2] = d.z, prho[3] = d.w;
-        }
+        Q.pmu[0] = R.pmu.x, Q.pmu[1] = R.pmu.y, Q.pmu[2] = R.pmu.z, Q.pmu[3] = R.pmu.w;
+        if (p.prior_rho != nullptr) prho[0] = R.prho.x, prho[1] = R.prho.y, prho[2] = R.prho.z, prho[3] = R.prho.w;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -264,7 +274,7 @@ __device__ __forceinline__ void load_quad(const SampleKlParams& p, int64_t i0, Q
                 const float sp = bf_softplus(prho[j]);
                 Q.pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
                 Q.piv[j] = bf_rcp_approx(2.0f * __fmul_rn(sp, sp));
-            } else {  // constant prior sigma (MOPED: rho_p == 1 everywhere), precomputed on the host
+            } else {  // constant prior sigma (MOPED: rho_p == 1 everywhere), folded on the host
                 Q.pc[j] = p.prior_const_c;
                 Q.piv[j] = p.prior_const_iv;
             }
@@ -280,18 +290,30 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const Samp
 #pragma unroll
     for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
     WT* const w_out = reinterpret_cast<WT*>(p.w_out);
+    const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
     const int64_t n = p.n;
     const int64_t nquad = n >> 2;  // full quads only
     const int64_t stride = (int64_t)gridDim.x * kThreads;
 
-    for (int64_t qb = (int64_t)blockIdx.x * kThreads + threadIdx.x; qb < nquad; qb += stride * QPT) {
+    int64_t qb = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    RawQuad raw[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u)
+        if (qb + u * stride < nquad) load_raw<PRIOR>(p, (qb + u * stride) << 2, raw[u]);
+
+    for (; qb < nquad; qb += stride * QPT) {
         QuadShared Q[QPT];
         bool live[QPT];
 #pragma unroll
         for (int u = 0; u < QPT; ++u) {
-            const int64_t q = qb + u * stride;
-            live[u] = q < nquad;
-            if (live[u]) load_quad<PRIOR>(p, q << 2, Q[u]);
+            live[u] = qb + u * stride < nquad;
+            if (live[u]) derive_quad<PRIOR>(p, raw[u], Q[u]);
+        }
+        // prefetch the next iteration's parameters: their latency hides behind this iteration's Philox work
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            const int64_t qn = qb + (QPT + u) * stride;
+            if (qn < nquad) load_raw<PRIOR>(p, qn << 2, raw[u]);
         }
 #pragma unroll
         for (int s = 0; s < SC; ++s) {
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const Samp
                     const float4 v = __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)sg * n + i0));
                     e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
                 } else {
-                    const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, p.step, p.k0, p.k1);
+                    const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, p.tensor_id, step, p.k0, p.k1);
                     e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
                 }
                 float w[4];
@@ -340,6 +362,7 @@ struct SampleKlBwdParams {
     int S;
     int accumulate;
     uint32_t k0, k1, step, tensor_id;
+    const uint32_t* step_ptr;
     float prior_const_ipv;  // 1/sigma_p^2 when the Gaussian prior has a constant sigma (prior_rho == NULL)
     BfMixture mix;
 };
@@ -383,6 +406,7 @@ __device__ __forceinline__ void st4_acc(float* p, int64_t i0, int64_t n, bool fu
 template <int PRIOR, typename GT, bool KL, bool VEC>
 __global__ void __launch_bounds__(kThreads) sample_kl_bwd_kernel(const SampleKlBwdParams p) {
     const GT* const gw = reinterpret_cast<const GT*>(p.grad_w);
+    const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
     const int64_t n = p.n;
     const int64_t nquad = (n + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -424,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) sample_kl_bwd_kernel(const SampleKlB
             if (p.eps_in != nullptr) {
                 ld4(p.eps_in + (int64_t)s * n, i0, n, full, e);
             } else {
-                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)s, p.tensor_id, p.step, p.k0, p.k1);
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
                 e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
             }
             float glq = 0.0f, glp = 0.0f;
@@ -541,7 +565,7 @@ extern "C" int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior
     p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
     p.n = n, p.w_stride = w_stride, p.accumulate = accumulate;
     p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32);
-    p.step = step, p.tensor_id = tensor_id;
+    p.step = step, p.tensor_id = tensor_id, p.step_ptr = bf_step_counter();
     p.mix = bf_make_mixture(pi, sigma1, sigma2);
 
     if (prior_kind == BF_PRIOR_GAUSSIAN && prior_rho == nullptr) {
@@ -611,7 +635,7 @@ extern "C" int bf_sample_kl_bwd(const void* grad_w, int32_t gw_dtype, int64_t gw
     p.g_logq = g_logq, p.g_logp = g_logp, p.eps_in = eps_in, p.grad_mu = grad_mu, p.grad_rho = grad_rho;
     p.n = n, p.gw_stride = gw_stride, p.S = S, p.accumulate = accumulate;
     p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32);
-    p.step = step, p.tensor_id = tensor_id;
+    p.step = step, p.tensor_id = tensor_id, p.step_ptr = bf_step_counter();
     p.mix = bf_make_mixture(pi, sigma1, sigma2);
     p.prior_const_ipv = 1.0f / (sigma1 * sigma1);
     const int grid = grid_for((n + 3) >> 2, 8);

@@ -8,7 +8,7 @@
 //     grad_mu  = sum_s dW_s
 //     grad_rho = sigmoid(rho) * sum_s dW_s o eps_s           (eps_s regenerated from the Philox counter)
 //
-// Structure: 128 x 128 output tiles, 6-stage TMA ring, tcgen05.mma into a
+// Structure: 128 x 128 output tiles, 5-stage TMA ring, tcgen05.mma into a
 // double-buffered TMEM accumulator.  The other half of TMEM holds two running
 // sums per tile (sum_s dW_s o eps_s and sum_s dW_s): after each sample's
 // contraction the epilogue warps pull the accumulator (tcgen05.ld), generate
@@ -34,10 +34,10 @@ namespace wg {
 using namespace tc;
 
 constexpr int BM = 128, BN = 128;
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2;  // 16 KiB each
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_COLS = 32, EPI_STRIDE = 36, EPI_WARPS = 4;
+constexpr int EPI_COLS = 32, EPI_STRIDE = 36, EPI_WARPS = 8;  // 2 warps per TMEM lane quarter, 2 chunks each
 constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_STRIDE * 4;
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;  // [0,128) acc0 | [128,256) acc1 | [256,384) sum dW*eps | [384,512) sum dW
@@ -54,6 +54,7 @@ struct Params {
     int* turn;            // [i_tiles*j_tiles], zero-initialised, self-resetting
     int accumulate;
     uint32_t k0, k1, step, tensor_id;
+    const uint32_t* step_ptr;  // optional device-resident offset added to `step`
 };
 
 struct Item {
@@ -172,9 +173,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else {
         // ===================== epilogue warps =====================
+        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter
+        // split the 4 column chunks (two warps per scheduler hide each other's dependency stalls)
+        const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* const stage_w = epi_stage + q * 32 * EPI_STRIDE;
+        float* const stage_w = epi_stage + (warp - 2) * 32 * EPI_STRIDE;
         int iter = 0;
         for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
             const Item it = decode_item(p, L);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
+                for (int c = 2 * half; c < min(n_chunks, 2 * half + 2); ++c) {
                     uint32_t a[32], sr[32], sm[32];
                     tmem_ld_32x32(lane_base + (uint32_t)(acc * BN + c * EPI_COLS), a);
                     if (!first) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                                                                  4 * t))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                             } else {
-                                v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)s, p.tensor_id, p.step, p.k0, p.k1);
+                                v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
                             }
                             e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
                         }
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 float* const dst = pass_kind == 0 ? p.grad_rho : p.grad_mu;
                 const int t_off = pass_kind == 0 ? T_SUM_RHO : T_SUM_MU;
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
+                for (int c = 2 * half; c < min(n_chunks, 2 * half + 2); ++c) {
                     uint32_t r[32];
                     tmem_ld_32x32(lane_base + (uint32_t)(t_off + c * EPI_COLS), r);
                     tmem_ld_wait();
@@ -352,7 +357,7 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     p.groups = groups, p.splits = splits;
     p.rho = rho, p.eps_in = eps_in, p.grad_mu = grad_mu, p.grad_rho = grad_rho, p.turn = turn_ws;
     p.accumulate = accumulate;
-    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id, p.step_ptr = bf_step_counter();
     const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
     if (eps)
         rc = with_mu ? launch<true, true>(ma, mb, p, st) : launch<true, false>(ma, mb, p, st);

@@ -322,8 +322,9 @@ class BayesLinear(torch.autograd.Function):
                 g_x = dx.view(x_shape).to(x_dtype)
             if has_bias:
                 db = torch.empty((S, N), dtype=torch.float32, device=dev)
+                bws = _workspace("bias_grad", dev, lib.bf_bias_grad_workspace_bytes(S, M, N))
                 rc = _timed("bias_grad", float(S * M * N * gyc.element_size()), dev,
-                            lambda: lib.bf_bias_grad(_ptr(gyc), _dt(cdt), _ptr(db), S, M, N, st))
+                            lambda: lib.bf_bias_grad(_ptr(gyc), _dt(cdt), _ptr(db), S, M, N, _ptr(bws), st))
                 _lib.check(rc, "bf_bias_grad")
                 stats["launches"] += 1
             if use_tc:

@@ -91,3 +91,36 @@ def set_gemm_dtype(d) -> None:
 
 def get_gemm_dtype() -> torch.dtype:
     return _global["gemm_dtype"]
+
+
+# ---- device-resident step counter (CUDA-graph capture of a whole training step) ----------
+_device_step = {"tensor": None}
+
+
+def enable_device_step(device) -> torch.Tensor:
+    """Allocate the device step counter and register it with the kernels.  From
+    then on eps is a function of (seed, tensor_id, host_step + device_step,
+    sample): call `advance_step()` once per training step -- it is a plain
+    device add, so it can live inside a captured CUDA graph."""
+    from . import _lib
+
+    dev = torch.device(device)
+    t = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().bf_set_step_counter(t.data_ptr()), "bf_set_step_counter")
+    _device_step["tensor"] = t
+    return t
+
+
+def disable_device_step() -> None:
+    from . import _lib
+
+    if _device_step["tensor"] is not None:
+        _lib.check(_lib.load().bf_set_step_counter(None), "bf_set_step_counter")
+        _device_step["tensor"] = None
+
+
+def advance_step(n: int = 1) -> None:
+    t = _device_step["tensor"]
+    if t is None:
+        raise RuntimeError("enable_device_step(device) first")
+    t.add_(n)

@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step (before the S-fold)")
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step (before the S-fold)")
+    ap.add_argument("--graph", type=int, default=1, help="capture the whole training step in one CUDA graph (1 GPU)")
     ap.add_argument("--samples", type=int, default=4)
     ap.add_argument("--seq", type=int, default=128)
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
@@ -216,8 +217,10 @@ def run_ours(args):
         # the variational masters (mu, rho, priors) stay fp32
         bf.cast_frequentist_(bm, torch.bfloat16)
     params = [p for p in bm.parameters() if p.requires_grad]
-    optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True)
+    use_graph = bool(args.graph) and world == 1 and not args.profile
+    optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True, capturable=use_graph)
     sync = parallel.GradSync(bm)
+    bf.enable_device_step(dev)  # eps = f(seed, tensor, host_step + device_step, sample): graph replays draw fresh eps
 
     B, T, S = args.batch, args.seq, args.samples
     g = torch.Generator().manual_seed(100 + rank)
@@ -226,7 +229,8 @@ def run_ours(args):
     ids_dev, labels_dev = ids_host.to(dev), labels_host.to(dev)
     out_host = torch.zeros(3, dtype=torch.float32).pin_memory()
 
-    def step(ids, labels):
+    def step_body(ids, labels):
+        bf.advance_step()
         optim.zero_grad(set_to_none=True)
         with bf.mc_samples(S):
             logits = bm(input_ids=ids.repeat(S, 1)).logits
@@ -240,6 +244,41 @@ def run_ours(args):
         optim.step()
         return loss, lp, lq
 
+    graph_note = "eager"
+    step = step_body
+    if use_graph:
+        try:
+            static_ids, static_labels = ids_dev.clone(), labels_dev.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_body(static_ids, static_labels)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            optim.zero_grad(set_to_none=True)
+            l0 = ops.stats["launches"]
+            with torch.cuda.graph(graph):
+                static_out = step_body(static_ids, static_labels)
+            launches_per_graph = ops.stats["launches"] - l0
+
+            def step(ids, labels):  # noqa: F811
+                if ids is not static_ids:
+                    static_ids.copy_(ids, non_blocking=True)
+                    static_labels.copy_(labels, non_blocking=True)
+                graph.replay()
+                ops.stats["launches"] += launches_per_graph
+                return static_out
+
+            ids_dev, labels_dev = static_ids, static_labels
+            graph_note = "whole training step captured in one CUDA graph"
+        except Exception as e:  # capture can fail on host syncs inside the host model
+            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            use_graph = False
+            step = step_body
+            torch.cuda.synchronize()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -250,7 +289,7 @@ def run_ours(args):
         step(ids_dev, labels_dev)
 
     # ---- timed region 1: inputs resident in HBM (value)
-    ops.enable_kernel_timing(True)
+    ops.enable_kernel_timing(not use_graph)
     launches0 = ops.stats["launches"]
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -265,6 +304,19 @@ def run_ours(args):
     launches = ops.stats["launches"] - launches0
     kern = ops.kernel_timing_summary()
     ops.enable_kernel_timing(False)
+    kern_steps = args.steps
+    if use_graph:
+        # CUDA events cannot bracket kernels inside a replayed graph: take the per-kernel durations from
+        # eager, instrumented executions of the same step right after the timed region
+        kern_steps = 2
+        step_body(ids_dev, labels_dev)
+        barrier()
+        ops.enable_kernel_timing(True)
+        for _ in range(kern_steps):
+            step_body(ids_dev, labels_dev)
+        barrier()
+        kern = ops.kernel_timing_summary()
+        ops.enable_kernel_timing(False)
 
     # ---- timed region 2: end to end through the public API with HOST buffers (e2e)
     barrier()
@@ -300,19 +352,22 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "tc::bayes_gemm_kernel (fwd + dgrad + fused wgrad, all layers)",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": g_calls / args.steps, "avg_launch_ms": g_ms / max(g_calls, 1),
-                "share_of_step": g_ms / args.steps / ms}
+                "traffic": None, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
+                "share_of_step": g_ms / kern_steps / ms,
+                "timing": "CUDA events around every launch on the launching stream" +
+                          (", taken in eager executions of the same step after the timed graph replays" if use_graph else
+                           ", inside the timed region")}
     sk = kern.get("sample_kl_fwd")
     roof_sk = None
     if sk and sk["ms"] > 0:
         gbs = sk["work"] / (sk["ms"] / 1e3) / 1e9
         roof_sk = {"bound": "hbm", "kernel": "sample_kl_fwd_fast_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
-                   "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "share_of_step": sk["ms"] / args.steps / ms,
+                   "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "share_of_step": sk["ms"] / kern_steps / ms,
                    "traffic": None}
     lin_f, att_f = flops_per_seq_sample(cfg, T)
     step_tf = (lin_f + att_f) * S * value / 1e12
-    kernels = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
-                   "share": v["ms"] / args.steps / ms} for k, v in sorted(kern.items())}
+    kernels = {k: {"calls_per_step": v["calls"] / kern_steps, "ms_per_step": v["ms"] / kern_steps,
+                   "share": v["ms"] / kern_steps / ms} for k, v in sorted(kern.items())}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.profile:
@@ -329,7 +384,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "seq/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": ids_host.numel() * 8 + labels_host.numel() * 8, "d2h_bytes_per_step": 12},
-            "gpu_launches": launches, "clocks": clk,
+            "gpu_launches": launches, "clocks": clk, "execution": graph_note,
             "grad_allreduce_bytes_per_step": sync.bytes_last_step}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -56,6 +56,11 @@ int bf_abi_version(void);
 const char* bf_last_error(void);
 /* 1 when the running device is sm_100 (tcgen05 path usable), else 0; <0 on error */
 int bf_device_is_sm100(void);
+/* Optional device-resident step counter (one process per GPU): when set, every kernel
+ * that draws eps uses  step + *device_counter  as the Philox step.  This is what makes a
+ * whole training step capturable in a CUDA graph: the `step` arguments get baked into the
+ * graph, the counter is bumped on the device between replays.  NULL switches it off. */
+int bf_set_step_counter(const uint32_t* device_counter);
 
 /* ------------------------------------------------------------------------- *
  * eps stream, exposed for the statistical tests.
@@ -154,8 +159,12 @@ int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, int64_t M, i
                           void* workspace, void* stream);
 
 /* column sums of gy over the M rows of each sample: db[s][j] = sum_m gy[s][m][j]
- * (the bias gradient F.linear's autograd produces).  db fp32 [S,N]. */
-int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N, void* stream);
+ * (the bias gradient F.linear's autograd produces).  db fp32 [S,N].  Deterministic
+ * two-stage reduction; workspace of bf_bias_grad_workspace_bytes(S, M, N) bytes,
+ * zero-filled once. */
+int64_t bf_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N);
+int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N, void* workspace,
+                 void* stream);
 
 #ifdef __cplusplus
 }
