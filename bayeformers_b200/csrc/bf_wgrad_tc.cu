@@ -33,16 +33,26 @@ int bf_sample_kl_bwd_impl_kl_only(const float* mu, const float* rho, int32_t pri
 namespace wg {
 using namespace tc;
 
-constexpr int BM = 128, BN = 128;
-constexpr int kStages = 5;
-constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2;  // 16 KiB each
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_COLS = 32, EPI_STRIDE = 36, EPI_WARPS = 8;  // 2 warps per TMEM lane quarter, 2 chunks each
-constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_STRIDE * 4;
+constexpr int BM = 128;
+constexpr int EPI_COLS = 32, EPI_WARPS = 8;  // 2 warps per TMEM lane quarter, each owning half of the column chunks
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
-constexpr int TMEM_COLS = 512;  // [0,128) acc0 | [128,256) acc1 | [256,384) sum dW*eps | [384,512) sum dW
-constexpr int T_SUM_RHO = 256, T_SUM_MU = 384;
-constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + EPI_BYTES + 256;
+constexpr int TMEM_COLS = 512;
+
+// Two tile shapes (TMEM is 512 columns in both):
+//   BN = 256 (mu frozen, the MOPED fine-tuning case): [0,256) accumulator | [256,512) sum dW*eps.
+//            128x256 tiles have 1.37x the arithmetic intensity of 128x128 ones, which is what the
+//            L2->SM operand stream (measured ~11-14 TB/s with everything in flight) needs.
+//   BN = 128 (mu trainable): [0,128) acc0 | [128,256) acc1 | [256,384) sum dW*eps | [384,512) sum dW.
+template <int BN>
+struct Cfg {
+    static constexpr int NACC = BN == 128 ? 2 : 1;
+    static constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int kStages = BN == 128 ? 6 : 4;
+    static constexpr int T_SUM_RHO = 256, T_SUM_MU = 384;
+    static constexpr int CHUNKS_PER_WARP = (BN / EPI_COLS) / 2;
+    static constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + 256;
+};
 
 struct Params {
     int64_t S, I, J, R;  // samples, rows of W (N), cols of W (K), reduction length (M)
@@ -75,22 +85,24 @@ __device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
     return it;
 }
 
-template <bool HAS_EPS, bool WITH_MU>
+template <int BN, bool HAS_EPS, bool WITH_MU>
 __global__ void __launch_bounds__(kThreads, 1)
     bayes_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
                        const __grid_constant__ Params p) {
+    using C = Cfg<BN>;
+    static_assert(!(WITH_MU && BN != 128), "the mu sum only fits next to 128-column accumulators");
+    constexpr int kStages = C::kStages, NACC = C::NACC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    float* const epi_stage = reinterpret_cast<float*>(smem_gen + kStages * STAGE_BYTES);
-    const uint32_t bar_base = smem_base + kStages * STAGE_BYTES + EPI_BYTES;
+    const uint32_t bar_base = smem_base + kStages * C::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
     volatile uint32_t* const tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * STAGE_BYTES + EPI_BYTES + 8 * (2 * kStages + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * C::STAGE_BYTES + 8 * (2 * kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -125,9 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int s = it.s_begin; s < it.s_end; ++s) {
                     for (int ks = it.k_begin; ks < it.k_end; ++ks) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-                        const uint32_t b_dst = a_dst + A_BYTES;
-                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                        const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+                        const uint32_t b_dst = a_dst + C::A_BYTES;
+                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                         const int r0 = ks * BLOCK_K;
 #pragma unroll
                         for (int a = 0; a < BM / ATOM_MN; ++a)  // gy[s][m][n]: MN-major, rows = reduction m
@@ -150,16 +162,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
                 const Item it = decode_item(p, L);
                 for (int s = it.s_begin; s < it.s_end; ++s, ++iter) {
-                    const int acc = iter & 1;
-                    const uint32_t acc_phase = (iter >> 1) & 1;
+                    const int acc = iter % NACC;
+                    const uint32_t acc_phase = (iter / NACC) & 1;
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                     for (int ks = it.k_begin; ks < it.k_end; ++ks) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint32_t a_src = smem_base + stage * STAGE_BYTES;
-                        const uint32_t b_src = a_src + A_BYTES;
+                        const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
+                        const uint32_t b_src = a_src + C::A_BYTES;
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc,
@@ -173,52 +185,110 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else {
         // ===================== epilogue warps =====================
-        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter
-        // split the 4 column chunks (two warps per scheduler hide each other's dependency stalls)
+        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the
+        // column chunks, and two warps per scheduler hide each other's dependency stalls
         const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* const stage_w = epi_stage + (warp - 2) * 32 * EPI_STRIDE;
         int iter = 0;
         for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
             const Item it = decode_item(p, L);
-            const int64_t i_base = (int64_t)it.i_blk * BM + q * 32;
             const int64_t j_base = (int64_t)it.j_blk * BN;
-            const int64_t my_row = i_base + lane;
+            const int64_t my_row = (int64_t)it.i_blk * BM + q * 32 + lane;
             const bool row_ok = my_row < p.I;
             int n_chunks = BN / EPI_COLS;  // warp-uniform
             if (j_base + BN > p.J) n_chunks = (int)((p.J - j_base + EPI_COLS - 1) / EPI_COLS);
+            const int c_lo = half * C::CHUNKS_PER_WARP;
+            const int c_hi = min(n_chunks, c_lo + C::CHUNKS_PER_WARP);
+            const bool single = (it.s_end - it.s_begin == 1);  // one sample: no running sum needed
 
             // ---- per sample: sums (TMEM) += accumulator (TMEM) o eps (registers) ----
             for (int s = it.s_begin; s < it.s_end; ++s, ++iter) {
-                const int acc = iter & 1;
-                const uint32_t acc_phase = (iter >> 1) & 1;
+                const int acc = iter % NACC;
+                const uint32_t acc_phase = (iter / NACC) & 1;
                 const bool first = (s == it.s_begin);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                if (!single) {
 #pragma unroll 1
-                for (int c = 2 * half; c < min(n_chunks, 2 * half + 2); ++c) {
-                    uint32_t a[32], sr[32], sm[32];
-                    tmem_ld_32x32(lane_base + (uint32_t)(acc * BN + c * EPI_COLS), a);
-                    if (!first) {
-                        tmem_ld_32x32(lane_base + (uint32_t)(T_SUM_RHO + c * EPI_COLS), sr);
-                        if (WITH_MU) tmem_ld_32x32(lane_base + (uint32_t)(T_SUM_MU + c * EPI_COLS), sm);
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t a[32], sr[32], sm[32];
+                        tmem_ld_32x32(lane_base + (uint32_t)(acc * BN + c * EPI_COLS), a);
+                        if (!first) {
+                            tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), sr);
+                            if (WITH_MU) tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), sm);
+                        }
+                        float e[32];
+                        const int64_t flat = my_row * p.J + j_base + c * EPI_COLS;
+                        if (row_ok) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                float4 v;
+                                if (HAS_EPS) {
+                                    v = (j_base + c * EPI_COLS + 4 * t + 4 <= p.J)
+                                            ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)s * p.I * p.J +
+                                                                                     flat + 4 * t))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                                } else {
+                                    v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
+                                }
+                                e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 32; ++t) e[t] = 0.0f;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const float av = __uint_as_float(a[t]);
+                            const float prev = first ? 0.0f : __uint_as_float(sr[t]);
+                            sr[t] = __float_as_uint(fmaf(av, e[t], prev));
+                            if (WITH_MU) sm[t] = __float_as_uint(first ? av : __uint_as_float(sm[t]) + av);
+                        }
+                        tmem_st_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), sr);
+                        if (WITH_MU) tmem_st_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), sm);
                     }
-                    // eps of W[my_row][j_base + 32c .. +31]: 8 aligned quads of the flat [I*J] stream
-                    float e[32];
-                    const int64_t flat = my_row * p.J + j_base + c * EPI_COLS;
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained
+                }
+            }
+
+            // ---- once per item: -> global gradients, items of one tile in fixed turn order ----
+            if (it.turns > 1) {
+                if (lane == 0) {
+                    const volatile int* t = p.turn + it.tile;
+                    while (*t != it.turn) __nanosleep(64);
+                    __threadfence();
+                }
+                __syncwarp();
+            }
+            const bool add = (it.turn > 0) || p.accumulate;
+            const int last_acc = (iter - 1) % NACC;
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t r[32], rm[32];
+                const int64_t jc = j_base + c * EPI_COLS;
+                const int64_t flat = my_row * p.J + jc;
+                float e[32];
+                if (single) {
+                    // the only sample of this item: combine accumulator and eps here, no TMEM round trip
+                    tmem_ld_32x32(lane_base + (uint32_t)(last_acc * BN + c * EPI_COLS), r);
                     if (row_ok) {
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
                             float4 v;
                             if (HAS_EPS) {
-                                v = (j_base + c * EPI_COLS + 4 * t + 4 <= p.J)
-                                        ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)s * p.I * p.J + flat +
-                                                                                 4 * t))
+                                v = (jc + 4 * t + 4 <= p.J)
+                                        ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)it.s_begin * p.I * p.J +
+                                                                                 flat + 4 * t))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                             } else {
-                                v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
+                                v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)it.s_begin, p.tensor_id, step, p.k0,
+                                                p.k1);
                             }
                             e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
                         }
@@ -229,70 +299,49 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tmem_ld_wait();
 #pragma unroll
                     for (int t = 0; t < 32; ++t) {
-                        const float av = __uint_as_float(a[t]);
-                        const float prev = first ? 0.0f : __uint_as_float(sr[t]);
-                        sr[t] = __float_as_uint(fmaf(av, e[t], prev));
-                        if (WITH_MU) sm[t] = __float_as_uint(first ? av : __uint_as_float(sm[t]) + av);
+                        if (WITH_MU) rm[t] = r[t];
+                        r[t] = __float_as_uint(__uint_as_float(r[t]) * e[t]);
                     }
-                    tmem_st_32x32(lane_base + (uint32_t)(T_SUM_RHO + c * EPI_COLS), sr);
-                    if (WITH_MU) tmem_st_32x32(lane_base + (uint32_t)(T_SUM_MU + c * EPI_COLS), sm);
-                }
-                tmem_st_wait();
-                // accumulator drained: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
-
-            // ---- once per item: sums -> global gradients (coalesced, fixed turn order) ----
-            if (it.turns > 1) {
-                if (lane == 0) {
-                    const volatile int* t = p.turn + it.tile;
-                    while (*t != it.turn) __nanosleep(64);
-                    __threadfence();
-                }
-                __syncwarp();
-            }
-            const bool add = (it.turn > 0) || p.accumulate;
-#pragma unroll 1
-            for (int pass_kind = 0; pass_kind < (WITH_MU ? 2 : 1); ++pass_kind) {
-                float* const dst = pass_kind == 0 ? p.grad_rho : p.grad_mu;
-                const int t_off = pass_kind == 0 ? T_SUM_RHO : T_SUM_MU;
-#pragma unroll 1
-                for (int c = 2 * half; c < min(n_chunks, 2 * half + 2); ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(lane_base + (uint32_t)(t_off + c * EPI_COLS), r);
+                } else {
+                    tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), r);
+                    if (WITH_MU) tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), rm);
                     tmem_ld_wait();
+                }
+                if (row_ok) {
+                    // thread = one row of W, 32 consecutive columns = one full 128 B line per thread
 #pragma unroll
-                    for (int v = 0; v < 8; ++v)  // lane = row; 16 B stores, conflict-free with the 36-float stride
-                        *reinterpret_cast<uint4*>(stage_w + lane * EPI_STRIDE + 4 * v) =
-                            make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
-                    __syncwarp();
-                    // 8 lanes x float4 cover one 32-column row segment (128 B), 4 rows per pass
-                    const int cj = 4 * (lane & 7);
-                    const int64_t j = j_base + c * EPI_COLS + cj;
-#pragma unroll
-                    for (int pass = 0; pass < 8; ++pass) {
-                        const int rr = pass * 4 + (lane >> 3);
-                        const int64_t i = i_base + rr;
-                        if (i < p.I && j < p.J) {  // J % 4 == 0: the quad is fully inside
-                            const int64_t flat = i * p.J + j;
-                            float4 o = *reinterpret_cast<const float4*>(stage_w + rr * EPI_STRIDE + cj);
-                            if (pass_kind == 0) {
-                                const float4 rho4 = __ldg(reinterpret_cast<const float4*>(p.rho + flat));
-                                o.x *= bf_softplus_grad(rho4.x), o.y *= bf_softplus_grad(rho4.y);
-                                o.z *= bf_softplus_grad(rho4.z), o.w *= bf_softplus_grad(rho4.w);
-                            }
-                            float4* d4 = reinterpret_cast<float4*>(dst + flat);
+                    for (int v = 0; v < 8; ++v) {
+                        if (jc + 4 * v + 4 <= p.J) {  // J % 4 == 0
+                            const float4 rho4 = __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v));
+                            float4 o;
+                            o.x = __uint_as_float(r[4 * v + 0]) * bf_softplus_grad(rho4.x);
+                            o.y = __uint_as_float(r[4 * v + 1]) * bf_softplus_grad(rho4.y);
+                            o.z = __uint_as_float(r[4 * v + 2]) * bf_softplus_grad(rho4.z);
+                            o.w = __uint_as_float(r[4 * v + 3]) * bf_softplus_grad(rho4.w);
+                            float4* d4 = reinterpret_cast<float4*>(p.grad_rho + flat + 4 * v);
                             if (add) {
                                 const float4 old = __ldcg(d4);
                                 o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                             }
                             __stcg(d4, o);
+                            if (WITH_MU) {
+                                float4 m = make_float4(__uint_as_float(rm[4 * v + 0]), __uint_as_float(rm[4 * v + 1]),
+                                                       __uint_as_float(rm[4 * v + 2]), __uint_as_float(rm[4 * v + 3]));
+                                float4* m4 = reinterpret_cast<float4*>(p.grad_mu + flat + 4 * v);
+                                if (add) {
+                                    const float4 old = __ldcg(m4);
+                                    m.x += old.x, m.y += old.y, m.z += old.z, m.w += old.w;
+                                }
+                                __stcg(m4, m);
+                            }
                         }
                     }
-                    __syncwarp();
                 }
+            }
+            if (single) {  // the accumulator was read in the final pass: release it only now
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(last_acc));
             }
             if (it.turns > 1) {
                 __threadfence();
@@ -314,13 +363,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
-template <bool HAS_EPS, bool WITH_MU>
+template <int BN, bool HAS_EPS, bool WITH_MU>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
-    auto kern = bayes_wgrad_kernel<HAS_EPS, WITH_MU>;
-    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    auto kern = bayes_wgrad_kernel<BN, HAS_EPS, WITH_MU>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     const int64_t n_items = (int64_t)p.i_tiles * p.j_tiles * p.groups * p.splits;
     const int64_t sms = bf_num_sms();
-    kern<<<(int)(n_items < sms ? n_items : sms), kThreads, SMEM_BYTES, st>>>(ma, mb, p);
+    kern<<<(int)(n_items < sms ? n_items : sms), kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ma, mb, p);
     BF_LAUNCH_OK();
     return 0;
 }
@@ -328,7 +377,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
 }  // namespace wg
 
 int64_t bf_wgrad_fused_workspace_ints(int64_t N, int64_t K) {
-    return (int64_t)tc::cdiv(N, wg::BM) * tc::cdiv(K, wg::BN);
+    return (int64_t)tc::cdiv(N, wg::BM) * tc::cdiv(K, 128);  // enough for either tile width
 }
 
 int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K,
@@ -344,9 +393,11 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     int rc;
     if ((rc = tc::encode_map(&ma, gy, S, M, N, tc::BLOCK_K))) return rc;
     if ((rc = tc::encode_map(&mb, x, S, M, K, tc::BLOCK_K))) return rc;
+    const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
+    const int bn = with_mu ? 128 : 256;
     Params p{};
     p.S = S, p.I = N, p.J = K, p.R = M;
-    p.i_tiles = tc::cdiv(N, BM), p.j_tiles = tc::cdiv(K, BN), p.k_steps = tc::cdiv(M, tc::BLOCK_K);
+    p.i_tiles = tc::cdiv(N, BM), p.j_tiles = tc::cdiv(K, bn), p.k_steps = tc::cdiv(M, tc::BLOCK_K);
     // fill the persistent grid: first cut a tile by groups of samples (each (element, sample) eps is still
     // generated exactly once), then by slices of the reduction (eps regenerated per slice)
     const int64_t tiles = (int64_t)p.i_tiles * p.j_tiles;
@@ -357,12 +408,12 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     p.groups = groups, p.splits = splits;
     p.rho = rho, p.eps_in = eps_in, p.grad_mu = grad_mu, p.grad_rho = grad_rho, p.turn = turn_ws;
     p.accumulate = accumulate;
-    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id, p.step_ptr = bf_step_counter();
-    const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
-    if (eps)
-        rc = with_mu ? launch<true, true>(ma, mb, p, st) : launch<true, false>(ma, mb, p, st);
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
+    p.step_ptr = bf_step_counter();
+    if (with_mu)
+        rc = eps ? launch<128, true, true>(ma, mb, p, st) : launch<128, false, true>(ma, mb, p, st);
     else
-        rc = with_mu ? launch<false, true>(ma, mb, p, st) : launch<false, false>(ma, mb, p, st);
+        rc = eps ? launch<256, true, false>(ma, mb, p, st) : launch<256, false, false>(ma, mb, p, st);
     if (rc) return rc;
     // KL terms do not involve gy: they are one elementwise pass added on top (eps regenerated once more)
     if (g_logq != nullptr || g_logp != nullptr)

@@ -273,11 +273,12 @@ def run_ours(args):
 
             ids_dev, labels_dev = static_ids, static_labels
             graph_note = "whole training step captured in one CUDA graph"
-        except Exception as e:  # capture can fail on host syncs inside the host model
-            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
-            use_graph = False
-            step = step_body
-            torch.cuda.synchronize()
+        except Exception as e:  # e.g. a host sync inside the host model: restart this process in eager mode
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}); re-running eagerly\n")
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--graph", "0"])
 
     def barrier():
         if world > 1:

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 echo "== pytest gpu"; timeout -k 10 900 python -m pytest tests -m gpu -q --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?"; tail -8 gpurun_out/pytest_gpu.log | cut -c1-300
 echo "== gemm timing"; timeout -k 10 300 python scripts/gpu_debug_gemm.py > gpurun_out/debug_gemm.log 2>&1; echo "exit $?"; grep -E "TF|rc [1-9]" gpurun_out/debug_gemm.log | head -20
-for B in 64 32 128; do
+for B in 64 128; do
 echo "== bench B=$B"; timeout -k 10 900 python bench.py --steps 8 --warmup 3 --batch $B $( [ $B != 64 ] && echo --no-cpu-baseline ) > gpurun_out/bench_b$B.json 2> gpurun_out/bench_b$B.err; echo "exit $?"; python - <<PY
 import json
 try:
