@@ -201,7 +201,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (j_base + BN > p.J) n_chunks = (int)((p.J - j_base + EPI_COLS - 1) / EPI_COLS);
             const int c_lo = half * C::CHUNKS_PER_WARP;
             const int c_hi = min(n_chunks, c_lo + C::CHUNKS_PER_WARP);
-            const bool single = (it.s_end - it.s_begin == 1);  // one sample: no running sum needed
 
             // ---- per sample: sums (TMEM) += accumulator (TMEM) o eps (registers) ----
             for (int s = it.s_begin; s < it.s_end; ++s, ++iter) {
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const bool first = (s == it.s_begin);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                if (!single) {
+                {
 #pragma unroll 1
                     for (int c = c_lo; c < c_hi; ++c) {
                         uint32_t a[32], sr[32], sm[32];
@@ -267,81 +266,50 @@ __global__ void __launch_bounds__(kThreads, 1)
                 __syncwarp();
             }
             const bool add = (it.turn > 0) || p.accumulate;
-            const int last_acc = (iter - 1) % NACC;
 #pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t r[32], rm[32];
-                const int64_t jc = j_base + c * EPI_COLS;
-                const int64_t flat = my_row * p.J + jc;
-                float e[32];
-                if (single) {
-                    // the only sample of this item: combine accumulator and eps here, no TMEM round trip
-                    tmem_ld_32x32(lane_base + (uint32_t)(last_acc * BN + c * EPI_COLS), r);
+            for (int kind = 0; kind < (WITH_MU ? 2 : 1); ++kind) {  // 0: grad_rho (x sigmoid(rho)), 1: grad_mu
+                float* const dst = kind == 0 ? p.grad_rho : p.grad_mu;
+                const int t_off = kind == 0 ? C::T_SUM_RHO : C::T_SUM_MU;
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t r[32];
+                    const int64_t jc = j_base + c * EPI_COLS;
+                    const int64_t flat = my_row * p.J + jc;
+                    tmem_ld_32x32(lane_base + (uint32_t)(t_off + c * EPI_COLS), r);
                     if (row_ok) {
+                        // thread = one row of W, 32 consecutive columns = one full 128 B line per thread.
+                        // All loads of the chunk are issued before any store (the compiler cannot hoist the
+                        // read-modify-write loads above stores to the same array on its own).
+                        float4 scale[8], old[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            float4 v;
-                            if (HAS_EPS) {
-                                v = (jc + 4 * t + 4 <= p.J)
-                                        ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)it.s_begin * p.I * p.J +
-                                                                                 flat + 4 * t))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                            } else {
-                                v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)it.s_begin, p.tensor_id, step, p.k0,
-                                                p.k1);
+                        for (int v = 0; v < 8; ++v) {
+                            const bool in = (jc + 4 * v + 4 <= p.J);  // J % 4 == 0
+                            scale[v] = (in && kind == 0) ? __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                            old[v] = (in && add) ? __ldcg(reinterpret_cast<const float4*>(dst + flat + 4 * v))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            if (jc + 4 * v + 4 <= p.J) {
+                                float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+                                if (kind == 0) {
+                                    g.x = bf_softplus_grad(scale[v].x), g.y = bf_softplus_grad(scale[v].y);
+                                    g.z = bf_softplus_grad(scale[v].z), g.w = bf_softplus_grad(scale[v].w);
+                                }
+                                float4 o;
+                                o.x = fmaf(__uint_as_float(r[4 * v + 0]), g.x, old[v].x);
+                                o.y = fmaf(__uint_as_float(r[4 * v + 1]), g.y, old[v].y);
+                                o.z = fmaf(__uint_as_float(r[4 * v + 2]), g.z, old[v].z);
+                                o.w = fmaf(__uint_as_float(r[4 * v + 3]), g.w, old[v].w);
+                                __stcg(reinterpret_cast<float4*>(dst + flat + 4 * v), o);
                             }
-                            e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
                         }
                     } else {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) e[t] = 0.0f;
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        if (WITH_MU) rm[t] = r[t];
-                        r[t] = __float_as_uint(__uint_as_float(r[t]) * e[t]);
-                    }
-                } else {
-                    tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), r);
-                    if (WITH_MU) tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), rm);
-                    tmem_ld_wait();
-                }
-                if (row_ok) {
-                    // thread = one row of W, 32 consecutive columns = one full 128 B line per thread
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        if (jc + 4 * v + 4 <= p.J) {  // J % 4 == 0
-                            const float4 rho4 = __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v));
-                            float4 o;
-                            o.x = __uint_as_float(r[4 * v + 0]) * bf_softplus_grad(rho4.x);
-                            o.y = __uint_as_float(r[4 * v + 1]) * bf_softplus_grad(rho4.y);
-                            o.z = __uint_as_float(r[4 * v + 2]) * bf_softplus_grad(rho4.z);
-                            o.w = __uint_as_float(r[4 * v + 3]) * bf_softplus_grad(rho4.w);
-                            float4* d4 = reinterpret_cast<float4*>(p.grad_rho + flat + 4 * v);
-                            if (add) {
-                                const float4 old = __ldcg(d4);
-                                o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-                            }
-                            __stcg(d4, o);
-                            if (WITH_MU) {
-                                float4 m = make_float4(__uint_as_float(rm[4 * v + 0]), __uint_as_float(rm[4 * v + 1]),
-                                                       __uint_as_float(rm[4 * v + 2]), __uint_as_float(rm[4 * v + 3]));
-                                float4* m4 = reinterpret_cast<float4*>(p.grad_mu + flat + 4 * v);
-                                if (add) {
-                                    const float4 old = __ldcg(m4);
-                                    m.x += old.x, m.y += old.y, m.z += old.z, m.w += old.w;
-                                }
-                                __stcg(m4, m);
-                            }
-                        }
+                        tmem_ld_wait();
                     }
                 }
-            }
-            if (single) {  // the accumulator was read in the final pass: release it only now
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(last_acc));
             }
             if (it.turns > 1) {
                 __threadfence();

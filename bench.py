@@ -259,7 +259,7 @@ def run_ours(args):
             graph = torch.cuda.CUDAGraph()
             optim.zero_grad(set_to_none=True)
             l0 = ops.stats["launches"]
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):  # same stream as the warm-up: handles/workspaces exist
                 static_out = step_body(static_ids, static_labels)
             launches_per_graph = ops.stats["launches"] - l0
 
