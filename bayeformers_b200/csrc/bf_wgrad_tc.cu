@@ -276,38 +276,34 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const int64_t jc = j_base + c * EPI_COLS;
                     const int64_t flat = my_row * p.J + jc;
                     tmem_ld_32x32(lane_base + (uint32_t)(t_off + c * EPI_COLS), r);
-                    if (row_ok) {
-                        // thread = one row of W, 32 consecutive columns = one full 128 B line per thread.
-                        // All loads of the chunk are issued before any store (the compiler cannot hoist the
-                        // read-modify-write loads above stores to the same array on its own).
-                        float4 scale[8], old[8];
+                    // thread = one row of W, 32 consecutive columns = one full 128 B line per thread.
+                    // All loads of the chunk are issued before any store (the compiler cannot hoist the
+                    // read-modify-write loads above stores to the same array on its own).
+                    float4 scale[8], old[8];
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            const bool in = (jc + 4 * v + 4 <= p.J);  // J % 4 == 0
-                            scale[v] = (in && kind == 0) ? __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                            old[v] = (in && add) ? __ldcg(reinterpret_cast<const float4*>(dst + flat + 4 * v))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                        tmem_ld_wait();
+                    for (int v = 0; v < 8; ++v) {
+                        const bool in = row_ok && (jc + 4 * v + 4 <= p.J);  // J % 4 == 0
+                        scale[v] = (in && kind == 0) ? __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        old[v] = (in && add) ? __ldcg(reinterpret_cast<const float4*>(dst + flat + 4 * v))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tmem_ld_wait();  // warp-collective: must stay outside any lane-divergent branch
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) {
-                            if (jc + 4 * v + 4 <= p.J) {
-                                float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-                                if (kind == 0) {
-                                    g.x = bf_softplus_grad(scale[v].x), g.y = bf_softplus_grad(scale[v].y);
-                                    g.z = bf_softplus_grad(scale[v].z), g.w = bf_softplus_grad(scale[v].w);
-                                }
-                                float4 o;
-                                o.x = fmaf(__uint_as_float(r[4 * v + 0]), g.x, old[v].x);
-                                o.y = fmaf(__uint_as_float(r[4 * v + 1]), g.y, old[v].y);
-                                o.z = fmaf(__uint_as_float(r[4 * v + 2]), g.z, old[v].z);
-                                o.w = fmaf(__uint_as_float(r[4 * v + 3]), g.w, old[v].w);
-                                __stcg(reinterpret_cast<float4*>(dst + flat + 4 * v), o);
+                    for (int v = 0; v < 8; ++v) {
+                        if (row_ok && jc + 4 * v + 4 <= p.J) {
+                            float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (kind == 0) {
+                                g.x = bf_softplus_grad(scale[v].x), g.y = bf_softplus_grad(scale[v].y);
+                                g.z = bf_softplus_grad(scale[v].z), g.w = bf_softplus_grad(scale[v].w);
                             }
+                            float4 o;
+                            o.x = fmaf(__uint_as_float(r[4 * v + 0]), g.x, old[v].x);
+                            o.y = fmaf(__uint_as_float(r[4 * v + 1]), g.y, old[v].y);
+                            o.z = fmaf(__uint_as_float(r[4 * v + 2]), g.z, old[v].z);
+                            o.w = fmaf(__uint_as_float(r[4 * v + 3]), g.w, old[v].w);
+                            __stcg(reinterpret_cast<float4*>(dst + flat + 4 * v), o);
                         }
-                    } else {
-                        tmem_ld_wait();
                     }
                 }
             }

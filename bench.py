@@ -252,6 +252,10 @@ def run_ours(args):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
+                # every Linear contraction is ours, so nothing has touched cuBLAS yet; SDPA may fall back to
+                # bmm under capture, and creating a cuBLAS handle while capturing is illegal: make it exist now
+                _d = torch.ones(64, 64, device=dev, dtype=torch.bfloat16)
+                torch.bmm(_d[None], _d[None]); torch.mm(_d.float(), _d.float())
                 for _ in range(3):
                     step_body(static_ids, static_labels)
             torch.cuda.current_stream().wait_stream(side)
