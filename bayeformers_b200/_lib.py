@@ -36,7 +36,7 @@ SIGNATURES = {
                                   c_int32, c_void_p]),
     "bf_linear_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
                                   c_void_p]),
-    "bf_linear_wgrad_fused_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "bf_linear_wgrad_fused_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int32]),
     "bf_linear_wgrad_fused": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                         c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                         c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,

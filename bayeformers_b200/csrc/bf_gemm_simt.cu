@@ -112,56 +112,92 @@ int launch_gemm(const GemmParams& p, int64_t S, cudaStream_t st) {
 }
 
 // ---- bias gradient: db[s][j] = sum_m gy[s][m][j] ---------------------------
-// Two deterministic stages in one launch: every block reduces a slab of rows for 64 columns
+// Two deterministic stages in one launch: every block reduces a slab of rows for 32*V columns
 // into a partial; the last block to finish a (sample, column-block) adds the partials in
-// slab order (self-resetting counter, no float atomics).
-constexpr int kColsPerBlock = 64;
+// slab order (self-resetting counter, no float atomics).  V = elements per lane and load:
+// 8 bf16 / 4 fp32 (16-byte loads, N % V == 0, 16 B aligned rows) or 2 (scalar, any shape).
 constexpr int kBiasThreads = 256;
+constexpr int kBiasWarps = kBiasThreads / 32;
+constexpr int kBiasRowsInFlight = 4;
 
-template <typename T>
+template <typename T, int V>
+struct BiasLoad;
+template <>
+struct BiasLoad<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+};
+template <>
+struct BiasLoad<float, 4> {
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+        const float4 u = __ldcs(reinterpret_cast<const float4*>(p));
+        v[0] = u.x, v[1] = u.y, v[2] = u.z, v[3] = u.w;
+    }
+};
+
+template <typename T, int V, bool VEC>
 __global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const T* __restrict__ gy, float* __restrict__ db,
                                                                  float* __restrict__ partial,
                                                                  unsigned int* __restrict__ counters, int64_t M,
                                                                  int64_t N, int64_t rows_per_slab) {
+    constexpr int kCols = 32 * V;
     const int s = blockIdx.y, slab = blockIdx.z, n_slabs = gridDim.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t c0 = (int64_t)blockIdx.x * kColsPerBlock + lane * 2;
+    const int64_t c0 = (int64_t)blockIdx.x * kCols + lane * V;
     const T* base = gy + (int64_t)s * M * N;
     const int64_t m_lo = (int64_t)slab * rows_per_slab;
     const int64_t m_hi = m_lo + rows_per_slab < M ? m_lo + rows_per_slab : M;
-    float a0 = 0.0f, a1 = 0.0f;
-    const bool ok0 = c0 < N, ok1 = c0 + 1 < N;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.0f;
     int64_t m = m_lo + warp;
-    for (; m + 3 * (kBiasThreads / 32) < m_hi; m += 4 * (kBiasThreads / 32)) {  // 4 rows in flight per warp
-        float v0[4], v1[4];
+    if constexpr (VEC) {
+        if (c0 < N) {  // N % V == 0: a lane's V columns are all inside or all outside
+            for (; m + (kBiasRowsInFlight - 1) * kBiasWarps < m_hi; m += kBiasRowsInFlight * kBiasWarps) {
+                float v[kBiasRowsInFlight][V];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const T* row = base + (m + u * (kBiasThreads / 32)) * N + c0;
-            v0[u] = ok0 ? bf_ld_as_float(row) : 0.0f;
-            v1[u] = ok1 ? bf_ld_as_float(row + 1) : 0.0f;
+                for (int u = 0; u < kBiasRowsInFlight; ++u) BiasLoad<T, V>::ld(base + (m + u * kBiasWarps) * N + c0, v[u]);
+#pragma unroll
+                for (int u = 0; u < kBiasRowsInFlight; ++u)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] += v[u][j];
+            }
+            for (; m < m_hi; m += kBiasWarps) {
+                float v[V];
+                BiasLoad<T, V>::ld(base + m * N + c0, v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[j] += v[j];
+            }
         }
+    } else {
+        for (; m < m_hi; m += kBiasWarps) {
+            const T* row = base + m * N + c0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a0 += v0[u], a1 += v1[u];
+            for (int j = 0; j < V; ++j)
+                if (c0 + j < N) acc[j] += bf_ld_as_float(row + j);
+        }
     }
-    for (; m < m_hi; m += kBiasThreads / 32) {
-        const T* row = base + m * N + c0;
-        if (ok0) a0 += bf_ld_as_float(row);
-        if (ok1) a1 += bf_ld_as_float(row + 1);
-    }
-    __shared__ float red[kBiasThreads / 32][kColsPerBlock];
+    __shared__ float red[kBiasWarps][kCols];
     __shared__ bool is_last;
-    red[warp][lane * 2] = a0;
-    red[warp][lane * 2 + 1] = a1;
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[warp][lane * V + j] = acc[j];
     __syncthreads();
     const int64_t cb = blockIdx.x;
     const int64_t n_cb = gridDim.x;
-    if (threadIdx.x < kColsPerBlock) {
+    for (int c = threadIdx.x; c < kCols; c += kBiasThreads) {
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kBiasThreads / 32; ++w) t += red[w][threadIdx.x];
-        partial[(((int64_t)s * n_cb + cb) * n_slabs + slab) * kColsPerBlock + threadIdx.x] = t;
-        __threadfence();
+        for (int w = 0; w < kBiasWarps; ++w) t += red[w][c];
+        partial[(((int64_t)s * n_cb + cb) * n_slabs + slab) * kCols + c] = t;
     }
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int done = atomicAdd(counters + s * n_cb + cb, 1u);
@@ -170,18 +206,18 @@ __global__ void __launch_bounds__(kBiasThreads) bias_grad_kernel(const T* __rest
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x < kColsPerBlock) {
-        const volatile float* pp = partial + ((int64_t)s * n_cb + cb) * n_slabs * kColsPerBlock + threadIdx.x;
+    for (int cc = threadIdx.x; cc < kCols; cc += kBiasThreads) {
+        const volatile float* pp = partial + ((int64_t)s * n_cb + cb) * n_slabs * kCols + cc;
         float t = 0.0f;
-        for (int k = 0; k < n_slabs; ++k) t += pp[(int64_t)k * kColsPerBlock];
-        const int64_t c = cb * kColsPerBlock + threadIdx.x;
+        for (int k = 0; k < n_slabs; ++k) t += pp[(int64_t)k * kCols];
+        const int64_t c = cb * kCols + cc;
         if (c < N) db[(int64_t)s * N + c] = t;
     }
     if (threadIdx.x == 0) counters[s * n_cb + cb] = 0u;
 }
 
-inline void bias_grid(int64_t S, int64_t M, int64_t N, int& n_cb, int& n_slabs, int64_t& rows_per_slab) {
-    n_cb = (int)((N + kColsPerBlock - 1) / kColsPerBlock);
+inline void bias_grid(int64_t S, int64_t M, int64_t N, int cols, int& n_cb, int& n_slabs, int64_t& rows_per_slab) {
+    n_cb = (int)((N + cols - 1) / cols);
     const int64_t target = (int64_t)bf_num_sms() * 4;
     int64_t slabs = target / (S * n_cb);
     const int64_t max_slabs = (M + 63) / 64;
@@ -190,6 +226,28 @@ inline void bias_grid(int64_t S, int64_t M, int64_t N, int& n_cb, int& n_slabs, 
     if (slabs > 65535) slabs = 65535;
     rows_per_slab = (M + slabs - 1) / slabs;
     n_slabs = (int)((M + rows_per_slab - 1) / rows_per_slab);
+}
+
+inline int64_t bias_ws_bytes(int64_t S, int64_t M, int64_t N, int cols) {
+    int n_cb, n_slabs;
+    int64_t rps;
+    bias_grid(S, M, N, cols, n_cb, n_slabs, rps);
+    // [counters: S*n_cb uint32, padded to 256 B][partials: S*n_cb*n_slabs*cols floats]
+    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
+    return cnt + S * n_cb * (int64_t)n_slabs * cols * 4;
+}
+
+template <typename T, int V, bool VEC>
+void launch_bias(const void* gy, float* db, int64_t S, int64_t M, int64_t N, void* workspace, cudaStream_t st) {
+    int n_cb, n_slabs;
+    int64_t rps;
+    bias_grid(S, M < 1 ? 1 : M, N, 32 * V, n_cb, n_slabs, rps);
+    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + cnt);
+    dim3 grid((unsigned)n_cb, (unsigned)S, (unsigned)n_slabs);
+    bias_grad_kernel<T, V, VEC><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const T*>(gy), db, partial, counters, M,
+                                                                N, rps);
 }
 
 }  // namespace
@@ -228,12 +286,12 @@ int bf_linear_wgrad_f32(const float* gy, const float* x, float* dw, int64_t S, i
 }
 
 extern "C" int64_t bf_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N) {
-    int n_cb, n_slabs;
-    int64_t rps;
-    bias_grid(S < 1 ? 1 : S, M < 1 ? 1 : M, N < 1 ? 1 : N, n_cb, n_slabs, rps);
-    // [counters: S*n_cb uint32, padded to 256 B][partials: S*n_cb*n_slabs*64 floats]
-    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
-    return cnt + S * n_cb * (int64_t)n_slabs * kColsPerBlock * 4;
+    S = S < 1 ? 1 : S, M = M < 1 ? 1 : M, N = N < 1 ? 1 : N;
+    int64_t b = bias_ws_bytes(S, M, N, 64);  // large enough for whichever variant bf_bias_grad picks
+    const int64_t b4 = bias_ws_bytes(S, M, N, 128), b8 = bias_ws_bytes(S, M, N, 256);
+    if (b4 > b) b = b4;
+    if (b8 > b) b = b8;
+    return b;
 }
 
 extern "C" int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N,
@@ -241,20 +299,15 @@ extern "C" int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t
     BF_CHECK_ARG(gy && db && workspace, "null pointer");
     BF_CHECK_ARG(gy_dtype == BF_F32 || gy_dtype == BF_BF16, "bad dtype");
     if (S == 0 || N == 0) return 0;
-    int n_cb, n_slabs;
-    int64_t rps;
-    bias_grid(S, M < 1 ? 1 : M, N, n_cb, n_slabs, rps);
-    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
-    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
-    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + cnt);
-    dim3 grid((unsigned)n_cb, (unsigned)S, (unsigned)n_slabs);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (gy_dtype == BF_BF16)
-        bias_grad_kernel<__nv_bfloat16><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gy), db,
-                                                                        partial, counters, M, N, rps);
-    else
-        bias_grad_kernel<float><<<grid, kBiasThreads, 0, st>>>(reinterpret_cast<const float*>(gy), db, partial,
-                                                                counters, M, N, rps);
+    const bool al16 = (reinterpret_cast<uintptr_t>(gy) & 15u) == 0;
+    if (gy_dtype == BF_BF16) {
+        if (al16 && N % 8 == 0) launch_bias<__nv_bfloat16, 8, true>(gy, db, S, M, N, workspace, st);
+        else launch_bias<__nv_bfloat16, 2, false>(gy, db, S, M, N, workspace, st);
+    } else {
+        if (al16 && N % 4 == 0) launch_bias<float, 4, true>(gy, db, S, M, N, workspace, st);
+        else launch_bias<float, 2, false>(gy, db, S, M, N, workspace, st);
+    }
     BF_LAUNCH_OK();
     return 0;
 }

@@ -9,10 +9,10 @@ int bf_linear_wgrad_f32(const float*, const float*, float*, int64_t, int64_t, in
 int bf_linear_fwd_bf16(const void*, const void*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, cudaStream_t);
 int bf_linear_dgrad_bf16(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, cudaStream_t);
 int bf_linear_wgrad_bf16(const void*, const void*, float*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
-int64_t bf_wgrad_fused_workspace_ints(int64_t N, int64_t K);
+int64_t bf_wgrad_fused_workspace_bytes_impl(int64_t S, int64_t M, int64_t N, int64_t K, int with_mu);
 int bf_linear_wgrad_fused_bf16(const void*, const void*, int64_t, int64_t, int64_t, int64_t, const float*, const float*,
                                int32_t, const float*, const float*, float, float, float, const float*, const float*,
-                               uint64_t, uint32_t, uint32_t, const float*, float*, float*, int32_t, int*, cudaStream_t);
+                               uint64_t, uint32_t, uint32_t, const float*, float*, float*, int32_t, void*, cudaStream_t);
 
 #define BF_CHECK_SHAPE()                                                        \
     BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1"); \
@@ -64,8 +64,10 @@ extern "C" int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t
     return bf_linear_wgrad_bf16(gy, x, dw, S, M, N, K, st);
 }
 
-extern "C" int64_t bf_linear_wgrad_fused_workspace_bytes(int64_t N, int64_t K) {
-    return bf_wgrad_fused_workspace_ints(N, K) * (int64_t)sizeof(int);
+extern "C" int64_t bf_linear_wgrad_fused_workspace_bytes(int64_t S, int64_t M, int64_t N, int64_t K,
+                                                         int32_t with_grad_mu) {
+    if (S < 1 || M < 1 || N < 1 || K < 1) return 0;
+    return bf_wgrad_fused_workspace_bytes_impl(S, M, N, K, with_grad_mu);
 }
 
 extern "C" int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K,
@@ -82,5 +84,5 @@ extern "C" int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, i
     BF_CHECK_ARG(!kl || prior_kind != BF_PRIOR_GAUSSIAN || prior_mu, "gaussian prior needs prior_mu");
     return bf_linear_wgrad_fused_bf16(gy, x, S, M, N, K, mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2,
                                       g_logq, g_logp, seed, step, tensor_id, eps_in, grad_mu, grad_rho, accumulate,
-                                      reinterpret_cast<int*>(workspace), reinterpret_cast<cudaStream_t>(stream));
+                                      workspace, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -57,6 +57,10 @@ __device__ __forceinline__ void named_bar_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_sync_dyn(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

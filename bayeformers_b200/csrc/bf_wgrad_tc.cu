@@ -4,110 +4,100 @@
 // does in the reference for  w = mu + softplus(rho) * eps ;  y = F.linear(x, w)
 // (bayeformers/nn/parameters/gaussian.py:101, bayeformers/nn/layers/linear.py:104):
 //
-//     dW_s     = gy_s^T x_s                                  (tensor cores, never written to HBM)
-//     grad_mu  = sum_s dW_s
-//     grad_rho = sigmoid(rho) * sum_s dW_s o eps_s           (eps_s regenerated from the Philox counter)
+//     dW_s     = gy_s^T x_s                                  (tensor cores; the raw dW_s never reaches HBM
+//                                                             unless mu is trainable)
+//     grad_mu  = sum_s dW_s                      (+ KL terms)
+//     grad_rho = sigmoid(rho) * sum_s dW_s o eps_s  (+ KL terms; eps_s regenerated from the Philox counter)
 //
-// Structure: 128 x 128 output tiles, 5-stage TMA ring, tcgen05.mma into a
-// double-buffered TMEM accumulator.  The other half of TMEM holds two running
-// sums per tile (sum_s dW_s o eps_s and sum_s dW_s): after each sample's
-// contraction the epilogue warps pull the accumulator (tcgen05.ld), generate
-// the matching eps quads, FMA into the running sums and write them back with
-// tcgen05.st -- no global traffic per sample.  Only when the last sample of a
-// work item is done are the sums staged through shared memory and written
-// (or read-modify-written) to grad_rho / grad_mu with coalesced 128 B rows.
+// Two launches:
 //
-// Small layers do not have enough tiles to fill 148 SMs, so a tile may be cut
-// into several work items (groups of samples, then slices of the reduction).
-// Items of one tile add their contribution to global memory in a FIXED order
-// (turn counters), which keeps the result run-to-run deterministic without
-// float atomics.
+//  1. bayes_wgrad_kernel -- persistent, warp-specialised (1 TMA warp, 1 MMA warp,
+//     8 epilogue warps), 128 x 256 output tiles, 4-stage TMA ring, tcgen05.mma into
+//     a DOUBLE-BUFFERED TMEM accumulator (2 x 256 columns).  A work item is
+//     (sample s, reduction slice sp, tile): small layers (768 x 768 has only 18
+//     tiles) are cut along the reduction M = B*T so that every SM has work.  The
+//     epilogue of item i overlaps the MMAs of item i+1: it pulls the accumulator
+//     (tcgen05.ld), regenerates the matching eps quads with Philox, multiplies,
+//     stages the 128 x 32 fp32 box in swizzled shared memory and TMA-stores it to
+//     the partial buffer P[s*splits+sp][N][K].
+//  2. wgrad_reduce_kernel -- one coalesced pass: grad_rho = sigmoid(rho) *
+//     (sum_t P[t] + KL terms), in the FIXED order t = 0..T-1, so the result is
+//     run-to-run deterministic (no float atomics, no turn-taking between CTAs).
+//     The partials are written and re-read back to back; for BERT-sized layers
+//     they are L2-resident (<= 75 MB against 126 MB).
 #include "bf_tc.cuh"
-
-int bf_sample_kl_bwd_impl_kl_only(const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
-                                  const float* prior_rho, float pi, float sigma1, float sigma2, const float* g_logq,
-                                  const float* g_logp, int64_t n, int32_t S, uint64_t seed, uint32_t step,
-                                  uint32_t tensor_id, const float* eps_in, float* grad_mu, float* grad_rho,
-                                  cudaStream_t st);
 
 namespace wg {
 using namespace tc;
 
-constexpr int BM = 128;
-constexpr int EPI_COLS = 32, EPI_WARPS = 8;  // 2 warps per TMEM lane quarter, each owning half of the column chunks
+constexpr int BM = 128, BN = 256;
+constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BOX_COLS = 32;                 // fp32 columns of one TMA-store box (128 B rows)
+constexpr int BOX_BYTES = BM * 128;          // 16 KiB
+constexpr int BOXES = BN / BOX_COLS;         // 8
+constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS;  // group g owns boxes b with b % 2 == g
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
-constexpr int TMEM_COLS = 512;
+constexpr int TMEM_COLS = 2 * BN;
 
-// Two tile shapes (TMEM is 512 columns in both):
-//   BN = 256 (mu frozen, the MOPED fine-tuning case): [0,256) accumulator | [256,512) sum dW*eps.
-//            128x256 tiles have 1.37x the arithmetic intensity of 128x128 ones, which is what the
-//            L2->SM operand stream (measured ~11-14 TB/s with everything in flight) needs.
-//   BN = 128 (mu trainable): [0,128) acc0 | [128,256) acc1 | [256,384) sum dW*eps | [384,512) sum dW.
-template <int BN>
+template <bool WITH_MU>
 struct Cfg {
-    static constexpr int NACC = BN == 128 ? 2 : 1;
-    static constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int kStages = BN == 128 ? 6 : 4;
-    static constexpr int T_SUM_RHO = 256, T_SUM_MU = 384;
-    static constexpr int CHUNKS_PER_WARP = (BN / EPI_COLS) / 2;
-    static constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + 256;
+    static constexpr int kStages = WITH_MU ? 3 : 4;
+    static constexpr int BUFS = WITH_MU ? 2 : 1;  // staging boxes per epilogue group
+    static constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + EPI_GROUPS * BUFS * BOX_BYTES + 256;
 };
 
 struct Params {
     int64_t S, I, J, R;  // samples, rows of W (N), cols of W (K), reduction length (M)
-    int i_tiles, j_tiles, k_steps, groups, splits;
-    const float* rho;
+    int i_tiles, j_tiles, k_steps, splits;
     const float* eps_in;  // [S][I][J] injected eps or null
-    float* grad_mu;       // null when mu is frozen
-    float* grad_rho;
-    int* turn;            // [i_tiles*j_tiles], zero-initialised, self-resetting
-    int accumulate;
     uint32_t k0, k1, step, tensor_id;
     const uint32_t* step_ptr;  // optional device-resident offset added to `step`
 };
 
 struct Item {
-    int tile, turn, turns, i_blk, j_blk, s_begin, s_end, k_begin, k_end;
+    int s, sp, i_blk, j_blk, k_begin, k_end;
 };
 __device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
     Item it;
-    it.turns = p.groups * p.splits;
-    it.turn = (int)(L % it.turns);
-    it.tile = (int)(L / it.turns);
-    const int g = it.turn / p.splits, sp = it.turn % p.splits;
-    it.j_blk = it.tile % p.j_tiles;
-    it.i_blk = it.tile / p.j_tiles;
-    it.s_begin = (int)((p.S * g) / p.groups);
-    it.s_end = (int)((p.S * (g + 1)) / p.groups);
-    it.k_begin = (int)(((int64_t)p.k_steps * sp) / p.splits);
-    it.k_end = (int)(((int64_t)p.k_steps * (sp + 1)) / p.splits);
+    it.j_blk = (int)(L % p.j_tiles);
+    int64_t q = L / p.j_tiles;
+    it.i_blk = (int)(q % p.i_tiles);
+    q /= p.i_tiles;
+    it.sp = (int)(q % p.splits);
+    it.s = (int)(q / p.splits);
+    it.k_begin = (int)(((int64_t)p.k_steps * it.sp) / p.splits);
+    it.k_end = (int)(((int64_t)p.k_steps * (it.sp + 1)) / p.splits);
     return it;
 }
 
-template <int BN, bool HAS_EPS, bool WITH_MU>
+template <bool HAS_EPS, bool WITH_MU>
 __global__ void __launch_bounds__(kThreads, 1)
     bayes_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
+                       const __grid_constant__ CUtensorMap map_prho, const __grid_constant__ CUtensorMap map_pmu,
                        const __grid_constant__ Params p) {
-    using C = Cfg<BN>;
-    static_assert(!(WITH_MU && BN != 128), "the mu sum only fits next to 128-column accumulators");
-    constexpr int kStages = C::kStages, NACC = C::NACC;
+    using C = Cfg<WITH_MU>;
+    constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + kStages * C::STAGE_BYTES;
+    const uint32_t out_base = smem_base + kStages * STAGE_BYTES;
+    uint8_t* const out_gen = smem_gen + kStages * STAGE_BYTES;
+    constexpr int OUT_BYTES = EPI_GROUPS * C::BUFS * BOX_BYTES;
+    const uint32_t bar_base = out_base + OUT_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
     volatile uint32_t* const tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * C::STAGE_BYTES + 8 * (2 * kStages + 4));
+        reinterpret_cast<volatile uint32_t*>(out_gen + OUT_BYTES + 8 * (2 * kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_gy);
         tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_prho);
+        if (WITH_MU) tma_prefetch_desc(&map_pmu);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -124,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
-    const int64_t n_items = (int64_t)p.i_tiles * p.j_tiles * p.groups * p.splits;
+    const int64_t n_items = p.S * p.splits * p.i_tiles * p.j_tiles;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -134,21 +124,19 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
                 const Item it = decode_item(p, L);
                 const int i0 = it.i_blk * BM, j0 = it.j_blk * BN;
-                for (int s = it.s_begin; s < it.s_end; ++s) {
-                    for (int ks = it.k_begin; ks < it.k_end; ++ks) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-                        const uint32_t b_dst = a_dst + C::A_BYTES;
-                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                        const int r0 = ks * BLOCK_K;
+                for (int ks = it.k_begin; ks < it.k_end; ++ks) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_BYTES;
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const int r0 = ks * BLOCK_K;
 #pragma unroll
-                        for (int a = 0; a < BM / ATOM_MN; ++a)  // gy[s][m][n]: MN-major, rows = reduction m
-                            tma_load_3d(a_dst + a * ATOM_BYTES, &map_gy, full_bar(stage), i0 + a * ATOM_MN, r0, s);
+                    for (int a = 0; a < BM / ATOM_MN; ++a)  // gy[s][m][n]: MN-major, rows = reduction m
+                        tma_load_3d(a_dst + a * ATOM_BYTES, &map_gy, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
 #pragma unroll
-                        for (int a = 0; a < BN / ATOM_MN; ++a)  // x[s][m][k]
-                            tma_load_3d(b_dst + a * ATOM_BYTES, &map_x, full_bar(stage), j0 + a * ATOM_MN, r0, s);
-                        if (++stage == kStages) stage = 0, phase ^= 1u;
-                    }
+                    for (int a = 0; a < BN / ATOM_MN; ++a)  // x[s][m][k]
+                        tma_load_3d(b_dst + a * ATOM_BYTES, &map_x, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
             }
         }
@@ -158,165 +146,113 @@ __global__ void __launch_bounds__(kThreads, 1)
             constexpr uint32_t idesc = make_idesc(true, true, BM, BN);
             int stage = 0;
             uint32_t phase = 0;
-            int iter = 0;  // counts (item, sample) pairs
-            for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
+            int iter = 0;
+            for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x, ++iter) {
                 const Item it = decode_item(p, L);
-                for (int s = it.s_begin; s < it.s_end; ++s, ++iter) {
-                    const int acc = iter % NACC;
-                    const uint32_t acc_phase = (iter / NACC) & 1;
-                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int ks = it.k_begin; ks < it.k_end; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int ks = it.k_begin; ks < it.k_end; ++ks) {
-                        mbar_wait(full_bar(stage), phase);
-                        tc_fence_after();
-                        const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
-                        const uint32_t b_src = a_src + C::A_BYTES;
+                    const uint32_t a_src = smem_base + stage * STAGE_BYTES;
+                    const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc,
-                                      (ks > it.k_begin || k > 0) ? 1u : 0u);
-                        umma_commit(empty_bar(stage));
-                        if (++stage == kStages) stage = 0, phase ^= 1u;
-                    }
-                    umma_commit(tfull_bar(acc));
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc,
+                                  (ks > it.k_begin || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(stage));
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
+                umma_commit(tfull_bar(acc));
             }
         }
     } else {
         // ===================== epilogue warps =====================
-        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the
-        // column chunks, and two warps per scheduler hide each other's dependency stalls
+        // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule); epilogue group g = (warp-2)/4 takes the
+        // boxes b with b % 2 == g, so the two warps that share a quarter split a tile's columns evenly.
         const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const bool store_thread = ((warp - 2) & 3) == 0 && lane == 0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t my_out = out_base + grp * C::BUFS * BOX_BYTES;
+        uint8_t* const my_out_gen = out_gen + grp * C::BUFS * BOX_BYTES;
         int iter = 0;
-        for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
+        for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x, ++iter) {
             const Item it = decode_item(p, L);
-            const int64_t j_base = (int64_t)it.j_blk * BN;
-            const int64_t my_row = (int64_t)it.i_blk * BM + q * 32 + lane;
-            const bool row_ok = my_row < p.I;
-            int n_chunks = BN / EPI_COLS;  // warp-uniform
-            if (j_base + BN > p.J) n_chunks = (int)((p.J - j_base + EPI_COLS - 1) / EPI_COLS);
-            const int c_lo = half * C::CHUNKS_PER_WARP;
-            const int c_hi = min(n_chunks, c_lo + C::CHUNKS_PER_WARP);
-
-            // ---- per sample: sums (TMEM) += accumulator (TMEM) o eps (registers) ----
-            for (int s = it.s_begin; s < it.s_end; ++s, ++iter) {
-                const int acc = iter % NACC;
-                const uint32_t acc_phase = (iter / NACC) & 1;
-                const bool first = (s == it.s_begin);
-                mbar_wait(tfull_bar(acc), acc_phase);
-                tc_fence_after();
-                {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int i0 = it.i_blk * BM, j0 = it.j_blk * BN;
+            const int64_t g_row = (int64_t)i0 + row;
+            const bool row_ok = g_row < p.I;
+            int n_boxes = BOXES;  // boxes that intersect the matrix
+            if ((int64_t)j0 + BN > p.J) n_boxes = (int)((p.J - j0 + BOX_COLS - 1) / BOX_COLS);
+            const int out_z = it.s * p.splits + it.sp;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            int last_b = -1;  // last box of this group
+            for (int b = grp; b < n_boxes; b += EPI_GROUPS) last_b = b;
+            if (last_b < 0) {  // nothing to read: hand the accumulator straight back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
 #pragma unroll 1
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        uint32_t a[32], sr[32], sm[32];
-                        tmem_ld_32x32(lane_base + (uint32_t)(acc * BN + c * EPI_COLS), a);
-                        if (!first) {
-                            tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), sr);
-                            if (WITH_MU) tmem_ld_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), sm);
-                        }
-                        float e[32];
-                        const int64_t flat = my_row * p.J + j_base + c * EPI_COLS;
-                        if (row_ok) {
+            for (int b = grp; b < n_boxes; b += EPI_GROUPS) {
+                uint32_t r[32];
+                tmem_ld_32x32(lane_base + (uint32_t)(acc * BN + b * BOX_COLS), r);
+                // eps of this thread's 32 elements (row g_row, columns jc .. jc+31) while the TMEM load is in flight
+                const int64_t jc = (int64_t)j0 + b * BOX_COLS;
+                const int64_t flat = g_row * p.J + jc;
+                float e[32];
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                float4 v;
-                                if (HAS_EPS) {
-                                    v = (j_base + c * EPI_COLS + 4 * t + 4 <= p.J)
-                                            ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)s * p.I * p.J +
-                                                                                     flat + 4 * t))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                                } else {
-                                    v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
-                                }
-                                e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 32; ++t) e[t] = 0.0f;
-                        }
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const float av = __uint_as_float(a[t]);
-                            const float prev = first ? 0.0f : __uint_as_float(sr[t]);
-                            sr[t] = __float_as_uint(fmaf(av, e[t], prev));
-                            if (WITH_MU) sm[t] = __float_as_uint(first ? av : __uint_as_float(sm[t]) + av);
-                        }
-                        tmem_st_32x32(lane_base + (uint32_t)(C::T_SUM_RHO + c * EPI_COLS), sr);
-                        if (WITH_MU) tmem_st_32x32(lane_base + (uint32_t)(C::T_SUM_MU + c * EPI_COLS), sm);
+                for (int t = 0; t < 8; ++t) {
+                    float4 v;
+                    if (HAS_EPS) {
+                        v = (row_ok && jc + 4 * t + 4 <= p.J)
+                                ? __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)it.s * p.I * p.J + flat + 4 * t))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        v = bf_eps_quad((uint32_t)((flat >> 2) + t), (uint32_t)it.s, p.tensor_id, step, p.k0, p.k1);
                     }
-                    tmem_st_wait();
+                    e[4 * t] = v.x, e[4 * t + 1] = v.y, e[4 * t + 2] = v.z, e[4 * t + 3] = v.w;
+                }
+                tmem_ld_wait();
+                if (b == last_b) {  // accumulator drained by this warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
-            }
-
-            // ---- once per item: -> global gradients, items of one tile in fixed turn order ----
-            if (it.turns > 1) {
-                if (lane == 0) {
-                    const volatile int* t = p.turn + it.tile;
-                    while (*t != it.turn) __nanosleep(64);
-                    __threadfence();
-                }
-                __syncwarp();
-            }
-            const bool add = (it.turn > 0) || p.accumulate;
-#pragma unroll 1
-            for (int kind = 0; kind < (WITH_MU ? 2 : 1); ++kind) {  // 0: grad_rho (x sigmoid(rho)), 1: grad_mu
-                float* const dst = kind == 0 ? p.grad_rho : p.grad_mu;
-                const int t_off = kind == 0 ? C::T_SUM_RHO : C::T_SUM_MU;
-#pragma unroll 1
-                for (int c = c_lo; c < c_hi; ++c) {
-                    uint32_t r[32];
-                    const int64_t jc = j_base + c * EPI_COLS;
-                    const int64_t flat = my_row * p.J + jc;
-                    tmem_ld_32x32(lane_base + (uint32_t)(t_off + c * EPI_COLS), r);
-                    // thread = one row of W, 32 consecutive columns = one full 128 B line per thread.
-                    // All loads of the chunk are issued before any store (the compiler cannot hoist the
-                    // read-modify-write loads above stores to the same array on its own).
-                    float4 scale[8], old[8];
+                if (store_thread) tma_store_wait_read<0>();  // the previous store of this group has read its buffer
+                named_bar_sync_dyn(1 + grp, 128);
+                uint8_t* const my_row = my_out_gen + row * 128;
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        const bool in = row_ok && (jc + 4 * v + 4 <= p.J);  // J % 4 == 0
-                        scale[v] = (in && kind == 0) ? __ldg(reinterpret_cast<const float4*>(p.rho + flat + 4 * v))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                        old[v] = (in && add) ? __ldcg(reinterpret_cast<const float4*>(dst + flat + 4 * v))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    tmem_ld_wait();  // warp-collective: must stay outside any lane-divergent branch
+                for (int ch = 0; ch < 8; ++ch)  // 8 x 16 B chunks, XOR-swizzled by (row % 8) like the TMA box
+                    *reinterpret_cast<float4*>(my_row + ((ch ^ (row & 7)) << 4)) =
+                        make_float4(__uint_as_float(r[4 * ch]) * e[4 * ch], __uint_as_float(r[4 * ch + 1]) * e[4 * ch + 1],
+                                    __uint_as_float(r[4 * ch + 2]) * e[4 * ch + 2],
+                                    __uint_as_float(r[4 * ch + 3]) * e[4 * ch + 3]);
+                if (WITH_MU) {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        if (row_ok && jc + 4 * v + 4 <= p.J) {
-                            float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-                            if (kind == 0) {
-                                g.x = bf_softplus_grad(scale[v].x), g.y = bf_softplus_grad(scale[v].y);
-                                g.z = bf_softplus_grad(scale[v].z), g.w = bf_softplus_grad(scale[v].w);
-                            }
-                            float4 o;
-                            o.x = fmaf(__uint_as_float(r[4 * v + 0]), g.x, old[v].x);
-                            o.y = fmaf(__uint_as_float(r[4 * v + 1]), g.y, old[v].y);
-                            o.z = fmaf(__uint_as_float(r[4 * v + 2]), g.z, old[v].z);
-                            o.w = fmaf(__uint_as_float(r[4 * v + 3]), g.w, old[v].w);
-                            __stcg(reinterpret_cast<float4*>(dst + flat + 4 * v), o);
-                        }
-                    }
+                    for (int ch = 0; ch < 8; ++ch)
+                        *reinterpret_cast<float4*>(my_row + BOX_BYTES + ((ch ^ (row & 7)) << 4)) =
+                            make_float4(__uint_as_float(r[4 * ch]), __uint_as_float(r[4 * ch + 1]),
+                                        __uint_as_float(r[4 * ch + 2]), __uint_as_float(r[4 * ch + 3]));
                 }
-            }
-            if (it.turns > 1) {
-                __threadfence();
-                named_bar_sync<1, EPI_WARPS * 32>();
-                if (warp == 2 && lane == 0) {
-                    const int next = (it.turn + 1 == it.turns) ? 0 : it.turn + 1;
-                    __threadfence();
-                    atomicExch(p.turn + it.tile, next);
+                fence_proxy_async();
+                named_bar_sync_dyn(1 + grp, 128);
+                if (store_thread) {
+                    tma_store_3d(&map_prho, my_out, (int)jc, i0, out_z);
+                    if (WITH_MU) tma_store_3d(&map_pmu, my_out + BOX_BYTES, (int)jc, i0, out_z);
+                    tma_store_commit();
                 }
             }
         }
+        if (store_thread) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -327,61 +263,226 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
-template <int BN, bool HAS_EPS, bool WITH_MU>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t st) {
-    auto kern = bayes_wgrad_kernel<BN, HAS_EPS, WITH_MU>;
-    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-    const int64_t n_items = (int64_t)p.i_tiles * p.j_tiles * p.groups * p.splits;
+template <bool HAS_EPS, bool WITH_MU>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mm,
+                  const Params& p, cudaStream_t st) {
+    auto kern = bayes_wgrad_kernel<HAS_EPS, WITH_MU>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<WITH_MU>::SMEM_BYTES));
+    const int64_t n_items = p.S * p.splits * p.i_tiles * p.j_tiles;
     const int64_t sms = bf_num_sms();
-    kern<<<(int)(n_items < sms ? n_items : sms), kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ma, mb, p);
+    kern<<<(int)(n_items < sms ? n_items : sms), kThreads, Cfg<WITH_MU>::SMEM_BYTES, st>>>(ma, mb, mr, mm, p);
     BF_LAUNCH_OK();
     return 0;
 }
 
+// ---- how many slices of the reduction: fill the persistent grid, keep items long enough that the
+// Philox epilogue (~10 us per 128x256 tile) stays hidden behind the next item's MMAs (0.22 us per k-step at peak)
+static int choose_splits(int64_t S, int64_t tiles, int k_steps) {
+    const int64_t sms = bf_num_sms();
+    const int64_t base = S * tiles;
+    const double fixed = 14.0;  // per-item overhead in k-step units (pipeline fill + exposed part of the epilogue)
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sp = 1; sp <= 16; ++sp) {
+        if (sp > 1 && k_steps / sp < 24) break;
+        const int64_t waves = (base * sp + sms - 1) / sms;
+        const double cost = (double)waves * ((double)((k_steps + sp - 1) / sp) + fixed) + 0.5 * sp;
+        if (cost < best_cost - 1e-9) best_cost = cost, best = sp;
+    }
+    return best;
+}
+
+constexpr int kRedThreads = 256;
+
+struct ReduceParams {
+    const float* part_rho;  // [T][n]
+    const float* part_mu;   // [T][n] or null
+    int T;
+    const float* mu;
+    const float* rho;
+    const float* prior_mu;
+    const float* prior_rho;
+    const float* g_logq;
+    const float* g_logp;
+    const float* eps_in;
+    float* grad_mu;
+    float* grad_rho;
+    int64_t n;
+    int S, accumulate;
+    uint32_t k0, k1, step, tensor_id;
+    const uint32_t* step_ptr;
+    float prior_const_ipv;
+    BfMixture mix;
+};
+
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+// grad_rho = sigmoid(rho) * (sum_t P_rho[t] + sum_s KL_s),  grad_mu = sum_t P_mu[t] + sum_s g_logp[s] dlogp/dw(w_s)
+// n % 4 == 0 (N*K with K % 8 == 0), all pointers 16 B aligned (torch allocations)
+template <int PRIOR, bool KL>
+__global__ void __launch_bounds__(kRedThreads) wgrad_reduce_kernel(const ReduceParams p) {
+    const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
+    const int64_t nquad = p.n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kRedThreads;
+    for (int64_t q = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; q < nquad; q += stride) {
+        const int64_t i0 = q << 2;
+        float4 ar = make_float4(0.f, 0.f, 0.f, 0.f), am = ar;
+        {
+            const float* src = p.part_rho + i0;
+            int t = 0;
+            for (; t + 4 <= p.T; t += 4) {  // 4 independent loads in flight, summed in fixed order
+                const float4 a = ld4s(src + (int64_t)t * p.n), b = ld4s(src + (int64_t)(t + 1) * p.n);
+                const float4 c = ld4s(src + (int64_t)(t + 2) * p.n), d = ld4s(src + (int64_t)(t + 3) * p.n);
+                ar.x += a.x, ar.y += a.y, ar.z += a.z, ar.w += a.w;
+                ar.x += b.x, ar.y += b.y, ar.z += b.z, ar.w += b.w;
+                ar.x += c.x, ar.y += c.y, ar.z += c.z, ar.w += c.w;
+                ar.x += d.x, ar.y += d.y, ar.z += d.z, ar.w += d.w;
+            }
+            for (; t < p.T; ++t) {
+                const float4 a = ld4s(src + (int64_t)t * p.n);
+                ar.x += a.x, ar.y += a.y, ar.z += a.z, ar.w += a.w;
+            }
+        }
+        if (p.grad_mu != nullptr && p.part_mu != nullptr) {
+            const float* src = p.part_mu + i0;
+            for (int t = 0; t < p.T; ++t) {
+                const float4 a = ld4s(src + (int64_t)t * p.n);
+                am.x += a.x, am.y += a.y, am.z += a.z, am.w += a.w;
+            }
+        }
+        const float4 rho4 = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+        const float rho[4] = {rho4.x, rho4.y, rho4.z, rho4.w};
+        float arv[4] = {ar.x, ar.y, ar.z, ar.w}, amv[4] = {am.x, am.y, am.z, am.w};
+        if (KL) {
+            const float4 mu4 = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
+            const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+            float sigma[4], pmu[4] = {0.f, 0.f, 0.f, 0.f}, inv_pvar[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sigma[j] = bf_softplus(rho[j]);
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
+                pmu[0] = v.x, pmu[1] = v.y, pmu[2] = v.z, pmu[3] = v.w;
+                if (p.prior_rho != nullptr) {
+                    const float4 pr = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
+                    const float prho[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float sp = bf_softplus(prho[j]);
+                        inv_pvar[j] = 1.0f / (sp * sp);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) inv_pvar[j] = p.prior_const_ipv;
+                }
+            }
+            float glq_sum = 0.0f;
+            for (int s = 0; s < p.S; ++s) {
+                float4 ev;
+                if (p.eps_in != nullptr)
+                    ev = __ldg(reinterpret_cast<const float4*>(p.eps_in + (int64_t)s * p.n + i0));
+                else
+                    ev = bf_eps_quad((uint32_t)q, (uint32_t)s, p.tensor_id, step, p.k0, p.k1);
+                const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+                const float glq = p.g_logq ? __ldg(p.g_logq + s) : 0.0f;
+                const float glp = p.g_logp ? __ldg(p.g_logp + s) : 0.0f;
+                glq_sum += glq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float w = __fadd_rn(mu[j], __fmul_rn(e[j], sigma[j]));
+                    float dp = 0.0f;
+                    if (PRIOR == BF_PRIOR_MIXTURE) dp = bf_mixture_dlogp(w, p.mix);
+                    if (PRIOR == BF_PRIOR_GAUSSIAN) dp = -(w - pmu[j]) * inv_pvar[j];
+                    const float gj = glp * dp;  // chain through w (both the mu and the sigma*eps path)
+                    amv[j] += gj;
+                    arv[j] += gj * e[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) arv[j] -= glq_sum / sigma[j];  // d log q / d sigma = -1/sigma, per sample
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) arv[j] *= bf_softplus_grad(rho[j]);
+        float4 o = make_float4(arv[0], arv[1], arv[2], arv[3]);
+        if (p.accumulate) {
+            const float4 a = *reinterpret_cast<const float4*>(p.grad_rho + i0);
+            o.x += a.x, o.y += a.y, o.z += a.z, o.w += a.w;
+        }
+        *reinterpret_cast<float4*>(p.grad_rho + i0) = o;
+        if (p.grad_mu != nullptr) {
+            float4 m = make_float4(amv[0], amv[1], amv[2], amv[3]);
+            if (p.accumulate) {
+                const float4 a = *reinterpret_cast<const float4*>(p.grad_mu + i0);
+                m.x += a.x, m.y += a.y, m.z += a.z, m.w += a.w;
+            }
+            *reinterpret_cast<float4*>(p.grad_mu + i0) = m;
+        }
+    }
+}
+
 }  // namespace wg
 
-int64_t bf_wgrad_fused_workspace_ints(int64_t N, int64_t K) {
-    return (int64_t)tc::cdiv(N, wg::BM) * tc::cdiv(K, 128);  // enough for either tile width
+static int64_t wgrad_partials(int64_t S, int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = (int64_t)tc::cdiv(N, wg::BM) * tc::cdiv(K, wg::BN);
+    return S * wg::choose_splits(S, tiles, tc::cdiv(M, tc::BLOCK_K));
+}
+
+int64_t bf_wgrad_fused_workspace_bytes_impl(int64_t S, int64_t M, int64_t N, int64_t K, int with_mu) {
+    return wgrad_partials(S, M, N, K) * N * K * (int64_t)sizeof(float) * (with_mu ? 2 : 1);
 }
 
 int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K,
                                const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
                                const float* prior_rho, float pi, float sigma1, float sigma2, const float* g_logq,
                                const float* g_logp, uint64_t seed, uint32_t step, uint32_t tensor_id,
-                               const float* eps_in, float* grad_mu, float* grad_rho, int32_t accumulate, int* turn_ws,
-                               cudaStream_t st) {
+                               const float* eps_in, float* grad_mu, float* grad_rho, int32_t accumulate,
+                               void* workspace, cudaStream_t st) {
     using namespace wg;
     BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "bf16 path needs K % 8 == 0 and N % 8 == 0");
-    BF_CHECK_ARG(turn_ws != nullptr, "turn workspace missing");
-    CUtensorMap ma, mb;
+    BF_CHECK_ARG(workspace != nullptr, "workspace missing");
+    BF_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 127u) == 0, "workspace must be 128 B aligned");
+    const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
+    Params p{};
+    p.S = S, p.I = N, p.J = K, p.R = M;
+    p.i_tiles = tc::cdiv(N, BM), p.j_tiles = tc::cdiv(K, BN), p.k_steps = tc::cdiv(M, tc::BLOCK_K);
+    p.splits = choose_splits(S, (int64_t)p.i_tiles * p.j_tiles, p.k_steps);
+    p.eps_in = eps_in;
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
+    p.step_ptr = bf_step_counter();
+    const int64_t T = S * p.splits;
+    float* const part_rho = reinterpret_cast<float*>(workspace);
+    float* const part_mu = with_mu ? part_rho + T * N * K : nullptr;
+
+    CUtensorMap ma, mb, mr, mm;
     int rc;
     if ((rc = tc::encode_map(&ma, gy, S, M, N, tc::BLOCK_K))) return rc;
     if ((rc = tc::encode_map(&mb, x, S, M, K, tc::BLOCK_K))) return rc;
-    const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
-    const int bn = with_mu ? 128 : 256;
-    Params p{};
-    p.S = S, p.I = N, p.J = K, p.R = M;
-    p.i_tiles = tc::cdiv(N, BM), p.j_tiles = tc::cdiv(K, bn), p.k_steps = tc::cdiv(M, tc::BLOCK_K);
-    // fill the persistent grid: first cut a tile by groups of samples (each (element, sample) eps is still
-    // generated exactly once), then by slices of the reduction (eps regenerated per slice)
-    const int64_t tiles = (int64_t)p.i_tiles * p.j_tiles;
-    const int64_t sms = bf_num_sms();
-    int groups = 1, splits = 1;
-    while (tiles * groups * 2 <= sms && groups * 2 <= S) groups *= 2;
-    while (tiles * groups * splits * 2 <= sms && p.k_steps / (splits * 2) >= 16) splits *= 2;
-    p.groups = groups, p.splits = splits;
-    p.rho = rho, p.eps_in = eps_in, p.grad_mu = grad_mu, p.grad_rho = grad_rho, p.turn = turn_ws;
-    p.accumulate = accumulate;
-    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
-    p.step_ptr = bf_step_counter();
+    if ((rc = tc::encode_map(&mr, part_rho, T, N, K, BM, true))) return rc;
+    if ((rc = tc::encode_map(&mm, with_mu ? part_mu : part_rho, T, N, K, BM, true))) return rc;
     if (with_mu)
-        rc = eps ? launch<128, true, true>(ma, mb, p, st) : launch<128, false, true>(ma, mb, p, st);
+        rc = eps ? launch<true, true>(ma, mb, mr, mm, p, st) : launch<false, true>(ma, mb, mr, mm, p, st);
     else
-        rc = eps ? launch<256, true, false>(ma, mb, p, st) : launch<256, false, false>(ma, mb, p, st);
+        rc = eps ? launch<true, false>(ma, mb, mr, mm, p, st) : launch<false, false>(ma, mb, mr, mm, p, st);
     if (rc) return rc;
-    // KL terms do not involve gy: they are one elementwise pass added on top (eps regenerated once more)
-    if (g_logq != nullptr || g_logp != nullptr)
-        return bf_sample_kl_bwd_impl_kl_only(mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2, g_logq, g_logp,
-                                             N * K, (int32_t)S, seed, step, tensor_id, eps_in, grad_mu, grad_rho, st);
+
+    ReduceParams r{};
+    r.part_rho = part_rho, r.part_mu = part_mu, r.T = (int)T;
+    r.mu = mu, r.rho = rho, r.prior_mu = prior_mu, r.prior_rho = prior_rho, r.g_logq = g_logq, r.g_logp = g_logp;
+    r.eps_in = eps_in, r.grad_mu = grad_mu, r.grad_rho = grad_rho, r.n = N * K, r.S = (int)S, r.accumulate = accumulate;
+    r.k0 = p.k0, r.k1 = p.k1, r.step = step, r.tensor_id = tensor_id, r.step_ptr = p.step_ptr;
+    r.prior_const_ipv = 1.0f / (sigma1 * sigma1);
+    r.mix = bf_make_mixture(pi, sigma1, sigma2);
+    const int64_t nquad = r.n >> 2;
+    const int64_t want = (nquad + kRedThreads - 1) / kRedThreads, cap = (int64_t)bf_num_sms() * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    const bool kl = g_logq != nullptr || g_logp != nullptr;
+    if (!kl)
+        wgrad_reduce_kernel<BF_PRIOR_NONE, false><<<grid, kRedThreads, 0, st>>>(r);
+    else if (prior_kind == BF_PRIOR_MIXTURE)
+        wgrad_reduce_kernel<BF_PRIOR_MIXTURE, true><<<grid, kRedThreads, 0, st>>>(r);
+    else if (prior_kind == BF_PRIOR_GAUSSIAN)
+        wgrad_reduce_kernel<BF_PRIOR_GAUSSIAN, true><<<grid, kRedThreads, 0, st>>>(r);
+    else
+        wgrad_reduce_kernel<BF_PRIOR_NONE, true><<<grid, kRedThreads, 0, st>>>(r);
+    BF_LAUNCH_OK();
     return 0;
 }

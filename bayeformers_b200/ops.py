@@ -331,7 +331,8 @@ class BayesLinear(torch.autograd.Function):
                 g_wrho = torch.empty_like(w_rho, dtype=torch.float32)
                 g_wmu = torch.empty_like(w_rho, dtype=torch.float32) if need_wmu else None
                 eps = _eps_arg(spec.w_stream, S, N * K, dev)
-                ws = _workspace("wgrad_turn", dev, lib.bf_linear_wgrad_fused_workspace_bytes(N, K))
+                ws = _workspace("wgrad_partials", dev,
+                                lib.bf_linear_wgrad_fused_workspace_bytes(S, M, N, K, int(need_wmu)))
                 pk = w_prior.kind
                 rc = _timed("gemm_wgrad_fused_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_wgrad_fused(
                     _ptr(gyc), _ptr(xg), S, M, N, K, BF_BF16, _ptr(w_mu), _ptr(w_rho), pk,
@@ -340,7 +341,7 @@ class BayesLinear(torch.autograd.Function):
                     _ptr(glq), _ptr(glp), spec.w_stream.seed, spec.w_stream.step, spec.w_stream.tensor_id, _ptr(eps),
                     _ptr(g_wmu), _ptr(g_wrho), 0, _ptr(ws), st))
                 _lib.check(rc, "bf_linear_wgrad_fused")
-                stats["launches"] += 1
+                stats["launches"] += 2  # contraction + fixed-order reduction
             else:
                 dW = torch.empty((S, N, K), dtype=torch.float32, device=dev)
                 rc = _timed("gemm_wgrad_f32", 2.0 * S * M * N * K, dev,

@@ -142,15 +142,18 @@ int bf_linear_dgrad(const void* gy, const void* w, void* dx, int64_t S, int64_t 
 int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t M, int64_t N, int64_t K,
                     int32_t dtype, void* stream);
 
-/* wgrad with the variational backward fused into its epilogue: the S weight
- * gradients never reach HBM.  Per output tile and sample the accumulator is
- * combined with a regenerated eps tile:
- *   grad_mu  (+)= sum_s dw[s]                     (skipped when grad_mu == NULL)
- *   grad_rho (+)= sigmoid(rho) * sum_s dw[s]*eps_s  (+ the KL terms as in bf_sample_kl_bwd)
+/* wgrad with the variational backward fused into its epilogue: the raw weight
+ * gradients of the S samples never reach HBM (unless mu is trainable).  The
+ * tensor-core epilogue regenerates the eps tile of each (sample, output tile)
+ * and emits dW_s o eps_s; a fixed-order reduction pass then forms
+ *   grad_mu  (+)= sum_s dw[s]                        (skipped when grad_mu == NULL)
+ *   grad_rho (+)= sigmoid(rho) * sum_s dw[s]*eps_s   (+ the KL terms as in bf_sample_kl_bwd)
  * mu/rho/prior/eps arguments as in bf_sample_kl_bwd, n == N*K.
- * workspace: bf_linear_wgrad_fused_workspace_bytes(N, K) bytes, zero-filled once
- * (per-output-tile turn counters, self-resetting). dtype must be BF_BF16. */
-int64_t bf_linear_wgrad_fused_workspace_bytes(int64_t N, int64_t K);
+ * workspace: bf_linear_wgrad_fused_workspace_bytes(S, M, N, K, grad_mu != NULL) bytes,
+ * 128 B aligned, contents irrelevant (per-(sample, reduction-slice) partial products;
+ * written and consumed inside the call).  dtype must be BF_BF16.  Deterministic:
+ * no float atomics, partials are summed in a fixed order. */
+int64_t bf_linear_wgrad_fused_workspace_bytes(int64_t S, int64_t M, int64_t N, int64_t K, int32_t with_grad_mu);
 int bf_linear_wgrad_fused(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K, int32_t dtype,
                           const float* mu, const float* rho, int32_t prior_kind, const float* prior_mu,
                           const float* prior_rho, float pi, float sigma1, float sigma2, const float* g_logq,

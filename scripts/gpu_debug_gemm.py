@@ -80,7 +80,7 @@ if __name__ == "__main__":
         gy = torch.randn(S, M, N, device=DEV).bfloat16(); b = torch.randn(S, N, device=DEV)
         y = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16); dx = torch.empty(S, M, K, device=DEV, dtype=torch.bfloat16)
         rho = torch.full((N, K), -5.0, device=DEV); g_rho = torch.empty(N, K, device=DEV)
-        ws = torch.zeros(lib.bf_linear_wgrad_fused_workspace_bytes(N, K), dtype=torch.uint8, device=DEV)
+        ws = torch.empty(lib.bf_linear_wgrad_fused_workspace_bytes(S, M, N, K, 0), dtype=torch.uint8, device=DEV)
         fl = 2 * S * M * N * K / 1e9
         r = {}
         r["fwd"] = t_ms(lambda: lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st))

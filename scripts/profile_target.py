@@ -31,7 +31,7 @@ gy = torch.randn(S, M, N, device=DEV).bfloat16()
 y = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16); dx = torch.empty(S, M, K, device=DEV, dtype=torch.bfloat16)
 mu2 = torch.randn(N, K, device=DEV) * 0.02; rho2 = torch.full((N, K), -5.0, device=DEV)
 g_rho = torch.empty(N, K, device=DEV)
-ws = torch.zeros(lib.bf_linear_wgrad_fused_workspace_bytes(N, K), dtype=torch.uint8, device=DEV)
+ws = torch.empty(lib.bf_linear_wgrad_fused_workspace_bytes(S, M, N, K, 0), dtype=torch.uint8, device=DEV)
 for _ in range(2):
     lib.bf_linear_fwd(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
     lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)

@@ -465,7 +465,7 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
     _lib.check(lib.bf_linear_wgrad(gy.data_ptr(), x.data_ptr(), dw.data_ptr(), S, M, N, K, BF_BF16, st), "wgrad")
     want_mu, want_rho = ops.sample_kl_backward(dw.view(S, -1), mu, rho, prior, stream, S, glq, glp, True)
     g_mu, g_rho = torch.empty_like(mu), torch.empty_like(mu)
-    ws = torch.zeros(lib.bf_linear_wgrad_fused_workspace_bytes(N, K), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.bf_linear_wgrad_fused_workspace_bytes(S, M, N, K, 1), dtype=torch.uint8, device=DEV)
 
     def fused(acc):
         _lib.check(lib.bf_linear_wgrad_fused(
@@ -476,15 +476,14 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
 
     fused(0)
     # both sides are fp32 sums of the same products in different association orders
-    # (the fused kernel splits the reduction over up to 8 CTAs): 1e-5 is fp32 noise here
+    # (the fused kernel may cut the reduction into slices): 1e-5 is fp32 noise here
     assert rel_err(g_rho.cpu().numpy(), want_rho.cpu().numpy()) < 1e-5
     assert rel_err(g_mu.cpu().numpy(), want_mu.cpu().numpy()) < 1e-5
     first = g_rho.clone()
     fused(0)
-    assert torch.equal(first, g_rho), "turn-ordered accumulation must be run-to-run deterministic"
+    assert torch.equal(first, g_rho), "fixed-order reduction of the partials must be run-to-run deterministic"
     fused(1)  # accumulate into existing gradients
     assert rel_err(g_rho.cpu().numpy(), 2 * want_rho.cpu().numpy()) < 1e-5
-    assert int(ws.view(torch.int32).abs().sum()) == 0  # turn counters reset themselves
 
 
 # ------------------------------------------------------------------ Embedding / LayerNorm (rows A9 / A10)
