@@ -23,7 +23,7 @@ from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
 from .runtime import (advance_step, disable_device_step, enable_device_step, manual_seed, mc_samples, set_gemm_dtype,
                       set_kl_grad)
 
-__all__ = ["to_bayesian", "cast_frequentist_", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
+__all__ = ["to_bayesian", "cast_frequentist_", "accelerate_host_", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
            "set_kl_grad", "enable_device_step", "disable_device_step", "advance_step"]
 
 
@@ -34,8 +34,10 @@ def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:
     The variational masters (mu, rho, priors) always stay fp32 (quirk Q4)."""
     from .nn.layers.common import BayesianLayer
 
+    from .nn.layers.layernorm import HostLayerNorm
+
     def walk(mod: tnn.Module) -> None:
-        if isinstance(mod, BayesianLayer):
+        if isinstance(mod, (BayesianLayer, HostLayerNorm)):  # fp32 masters stay fp32
             return
         for p in mod._parameters.values():
             if p is not None and p.is_floating_point():
@@ -47,6 +49,19 @@ def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:
             walk(child)
 
     walk(model)
+    return model
+
+
+def accelerate_host_(model: tnn.Module) -> tnn.Module:
+    """Opt-in: route the host model's remaining frequentist `nn.LayerNorm`s
+    (exact class, 1-D normalized_shape) through the native S-sample LayerNorm
+    kernels with a shared affine.  Parameters are kept (same tensors, fp32);
+    state_dict names do not change.  In place; returns the model."""
+    from .nn.layers.layernorm import HostLayerNorm
+
+    for mod in model.modules():
+        if mod.__class__ is tnn.LayerNorm and mod.elementwise_affine and len(mod.normalized_shape) == 1:
+            mod.__class__ = HostLayerNorm
     return model
 
 

@@ -42,6 +42,12 @@ SIGNATURES = {
                                         c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
                                         c_int32, c_void_p, c_void_p]),
     "bf_bias_grad_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_layernorm_supported": (c_int32, [c_int64]),
+    "bf_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bf_layernorm_bwd_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
 }
 

@@ -58,19 +58,22 @@ class LayerNorm(BayesianLayer):
                                                self.bias.next_stream(S), S, torch.float32, kl_grad)
             logq, logp = logq + lq_b, logp + lp_b
         self._publish(logq, logp, S, kl_grad)
+        if len(self.normalized_shape) == 1 and ops.layernorm_supported(input, self.normalized_shape):
+            if input.shape[0] % S != 0:
+                raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
+            # native S-sample kernel: statistics, per-sample affine and their gradients in one pass each way
+            return ops.LayerNormFn.apply(input, w, b, S, self.eps)
         if S == 1:
             return F.layer_norm(input, self.normalized_shape, w[0].to(input.dtype),
                                 None if b is None else b[0].to(input.dtype), self.eps)
         if input.shape[0] % S != 0:
             raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
         xn = F.layer_norm(input, self.normalized_shape, None, None, self.eps)
-        lead = [S, input.shape[0] // S] + [1] * (input.dim() - 1 - len(self.normalized_shape))
         xs = xn.view(S, input.shape[0] // S, *input.shape[1:])
         shape_w = [S, 1] + [1] * (input.dim() - 1 - len(self.normalized_shape)) + list(self.normalized_shape)
         y = xs * w.to(input.dtype).view(shape_w)
         if b is not None:
             y = y + b.to(input.dtype).view(shape_w)
-        del lead
         return y.view(input.shape)
 
     @classmethod
@@ -86,3 +89,17 @@ class LayerNorm(BayesianLayer):
             if has_bias:
                 baye.bias_prior = moped_(baye.bias, ln.bias, delta, freeze)
         return baye
+
+
+class HostLayerNorm(nn.LayerNorm):
+    """Frequentist `nn.LayerNorm` of the host model routed through the same
+    native kernels (shared affine, fp32 master gamma/beta, activations in the
+    input's dtype).  Installed by `bayeformers_b200.accelerate_host_`; numerics
+    are those of F.layer_norm with fp32 statistics.  Falls back to the stock
+    implementation for shapes the kernels do not take."""
+
+    def forward(self, input: Tensor) -> Tensor:
+        if (self.weight is not None and len(self.normalized_shape) == 1
+                and ops.layernorm_supported(input, self.normalized_shape)):
+            return ops.LayerNormFn.apply(input, self.weight, self.bias, 1, self.eps)
+        return super().forward(input)

@@ -362,6 +362,69 @@ class BayesLinear(torch.autograd.Function):
         return g_x, g_wmu, g_wrho, g_bmu, g_brho, None, None, None, None, None
 
 
+class LayerNormFn(torch.autograd.Function):
+    """y = layer_norm(x) * gamma_s + beta_s for the S folded samples (rows
+    [s*M, (s+1)*M) use sample s); gamma / beta are fp32 [S, H] (sampled) or [H]
+    (shared affine).  Replaces F.layer_norm and its autograd."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, S: int, eps: float):
+        _require_cuda(x, "input")
+        lib = _lib.load()
+        dev = x.device
+        H = x.shape[-1]
+        rows = x.numel() // H
+        if rows % S != 0:
+            raise ValueError(f"{rows} rows are not a multiple of mc_samples={S}")
+        M = rows // S
+        xc = x.detach().contiguous()
+        g = gamma.detach().to(torch.float32).contiguous()
+        b = None if beta is None else beta.detach().to(torch.float32).contiguous()
+        stride = H if g.dim() == 2 and g.shape[0] == S and S > 1 else 0
+        if g.numel() != (S * H if stride else H):
+            raise ValueError(f"affine of shape {tuple(gamma.shape)} does not match S={S}, H={H}")
+        y = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        nbytes = float(rows * H * xc.element_size() * 2)
+        rc = _timed("layernorm_fwd", nbytes, dev, lambda: lib.bf_layernorm_fwd(
+            _ptr(xc), _dt(xc.dtype), _ptr(g), _ptr(b), stride, S, M, H, float(eps), _ptr(y), _ptr(mean), _ptr(rstd),
+            _stream(dev)))
+        _lib.check(rc, "bf_layernorm_fwd")
+        stats["launches"] += 1
+        ctx.save_for_backward(xc, g, mean, rstd)
+        ctx.meta = (S, M, H, stride, gamma.shape, gamma.dtype, None if beta is None else beta.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        xc, g, mean, rstd = ctx.saved_tensors
+        S, M, H, stride, g_shape, g_dtype, b_dtype = ctx.meta
+        dev = xc.device
+        gyc = gy.contiguous().to(xc.dtype)
+        dx = torch.empty_like(xc)
+        Sa = S if stride else 1  # a shared affine is one "sample" spanning all rows
+        dgamma = torch.empty((Sa, H), dtype=torch.float32, device=dev)
+        dbeta = torch.empty((Sa, H), dtype=torch.float32, device=dev) if b_dtype is not None else None
+        ws = _workspace("layernorm_bwd", dev, lib.bf_layernorm_bwd_workspace_bytes(Sa, M * S // Sa, H))
+        nbytes = float(xc.numel() * xc.element_size() * 3)
+        rc = _timed("layernorm_bwd", nbytes, dev, lambda: lib.bf_layernorm_bwd(
+            _ptr(gyc), _ptr(xc), _dt(xc.dtype), _ptr(g), stride, _ptr(mean), _ptr(rstd), Sa, M * S // Sa, H, _ptr(dx),
+            _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream(dev)))
+        _lib.check(rc, "bf_layernorm_bwd")
+        stats["launches"] += 1
+        dg = dgamma.view(g_shape).to(g_dtype) if ctx.needs_input_grad[1] else None
+        db = dbeta.view(g_shape).to(b_dtype) if (dbeta is not None and ctx.needs_input_grad[2]) else None
+        return dx.view(gy.shape), dg, db, None, None
+
+
+def layernorm_supported(x: torch.Tensor, normalized_shape) -> bool:
+    """Shapes / dtypes the native LayerNorm kernels take (others use F.layer_norm)."""
+    return (x.is_cuda and len(normalized_shape) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+            and bool(_lib.load().bf_layernorm_supported(int(normalized_shape[0]))))
+
+
 def philox_normal(n: int, seed: int, step: int, tensor_id: int, sample_id: int, device) -> torch.Tensor:
     """eps stream of one (tensor, sample, step) -- for the statistical tests."""
     lib = _lib.load()

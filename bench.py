@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--kl-grad", type=int, default=1)
     ap.add_argument("--ref-batch", type=int, default=2, help="sequences per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-ln", type=int, default=1,
+                    help="route the host model's frequentist LayerNorms through the native LayerNorm kernels")
     ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
     ap.add_argument("--profile", action="store_true",
                     help="for runs under ncu only: allow < 3 warm-up steps, skip the e2e and CPU legs (numbers invalid)")
@@ -185,6 +187,7 @@ def workload_config(args):
                         "training step (S-sample fwd + ELBO + bwd + clip + AdamW)",
             "seq_len": args.seq, "mc_samples": args.samples, "batch_per_gpu": args.batch,
             "global_batch": args.batch * args.gpus, "gemm": args.gemm, "kl_grad": bool(args.kl_grad),
+            "host_layernorm": "native kernels (bf_layernorm_*)" if args.host_ln else "torch",
             "parallelism": f"dp{args.gpus} (batch sharded, identical Philox weights per rank, NCCL grad all-reduce)",
             "l2": "working set (0.7 GB sampled weights + activations) far exceeds the 126 MB L2; no explicit flush"}
 
@@ -206,10 +209,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
+    if os.environ.get("BF_ANOMALY"):  # debugging aid: forward traceback of a failing backward node
+        torch.autograd.set_detect_anomaly(True)
 
     model, cfg = build_bert(args.layers)
     bf.manual_seed(1234)
-    bm = bf.to_bayesian(model, delta=0.05, freeze=True, gemm_dtype=args.gemm, kl_grad=bool(args.kl_grad)).to(dev).train()
+    bm = bf.to_bayesian(model, delta=0.05, freeze=True, gemm_dtype=args.gemm, kl_grad=bool(args.kl_grad))
+    if args.host_ln:
+        bf.accelerate_host_(bm)  # same parameters and numerics, native fwd/bwd kernels (fp32 gamma/beta)
+    bm = bm.to(dev).train()
     if world > 1:
         parallel.broadcast_seed(0)
     if args.gemm == "bf16":
@@ -263,8 +271,18 @@ def run_ours(args):
             graph = torch.cuda.CUDAGraph()
             optim.zero_grad(set_to_none=True)
             l0 = ops.stats["launches"]
-            with torch.cuda.graph(graph, stream=side):  # same stream as the warm-up: handles/workspaces exist
-                static_out = step_body(static_ids, static_labels)
+            # HF treats "CUDA stream is capturing" like tracing and then always materialises a [B,1,T,T]
+            # attention mask (transformers/masking_utils.py:_ignore_bidirectional_mask_sdpa), which pushes SDPA
+            # onto the unfused math path.  With attention_mask=None there is no data-dependent branch to protect,
+            # so keep the eager behaviour (no mask -> fused cuDNN attention) while capturing.
+            import transformers.masking_utils as hf_masking
+            hf_is_tracing = hf_masking.is_tracing
+            hf_masking.is_tracing = lambda *a, **k: False
+            try:
+                with torch.cuda.graph(graph, stream=side):  # same stream as the warm-up: handles/workspaces exist
+                    static_out = step_body(static_ids, static_labels)
+            finally:
+                hf_masking.is_tracing = hf_is_tracing
             launches_per_graph = ops.stats["launches"] - l0
 
             def step(ids, labels):  # noqa: F811

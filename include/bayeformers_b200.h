@@ -169,6 +169,30 @@ int64_t bf_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N);
 int bf_bias_grad(const void* gy, int32_t gy_dtype, float* db, int64_t S, int64_t M, int64_t N, void* workspace,
                  void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * S-sample LayerNorm (the Bayesian LayerNorm the north_star
+ * names, absent from the reference snapshot; specified as the reference's
+ * Gaussian.sample (gaussian.py:90-101) composed with F.layer_norm).
+ *
+ *   fwd : y[s][m][:] = (x[s][m][:] - mean) * rstd * gamma[s][:] + beta[s][:]
+ *   bwd : dx, dgamma[s][:] = sum_m gy*xhat, dbeta[s][:] = sum_m gy
+ *
+ * x, y, gy, dx  [S*M, H] of `dtype` (BF_F32 / BF_BF16), rows [s*M, (s+1)*M) use sample s
+ * gamma, beta   fp32, sample s at offset s*affine_stride (affine_stride == 0: one
+ *               shared affine -- the frequentist LayerNorm); beta may be NULL
+ * mean, rstd    [S*M] fp32, written by fwd, read by bwd
+ * H             256, 512, 768 or 1024 (bf_layernorm_supported); statistics in fp32
+ * workspace     bf_layernorm_bwd_workspace_bytes(S, M, H) bytes, zero-filled once;
+ *               deterministic two-stage reduction of dgamma / dbeta
+ * ------------------------------------------------------------------------- */
+int bf_layernorm_supported(int64_t H);
+int bf_layernorm_fwd(const void* x, int32_t dtype, const float* gamma, const float* beta, int64_t affine_stride,
+                     int64_t S, int64_t M, int64_t H, float eps, void* y, float* mean, float* rstd, void* stream);
+int64_t bf_layernorm_bwd_workspace_bytes(int64_t S, int64_t M, int64_t H);
+int bf_layernorm_bwd(const void* gy, const void* x, int32_t dtype, const float* gamma, int64_t affine_stride,
+                     const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, void* dx, float* dgamma,
+                     float* dbeta, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

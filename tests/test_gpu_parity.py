@@ -486,6 +486,62 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
     assert rel_err(g_rho.cpu().numpy(), 2 * want_rho.cpu().numpy()) < 1e-5
 
 
+
+# ------------------------------------------------------------------ native S-sample LayerNorm (row A10)
+@pytest.mark.parametrize("S,M,H", [(1, 7, 256), (3, 33, 768), (4, 1000, 768), (2, 129, 1024), (1, 4096, 512)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_native_layernorm_vs_torch_fp64(S, M, H, dtype):
+    """bf_layernorm_fwd/bwd through ops.LayerNormFn against F.layer_norm evaluated per
+    sample in float64 on the CPU (the torch operator the reference-style layer composes)."""
+    gen = torch.Generator().manual_seed(S * 1000 + M + H)
+    x = (torch.randn(S * M, H, generator=gen) * 2 + 0.5).to(dtype)
+    gamma = 1 + 0.1 * torch.randn(S, H, generator=gen)
+    beta = 0.1 * torch.randn(S, H, generator=gen)
+    gy = torch.randn(S * M, H, generator=gen).to(dtype)
+    xd = x.to(DEV).requires_grad_()
+    gd, bd = gamma.to(DEV).requires_grad_(), beta.to(DEV).requires_grad_()
+    y = ops.LayerNormFn.apply(xd, gd, bd, S, 1e-12)
+    y.backward(gy.to(DEV))
+    x64 = x.double().requires_grad_()
+    g64, b64 = gamma.double().requires_grad_(), beta.double().requires_grad_()
+    y64 = torch.cat([torch.nn.functional.layer_norm(x64[s * M:(s + 1) * M], (H,), g64[s], b64[s], 1e-12) for s in range(S)])
+    y64.backward(gy.double())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert y.dtype == dtype
+    assert rel_err(y.detach().float().cpu().numpy(), y64.detach().numpy()) < tol
+    assert rel_err(xd.grad.float().cpu().numpy(), x64.grad.numpy()) < tol
+    # the affine gradients are fp32 sums of fp32 products whatever the activation dtype
+    assert rel_err(gd.grad.cpu().numpy(), g64.grad.numpy()) < 2e-5
+    assert rel_err(bd.grad.cpu().numpy(), b64.grad.numpy()) < 2e-5
+    # deterministic: a second backward gives the same bits
+    xd2 = x.to(DEV).requires_grad_()
+    gd2, bd2 = gamma.to(DEV).requires_grad_(), beta.to(DEV).requires_grad_()
+    ops.LayerNormFn.apply(xd2, gd2, bd2, S, 1e-12).backward(gy.to(DEV))
+    assert torch.equal(gd.grad, gd2.grad) and torch.equal(bd.grad, bd2.grad) and torch.equal(xd.grad, xd2.grad)
+
+
+def test_host_layernorm_shared_affine_matches_torch():
+    """accelerate_host_: frequentist nn.LayerNorm through the native kernel == stock module."""
+    torch.manual_seed(3)
+    ln = torch.nn.LayerNorm(768, eps=1e-12)
+    with torch.no_grad():
+        ln.weight.add_(0.1 * torch.randn(768)); ln.bias.add_(0.1 * torch.randn(768))
+    import copy
+    ref = copy.deepcopy(ln).to(DEV)
+    fast = bf.accelerate_host_(torch.nn.Sequential(copy.deepcopy(ln))).to(DEV)[0]
+    assert type(fast).__name__ == "HostLayerNorm" and list(fast.state_dict()) == list(ref.state_dict())
+    x = torch.randn(4, 50, 768, device=DEV)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    with bf.mc_samples(4):  # folded run: the shared affine must ignore S
+        ya = fast(xa)
+    yb = ref(xb)
+    gy = torch.randn_like(x)
+    ya.backward(gy); yb.backward(gy)
+    assert rel_err(ya.detach().cpu().numpy(), yb.detach().cpu().numpy()) < FP32_TOL
+    assert rel_err(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < FP32_TOL
+    assert rel_err(fast.weight.grad.cpu().numpy(), ref.weight.grad.cpu().numpy()) < 2e-5
+    assert rel_err(fast.bias.grad.cpu().numpy(), ref.bias.grad.cpu().numpy()) < 2e-5
+
 # ------------------------------------------------------------------ Embedding / LayerNorm (rows A9 / A10)
 def test_embedding_and_layernorm_against_composed_oracle():
     torch.manual_seed(0)
