@@ -20,10 +20,11 @@ from .nn.model import Model
 from .nn.parameters.base import Parameter
 from .nn.parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE
 from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
+from .presample import enable_presample
 from .runtime import (advance_step, disable_device_step, enable_device_step, manual_seed, mc_samples, set_gemm_dtype,
                       set_kl_grad)
 
-__all__ = ["to_bayesian", "cast_frequentist_", "accelerate_host_", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
+__all__ = ["to_bayesian", "cast_frequentist_", "accelerate_host_", "enable_presample", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
            "set_kl_grad", "enable_device_step", "disable_device_step", "advance_step"]
 
 

@@ -16,6 +16,14 @@ LIB_PATH = os.path.join(_PKG, "libbayeformers_b200.so")
 BF_F32, BF_BF16 = 0, 1
 BF_PRIOR_MIXTURE, BF_PRIOR_GAUSSIAN, BF_PRIOR_NONE = 0, 1, 2
 
+class BfTensorDesc(ctypes.Structure):
+    """`bf_tensor_desc` of include/bayeformers_b200.h (multi-tensor sample+KL)."""
+    _fields_ = [("mu", c_void_p), ("rho", c_void_p), ("prior_mu", c_void_p), ("prior_rho", c_void_p),
+                ("w_out", c_void_p), ("n", c_int64), ("w_stride", c_int64), ("tensor_id", c_uint32),
+                ("step", c_uint32), ("prior_kind", c_int32), ("w_dtype", c_int32), ("pi", c_float),
+                ("sigma1", c_float), ("sigma2", c_float), ("vec", c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/bayeformers_b200.h one to one
 SIGNATURES = {
     "bf_abi_version": (c_int32, []),
@@ -27,6 +35,10 @@ SIGNATURES = {
     "bf_sample_kl_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_int64, c_int32, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_int32,
                                    c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "bf_sample_kl_multi_chunk_quads": (c_int32, []),
+    "bf_sample_kl_multi_workspace_bytes": (c_int64, [c_int64]),
+    "bf_sample_kl_fwd_multi": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_uint64, c_uint32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_sample_kl_bwd": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                    c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_int32, c_uint64,
                                    c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

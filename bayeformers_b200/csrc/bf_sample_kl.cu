@@ -491,6 +491,161 @@ __global__ void __launch_bounds__(kThreads) philox_normal_kernel(float* out, int
     }
 }
 
+// ---------------------------------------------------------------------------
+// multi-tensor forward: every variational tensor of a model in ONE launch
+// (SURVEY.md section 8f row 2).  The work list is cut into chunks of at most
+// kChunkQuads quads of one tensor; blocks walk the chunk table grid-stride, so
+// a BERT's 148 tensors (from 768-element biases to 3072x768 matrices) load the
+// SMs evenly instead of paying 148 launches with ragged tails.  Reductions stay
+// deterministic: per-chunk partial (block tree) -> per-slot sum in chunk order.
+// ---------------------------------------------------------------------------
+constexpr int kChunkQuads = 4096;
+
+struct MultiParams {
+    const bf_tensor_desc* descs;
+    const int2* chunks;   // {tensor index, first quad}
+    int n_chunks;
+    int s0;               // first sample of this launch
+    float* partials;      // [n_chunks][2*SC]
+    uint32_t k0, k1, step;
+    const uint32_t* step_ptr;
+    char* w_base;  // when set, descs[].w_out are byte offsets from it
+};
+
+template <int PRIOR, typename WT, int SC>
+__device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const MultiParams& mp, int64_t q_begin,
+                                            uint32_t step, float (&q_acc)[SC], float (&p_acc)[SC]) {
+    SampleKlParams p{};
+    p.mu = d.mu, p.rho = d.rho, p.prior_mu = d.prior_mu, p.prior_rho = d.prior_rho;
+    p.mix.pi = d.pi;
+    WT* const w_out = mp.w_base ? reinterpret_cast<WT*>(mp.w_base + reinterpret_cast<intptr_t>(d.w_out))
+                                : reinterpret_cast<WT*>(d.w_out);
+    const int64_t n = d.n;
+    const int64_t nquad = (n + 3) >> 2;
+    int64_t q_end = q_begin + kChunkQuads;
+    if (q_end > nquad) q_end = nquad;
+    if (PRIOR == BF_PRIOR_GAUSSIAN && d.prior_rho == nullptr) {
+        p.prior_const_c = -BF_LOG_SQRT_2PI - logf(d.sigma1);
+        p.prior_const_iv = 1.0f / (2.0f * d.sigma1 * d.sigma1);
+    }
+    if (PRIOR == BF_PRIOR_MIXTURE) {  // same constants as bf_make_mixture (host), evaluated per block
+        const float v1 = d.sigma1 * d.sigma1, v2 = d.sigma2 * d.sigma2;
+        p.mix.one_minus_pi = 1.0f - d.pi;
+        p.mix.inv_two_var1 = 1.0f / (2.0f * v1), p.mix.inv_two_var2 = 1.0f / (2.0f * v2);
+        p.mix.log_s1 = logf(d.sigma1), p.mix.log_s2 = logf(d.sigma2);
+        p.mix.inv_var1 = 1.0f / v1, p.mix.inv_var2 = 1.0f / v2;
+    }
+    const bool vec = d.vec != 0;
+    for (int64_t q = q_begin + threadIdx.x; q < q_end; q += kThreads) {
+        const int64_t i0 = q << 2;
+        QuadShared Q;
+        if (vec) {
+            RawQuad R;
+            load_raw<PRIOR>(p, i0, R);
+            derive_quad<PRIOR>(p, R, Q);
+        } else {
+            RawQuad R;
+            float t[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = i0 + j < n;
+                t[0][j] = ok ? __ldg(d.mu + i0 + j) : 0.0f;
+                t[1][j] = ok ? __ldg(d.rho + i0 + j) : 0.0f;
+                t[2][j] = (ok && PRIOR == BF_PRIOR_GAUSSIAN) ? __ldg(d.prior_mu + i0 + j) : 0.0f;
+                t[3][j] = (ok && PRIOR == BF_PRIOR_GAUSSIAN && d.prior_rho) ? __ldg(d.prior_rho + i0 + j) : 0.0f;
+            }
+            R.mu = make_float4(t[0][0], t[0][1], t[0][2], t[0][3]);
+            R.rho = make_float4(t[1][0], t[1][1], t[1][2], t[1][3]);
+            R.pmu = make_float4(t[2][0], t[2][1], t[2][2], t[2][3]);
+            R.prho = make_float4(t[3][0], t[3][1], t[3][2], t[3][3]);
+            derive_quad<PRIOR>(p, R, Q);
+        }
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            const int sg = mp.s0 + s;
+            const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, d.tensor_id, step + d.step, mp.k0, mp.k1);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            float w[4];
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = element_terms<PRIOR>(Q.mu[j], Q.sigma[j], Q.qc[j], Q.qiv[j], e[j], Q.pmu[j], Q.pc[j], Q.piv[j],
+                                                p.mix, q_acc[s], p_acc[s]);
+                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * d.w_stride + i0, w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i0 + j < n) {
+                        w[j] = element_terms<PRIOR>(Q.mu[j], Q.sigma[j], Q.qc[j], Q.qiv[j], e[j], Q.pmu[j], Q.pc[j],
+                                                    Q.piv[j], p.mix, q_acc[s], p_acc[s]);
+                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * d.w_stride + i0 + j, w[j]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int SC>
+__global__ void __launch_bounds__(kThreads) sample_kl_multi_kernel(const MultiParams mp) {
+    __shared__ float red[2 * kMaxSC][kThreads / 32];
+    const uint32_t step = mp.step + (mp.step_ptr ? __ldg(mp.step_ptr) : 0u);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < mp.n_chunks; c += gridDim.x) {
+        const int2 ch = __ldg(mp.chunks + c);
+        const bf_tensor_desc d = mp.descs[ch.x];
+        float q_acc[SC], p_acc[SC];
+#pragma unroll
+        for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
+        const int64_t qb = (int64_t)ch.y;
+        const bool bf = d.w_dtype == BF_BF16;
+        if (d.prior_kind == BF_PRIOR_GAUSSIAN) {
+            if (bf) multi_chunk<BF_PRIOR_GAUSSIAN, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
+            else multi_chunk<BF_PRIOR_GAUSSIAN, float, SC>(d, mp, qb, step, q_acc, p_acc);
+        } else if (d.prior_kind == BF_PRIOR_MIXTURE) {
+            if (bf) multi_chunk<BF_PRIOR_MIXTURE, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
+            else multi_chunk<BF_PRIOR_MIXTURE, float, SC>(d, mp, qb, step, q_acc, p_acc);
+        } else {
+            if (bf) multi_chunk<BF_PRIOR_NONE, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
+            else multi_chunk<BF_PRIOR_NONE, float, SC>(d, mp, qb, step, q_acc, p_acc);
+        }
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            const float a = bf_warp_sum(q_acc[s]);
+            const float b = bf_warp_sum(p_acc[s]);
+            if (lane == 0) {
+                red[2 * s][warp] = a;
+                red[2 * s + 1][warp] = b;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * SC) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
+            mp.partials[(int64_t)c * 2 * SC + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// one block per output slot: sum the chunk partials of that slot in chunk order
+__global__ void __launch_bounds__(64) sample_kl_multi_finish_kernel(const float* __restrict__ partials,
+                                                                    const int2* __restrict__ slot_ranges, int SC, int s0,
+                                                                    int S, float* __restrict__ logq,
+                                                                    float* __restrict__ logp) {
+    const int slot = blockIdx.x;
+    const int2 r = __ldg(slot_ranges + slot);  // chunks [r.x, r.y)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int v = warp; v < 2 * SC; v += 2) {
+        double t = 0.0;
+        for (int c = r.x + lane; c < r.y; c += 32) t += (double)partials[(int64_t)c * 2 * SC + v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) ((v & 1) ? logp : logq)[(int64_t)slot * S + s0 + (v >> 1)] = (float)t;
+    }
+}
+
 inline int grid_for(int64_t nquad, int blocks_per_sm) {
     const int64_t want = (nquad + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)bf_num_sms() * blocks_per_sm;
@@ -689,4 +844,45 @@ int bf_sample_kl_bwd_impl_kl_only(const float* mu, const float* rho, int32_t pri
                                   cudaStream_t st) {
     return bf_sample_kl_bwd(nullptr, BF_F32, n, mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2, g_logq,
                             g_logp, n, S, seed, step, tensor_id, eps_in, grad_mu, grad_rho, 1, st);
+}
+
+// ---- multi-tensor entry points --------------------------------------------------------
+extern "C" int32_t bf_sample_kl_multi_chunk_quads(void) { return kChunkQuads; }
+
+extern "C" int64_t bf_sample_kl_multi_workspace_bytes(int64_t n_chunks) {
+    return (n_chunks < 1 ? 1 : n_chunks) * 2 * kMaxSC * (int64_t)sizeof(float);
+}
+
+extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t* chunks, int32_t n_chunks,
+                                      const int32_t* slot_ranges, int32_t n_slots, int32_t S, uint64_t seed,
+                                      uint32_t step, float* logq_out, float* logp_out, void* workspace, void* w_base,
+                                      void* stream) {
+    BF_CHECK_ARG(descs && chunks && slot_ranges && logq_out && logp_out && workspace, "null pointer");
+    BF_CHECK_ARG(n_chunks >= 1 && n_slots >= 1 && S >= 1, "bad counts");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    MultiParams mp{};
+    mp.descs = descs, mp.chunks = reinterpret_cast<const int2*>(chunks), mp.n_chunks = n_chunks;
+    mp.partials = reinterpret_cast<float*>(workspace);
+    mp.k0 = (uint32_t)(seed & 0xffffffffu), mp.k1 = (uint32_t)(seed >> 32), mp.step = step;
+    mp.step_ptr = bf_step_counter();
+    mp.w_base = reinterpret_cast<char*>(w_base);
+    const int64_t cap = (int64_t)bf_num_sms() * kFwdBlocksPerSm;
+    const int grid = (int)(n_chunks < cap ? n_chunks : cap);
+    for (int s0 = 0; s0 < S;) {
+        int sc = 1;
+        while (sc * 2 <= kMaxSC && s0 + sc * 2 <= S) sc *= 2;
+        mp.s0 = s0;
+        switch (sc) {
+            case 1: sample_kl_multi_kernel<1><<<grid, kThreads, 0, st>>>(mp); break;
+            case 2: sample_kl_multi_kernel<2><<<grid, kThreads, 0, st>>>(mp); break;
+            case 4: sample_kl_multi_kernel<4><<<grid, kThreads, 0, st>>>(mp); break;
+            default: sample_kl_multi_kernel<8><<<grid, kThreads, 0, st>>>(mp); break;
+        }
+        BF_LAUNCH_OK();
+        sample_kl_multi_finish_kernel<<<n_slots, 64, 0, st>>>(mp.partials, reinterpret_cast<const int2*>(slot_ranges), sc,
+                                                             s0, S, logq_out, logp_out);
+        BF_LAUNCH_OK();
+        s0 += sc;
+    }
+    return 0;
 }

@@ -45,6 +45,7 @@ class BayesianLayer(nn.Module):
         # grad-carrying versions of the two scalars when kl_grad is on
         self.live_log_prior = None
         self.live_log_variational_posterior = None
+        self._presampled = None  # one forward's draw made by presample.Presampler (consumed by forward)
 
     def _kl_grad(self) -> bool:
         return runtime.get_kl_grad() if self.kl_grad is None else self.kl_grad

@@ -47,9 +47,17 @@ class Linear(BayesianLayer):
         has_bias = isinstance(self.bias, Gaussian)
         w_prior = prior_spec_of(self.weight_prior)
         b_prior = prior_spec_of(self.bias_prior) if has_bias else ops.PriorSpec()
-        spec = ops.LinearSpec(S=S, gemm_dtype=self._gemm_dtype(), kl_grad=kl_grad, w_prior=w_prior, b_prior=b_prior,
-                              w_stream=self.weight.next_stream(S),
-                              b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec())
+        pre, self._presampled = self._presampled, None  # a draw serves exactly one forward
+        if pre is not None and pre[0] != S:
+            pre = None
+        if pre is not None:
+            spec = ops.LinearSpec(S=S, gemm_dtype=self._gemm_dtype(), kl_grad=kl_grad, w_prior=w_prior, b_prior=b_prior,
+                                  w_stream=pre[5], b_stream=pre[6], presampled=pre[1:5])
+        else:
+            spec = ops.LinearSpec(S=S, gemm_dtype=self._gemm_dtype(), kl_grad=kl_grad, w_prior=w_prior,
+                                  b_prior=b_prior, w_stream=self.weight.next_stream(S),
+                                  b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec())
+        self._last_streams = (spec.w_stream, spec.b_stream)  # identity of this forward's eps draw (tests, debugging)
         y, logq, logp = ops.BayesLinear.apply(
             input, self.weight.mu, self.weight.rho,
             self.bias.mu if has_bias else None, self.bias.rho if has_bias else None,

@@ -24,10 +24,15 @@ class Model(Module):
     def __init__(self, model: Optional[Module] = None) -> None:
         super().__init__()
         self.model = model
+        self._presampler = None  # set by bayeformers_b200.enable_presample
 
     def forward(self, *args, **kwargs) -> Any:
         if self.model is None:
             raise NotImplementedError("Forward pass not implemented yet")
+        if self._presampler is not None:
+            # extension: draw every Bayesian Linear's weights for this forward in one multi-tensor launch
+            from .. import runtime
+            self._presampler.run(runtime.get_mc_samples())
         return self.model.forward(*args, **kwargs)
 
     @property

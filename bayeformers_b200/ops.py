@@ -230,6 +230,7 @@ class LinearSpec:
     b_prior: PriorSpec
     w_stream: StreamSpec
     b_stream: StreamSpec = field(default_factory=StreamSpec)
+    presampled: Optional[Tuple] = None  # (W[S,N,K], b[S,N] or None, logq[S], logp[S]) from presample.Presampler
 
 
 def tc_eligible(N: int, K: int) -> bool:
@@ -263,17 +264,22 @@ class BayesLinear(torch.autograd.Function):
         xg = x.detach().reshape(S, M, K).to(cdt).contiguous()
         has_bias = b_mu is not None
 
-        logq = torch.empty(S, dtype=torch.float32, device=dev)
-        logp = torch.empty(S, dtype=torch.float32, device=dev)
-        w_prior = PriorSpec(spec.w_prior.kind, spec.w_prior.pi, spec.w_prior.sigma1, spec.w_prior.sigma2, wp_mu, wp_rho)
-        W = sample_kl_forward(w_mu.detach(), w_rho.detach(), w_prior, spec.w_stream, S, cdt, logq, logp, False)
-        b = None
-        b_prior = None
-        if has_bias:
-            b_prior = PriorSpec(spec.b_prior.kind, spec.b_prior.pi, spec.b_prior.sigma1, spec.b_prior.sigma2,
-                                bp_mu, bp_rho)
-            b = sample_kl_forward(b_mu.detach(), b_rho.detach(), b_prior, spec.b_stream, S, torch.float32, logq, logp,
-                                  True)
+        if spec.presampled is not None:
+            W, b, logq, logp = spec.presampled
+            if W.dtype != cdt or (has_bias and b is None):
+                raise RuntimeError("presampled weights do not match this layer's GEMM mode")
+        else:
+            logq = torch.empty(S, dtype=torch.float32, device=dev)
+            logp = torch.empty(S, dtype=torch.float32, device=dev)
+            w_prior = PriorSpec(spec.w_prior.kind, spec.w_prior.pi, spec.w_prior.sigma1, spec.w_prior.sigma2, wp_mu,
+                                wp_rho)
+            W = sample_kl_forward(w_mu.detach(), w_rho.detach(), w_prior, spec.w_stream, S, cdt, logq, logp, False)
+            b = None
+            if has_bias:
+                b_prior = PriorSpec(spec.b_prior.kind, spec.b_prior.pi, spec.b_prior.sigma1, spec.b_prior.sigma2,
+                                    bp_mu, bp_rho)
+                b = sample_kl_forward(b_mu.detach(), b_rho.detach(), b_prior, spec.b_stream, S, torch.float32, logq,
+                                      logp, True)
         out_dtype = x.dtype if (use_tc and x.dtype in (torch.float32, torch.bfloat16)) else torch.float32
         y = torch.empty((S, M, N), dtype=out_dtype, device=dev)
         if M > 0:

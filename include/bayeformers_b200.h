@@ -101,6 +101,46 @@ int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior_kind, cons
                      void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Multi-tensor form of bf_sample_kl_fwd: all variational tensors of a model in
+ * one launch per sample chunk.  Same arithmetic,
+ * same eps stream, same results as calling bf_sample_kl_fwd tensor by tensor
+ * (log-prob sums agree to fp32 summation order).
+ *
+ * descs        DEVICE array of n_tensors descriptors (below)
+ * chunks       DEVICE int32 pairs {tensor index, first quad}: the work list, each entry
+ *              covering at most bf_sample_kl_multi_chunk_quads() quads (4 elements) of
+ *              one tensor, entries of one output slot contiguous
+ * slot_ranges  DEVICE int32 pairs {first chunk, last chunk + 1} per output slot; a slot
+ *              is what one (logq, logp) pair sums over -- typically weight + bias of a layer
+ * logq_out, logp_out  [n_slots][S] fp32 (overwritten)
+ * step         added to every descriptor's own `step`
+ * w_base       NULL, or a base address: descriptors' `w_out` are then byte OFFSETS from it
+ *              (lets a static descriptor table serve a freshly allocated output arena per call)
+ * workspace    bf_sample_kl_multi_workspace_bytes(n_chunks) bytes, contents irrelevant
+ * ------------------------------------------------------------------------- */
+typedef struct bf_tensor_desc {
+    const float* mu;
+    const float* rho;
+    const float* prior_mu;  /* BF_PRIOR_GAUSSIAN only */
+    const float* prior_rho; /* NULL: constant prior sigma in `sigma1` */
+    void* w_out;            /* [S][w_stride] of w_dtype, or NULL */
+    int64_t n;
+    int64_t w_stride;
+    uint32_t tensor_id;
+    uint32_t step;
+    int32_t prior_kind;
+    int32_t w_dtype;
+    float pi, sigma1, sigma2;
+    int32_t vec; /* 1: all pointers 16 B aligned, n % 4 == 0, (w_stride * elem) % 16 == 0 */
+} bf_tensor_desc;
+
+int32_t bf_sample_kl_multi_chunk_quads(void);
+int64_t bf_sample_kl_multi_workspace_bytes(int64_t n_chunks);
+int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t* chunks, int32_t n_chunks,
+                           const int32_t* slot_ranges, int32_t n_slots, int32_t S, uint64_t seed, uint32_t step,
+                           float* logq_out, float* logp_out, void* workspace, void* w_base, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Backward of the above (stand-alone form): eps is RECOMPUTED from the seed.
  * Replaces what autograd does for gaussian.py:101 (mu + eps*softplus(rho)) and,
  * when g_logq/g_logp are given, for the two log_prob reductions (the KL

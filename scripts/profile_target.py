@@ -37,5 +37,17 @@ for _ in range(2):
     lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
     lib.bf_linear_wgrad_fused(gy.data_ptr(), x.data_ptr(), S, M, N, K, BF_BF16, mu2.data_ptr(), rho2.data_ptr(), 2, None, None,
                               0.5, 1.0, 1.0, None, None, 7, 0, 1, None, None, g_rho.data_ptr(), 0, ws.data_ptr(), st)
+# native LayerNorm at the BERT-base activation shape (S=4 x 64 sequences x 128 tokens)
+rows, H = 4 * 64 * 128, 768
+xa = torch.randn(rows, H, device=DEV).bfloat16().requires_grad_()
+ga = torch.ones(4, H, device=DEV, requires_grad=True); ba = torch.zeros(4, H, device=DEV, requires_grad=True)
+for _ in range(2):
+    ya = ops.LayerNormFn.apply(xa, ga, ba, 4, 1e-12)
+    ya.backward(torch.ones_like(ya))
+# bias gradient at the FFN shape
+db = torch.empty(S, N, device=DEV)
+bws = torch.zeros(lib.bf_bias_grad_workspace_bytes(S, M, N), dtype=torch.uint8, device=DEV)
+for _ in range(2):
+    lib.bf_bias_grad(gy.data_ptr(), BF_BF16, db.data_ptr(), S, M, N, bws.data_ptr(), st)
 torch.cuda.synchronize()
 print("profile target done")

@@ -487,6 +487,55 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
 
 
 
+
+# ------------------------------------------------------------------ multi-tensor sampling (section 8f row 2)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_presample_equals_per_layer_path(mode):
+    """enable_presample: one bf_sample_kl_fwd_multi launch for the whole model gives the same weights,
+    log-probs, outputs and gradients as the per-layer kernels fed the same Philox stream."""
+    import copy
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 136), torch.nn.Tanh(), torch.nn.Linear(136, 4104, bias=False),
+                              torch.nn.Tanh(), torch.nn.Linear(4104, 10))
+    bf.manual_seed(77)
+    S, B = 3, 8
+    x = torch.randn(S * B, 64, device=DEV)
+    tol = FP32_TOL if mode == "fp32" else BF16_TOL
+    for prior_kw in ({"delta": 0.05}, {}):  # MOPED Gaussian prior / default scale mixture
+        a = bf.to_bayesian(copy.deepcopy(net), gemm_dtype=mode, kl_grad=True, **prior_kw).to(DEV)
+        b = copy.deepcopy(a)
+        bf.enable_presample(a)
+        with bf.mc_samples(S):
+            ya = a(x)
+        la = ya.square().sum() + 1e-3 * (a.log_variational_posterior() - a.log_prior()).sum()
+        la.backward()
+        # replay the same eps through the per-layer kernels of the twin model
+        for la_, lb_ in zip(a.bayesian_children, b.bayesian_children):
+            ws, bs = la_._last_streams
+            assert ws.step & 0x80000000
+            n = lb_.weight.mu.numel()
+            lb_.weight.normal = FixedEps([ops.philox_normal(n, ws.seed, ws.step, ws.tensor_id, s, DEV).view_as(lb_.weight.mu)
+                                          for s in range(S)])
+            if isinstance(lb_.bias, bnn.Gaussian):
+                nb = lb_.bias.mu.numel()
+                lb_.bias.normal = FixedEps([ops.philox_normal(nb, bs.seed, bs.step, bs.tensor_id, s, DEV) for s in range(S)])
+        with bf.mc_samples(S):
+            yb = b(x)
+        lb = yb.square().sum() + 1e-3 * (b.log_variational_posterior() - b.log_prior()).sum()
+        lb.backward()
+        assert rel_err(ya.detach().cpu().numpy(), yb.detach().cpu().numpy()) < tol
+        assert rel_err(a.log_prior().detach().cpu().numpy(), b.log_prior().detach().cpu().numpy()) < 2e-6
+        assert rel_err(a.log_variational_posterior().detach().cpu().numpy(),
+                       b.log_variational_posterior().detach().cpu().numpy()) < 2e-6
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            assert (pa.grad is None) == (pb.grad is None)
+            if pa.grad is not None:
+                assert rel_err(pa.grad.cpu().numpy(), pb.grad.cpu().numpy()) < tol
+        # a second forward draws a different step; a forward without a fresh draw falls back per layer
+        with bf.mc_samples(S):
+            y2 = a(x)
+        assert not torch.equal(y2, ya)
+
 # ------------------------------------------------------------------ native S-sample LayerNorm (row A10)
 @pytest.mark.parametrize("S,M,H", [(1, 7, 256), (3, 33, 768), (4, 1000, 768), (2, 129, 1024), (1, 4096, 512)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
