@@ -19,8 +19,11 @@
 
 namespace {
 
-constexpr int kLnThreads = 512;
+constexpr int kLnThreads = 512;  // backward: 1 block of 16 warps per SM (128 registers per thread)
 constexpr int kLnWarps = kLnThreads / 32;
+constexpr int kLnFwdThreads = 256;  // forward: 4 blocks of 8 warps per SM (<= 64 registers per thread)
+constexpr int kLnFwdWarps = kLnFwdThreads / 32;
+constexpr int kLnFwdBlocksPerSm = 4;
 
 template <typename T>
 struct Pack8;  // 8 consecutive elements <-> fp32
@@ -70,7 +73,7 @@ __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
 
 // ------------------------------------------------------------------ forward
 template <typename T, int C>
-__global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(kLnFwdThreads, kLnFwdBlocksPerSm) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, T* __restrict__ y,
                                                                    float* __restrict__ mean_out,
                                                                    float* __restrict__ rstd_out, int64_t M,
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const T* __re
     const float* g = gamma + (int64_t)s * affine_stride;
     const float* b = beta ? beta + (int64_t)s * affine_stride : nullptr;
     const int64_t row0 = (int64_t)s * M;
-    for (int64_t m = (int64_t)blockIdx.x * kLnWarps + warp; m < M; m += (int64_t)gridDim.x * kLnWarps) {
+    for (int64_t m = (int64_t)blockIdx.x * kLnFwdWarps + warp; m < M; m += (int64_t)gridDim.x * kLnFwdWarps) {
         const T* xr = x + (row0 + m) * H;
         Pack8<T> px[C];
 #pragma unroll
@@ -273,11 +276,12 @@ inline int ln_blocks(int64_t S, int64_t M) {
 template <typename T, int C>
 int launch_fwd_c(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t S,
                  int64_t M, int64_t astride, float eps, cudaStream_t st) {
-    int64_t need = (M + kLnWarps - 1) / kLnWarps;
-    const int64_t cap = (int64_t)bf_num_sms() * 2 / S + 1;
+    int64_t need = (M + kLnFwdWarps - 1) / kLnFwdWarps;
+    int64_t cap = (int64_t)bf_num_sms() * kLnFwdBlocksPerSm / S;  // one full wave of resident blocks over all samples
+    if (cap < 1) cap = 1;
     if (need > cap) need = cap;
     dim3 grid((unsigned)(need < 1 ? 1 : need), (unsigned)S);
-    layernorm_fwd_kernel<T, C><<<grid, kLnThreads, 0, st>>>(reinterpret_cast<const T*>(x), gamma, beta,
+    layernorm_fwd_kernel<T, C><<<grid, kLnFwdThreads, 0, st>>>(reinterpret_cast<const T*>(x), gamma, beta,
                                                              reinterpret_cast<T*>(y), mean, rstd, M, astride, eps);
     return 0;
 }
