@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step (before the S-fold)")
-    ap.add_argument("--graph", type=int, default=1, help="capture the whole training step in one CUDA graph (1 GPU)")
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step (before the S-fold)")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1: capture the whole training step in one CUDA graph; 0: eager")
     ap.add_argument("--samples", type=int, default=4)
     ap.add_argument("--seq", type=int, default=128)
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
@@ -229,7 +230,7 @@ def run_ours(args):
         # the variational masters (mu, rho, priors) stay fp32
         bf.cast_frequentist_(bm, torch.bfloat16)
     params = [p for p in bm.parameters() if p.requires_grad]
-    use_graph = bool(args.graph) and world == 1 and not args.profile
+    use_graph = bool(args.graph) and not args.profile
     optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True, capturable=use_graph)
     sync = parallel.GradSync(bm)
     bf.enable_device_step(dev)  # eps = f(seed, tensor, host_step + device_step, sample): graph replays draw fresh eps
@@ -304,7 +305,11 @@ def run_ours(args):
             traceback.print_exc(file=sys.stderr)
             sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}); re-running eagerly\n")
             sys.stderr.flush()
-            os.execv(sys.executable, [sys.executable] + sys.argv + ["--graph", "0"])
+            if world == 1:
+                os.execv(sys.executable, [sys.executable] + sys.argv + ["--graph", "0"])
+            use_graph, step, graph_note = False, step_body, "eager (graph capture failed)"
+            ids_dev, labels_dev = ids_host.to(dev), labels_host.to(dev)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -379,7 +384,10 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "tc::bayes_gemm_kernel (fwd + dgrad + fused wgrad, all layers)",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
+                # dram__bytes_read+write of the profiled FFN-shape fwd launch (S=4, M=4096, N=3072, K=768; algorithmic
+                # operand+result bytes 145 MB, most of the bf16 result still in L2 at kernel end):
+                # profiles/r01_ncu_full_kernels.md row 5
+                "traffic": 92.0e6, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
                 "share_of_step": g_ms / kern_steps / ms,
                 "timing": "CUDA events around every launch on the launching stream" +
                           (", taken in eager executions of the same step after the timed graph replays" if use_graph else

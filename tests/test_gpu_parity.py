@@ -419,7 +419,8 @@ def test_kl_grad_true_flows_through_model_scalars():
 
 # ------------------------------------------------------------------ tcgen05 contractions vs fp32 math on the same bf16 inputs
 @pytest.mark.parametrize("S,M,N,K", [(1, 128, 256, 64), (1, 128, 256, 512), (2, 256, 512, 256), (3, 200, 768, 136),
-                                     (1, 1000, 72, 3072), (2, 384, 3072, 768), (4, 1024, 768, 768)])
+                                     (1, 1000, 72, 3072), (2, 384, 3072, 768), (4, 1024, 768, 768),
+                                     (2, 300, 520, 136), (1, 1000, 776, 1544), (4, 513, 264, 72), (1, 2048, 3072, 768)])
 def test_tc_contractions(S, M, N, K):
     lib = _lib.load()
     gen = torch.Generator().manual_seed(S * 1000 + M)
