@@ -25,13 +25,15 @@
 //     run-to-run deterministic (no float atomics, no turn-taking between CTAs).
 //     The partials are written and re-read back to back; for BERT-sized layers
 //     they are L2-resident (<= 75 MB against 126 MB).
+#include <cstdlib>
+
 #include "bf_tc.cuh"
 
 namespace wg {
 using namespace tc;
 
 constexpr int BM = 128, BN = 256;
-constexpr int A_BYTES = BM * BLOCK_K * 2, B_BYTES = BN * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = BM * BLOCK_K * 2;
 constexpr int BOX_COLS = 32;                 // fp32 columns of one TMA-store box (128 B rows)
 constexpr int BOX_BYTES = BM * 128;          // 16 KiB
 constexpr int BOXES = BN / BOX_COLS;         // 8
@@ -39,10 +41,15 @@ constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS;  // group g owns boxes
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 2 * BN;
 
-template <bool WITH_MU>
+// PAIR: two CTAs of a cluster share one 256-row MMA (cta_group::2, see bf_gemm_tc2.cu): each loads its 128 rows of
+// gy^T and only 128 of the 256 x columns, 32 KiB per k-step instead of 48 KiB, so the ring gets 6 stages.
+template <bool WITH_MU, bool PAIR>
 struct Cfg {
-    static constexpr int kStages = WITH_MU ? 3 : 4;
+    static constexpr int LOAD_N = PAIR ? BN / 2 : BN;  // x columns this CTA loads
+    static constexpr int B_BYTES = LOAD_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BUFS = WITH_MU ? 2 : 1;  // staging boxes per epilogue group
+    static constexpr int kStages = PAIR ? (WITH_MU ? 5 : 6) : (WITH_MU ? 3 : 4);
     static constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + EPI_GROUPS * BUFS * BOX_BYTES + 256;
 };
 
@@ -70,13 +77,15 @@ __device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
     return it;
 }
 
-template <bool HAS_EPS, bool WITH_MU>
+template <bool HAS_EPS, bool WITH_MU, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     bayes_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
                        const __grid_constant__ CUtensorMap map_prho, const __grid_constant__ CUtensorMap map_pmu,
                        const __grid_constant__ Params p) {
-    using C = Cfg<WITH_MU>;
-    constexpr int kStages = C::kStages;
+    using C = Cfg<WITH_MU, PAIR>;
+    constexpr int kStages = C::kStages, STAGE_BYTES = C::STAGE_BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+    const bool leader = rank == 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -104,50 +113,60 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), EPI_WARPS);
+            mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * EPI_WARPS);  // PAIR: leader's copy collects both CTAs
         }
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+        else tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     const int64_t n_items = p.S * p.splits * p.i_tiles * p.j_tiles;
+    const int64_t worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x, n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA: its own halves) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
+            for (int64_t L = worker; L < n_items; L += n_workers) {
                 const Item it = decode_item(p, L);
-                const int i0 = it.i_blk * BM, j0 = it.j_blk * BN;
+                const int i0 = it.i_blk * (PAIR ? 2 * BM : BM) + (int)rank * BM;
+                const int j0 = it.j_blk * BN + (int)rank * C::LOAD_N;
                 for (int ks = it.k_begin; ks < it.k_end; ++ks) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                     const uint32_t b_dst = a_dst + A_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    if (leader) mbar_expect_tx(full_bar(stage), (PAIR ? 2 : 1) * STAGE_BYTES);
                     const int r0 = ks * BLOCK_K;
 #pragma unroll
-                    for (int a = 0; a < BM / ATOM_MN; ++a)  // gy[s][m][n]: MN-major, rows = reduction m
-                        tma_load_3d(a_dst + a * ATOM_BYTES, &map_gy, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
+                    for (int a = 0; a < BM / ATOM_MN; ++a) {  // gy[s][m][n]: MN-major, rows = reduction m
+                        if (PAIR) tma_load_3d_2sm(a_dst + a * ATOM_BYTES, &map_gy, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
+                        else tma_load_3d(a_dst + a * ATOM_BYTES, &map_gy, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
+                    }
 #pragma unroll
-                    for (int a = 0; a < BN / ATOM_MN; ++a)  // x[s][m][k]
-                        tma_load_3d(b_dst + a * ATOM_BYTES, &map_x, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
+                    for (int a = 0; a < C::LOAD_N / ATOM_MN; ++a) {  // x[s][m][k]
+                        if (PAIR) tma_load_3d_2sm(b_dst + a * ATOM_BYTES, &map_x, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
+                        else tma_load_3d(b_dst + a * ATOM_BYTES, &map_x, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
+                    }
                     if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(true, true, BM, BN);
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(true, true, PAIR ? 2 * BM : BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x, ++iter) {
+            for (int64_t L = worker; L < n_items; L += n_workers, ++iter) {
                 const Item it = decode_item(p, L);
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
@@ -160,13 +179,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint32_t a_src = smem_base + stage * STAGE_BYTES;
                     const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc,
-                                  (ks > it.k_begin || k > 0) ? 1u : 0u);
-                    umma_commit(empty_bar(stage));
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t accum = (ks > it.k_begin || k > 0) ? 1u : 0u;
+                        if (PAIR) umma_bf16_2sm(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc, accum);
+                        else umma_bf16(d_tmem, operand_desc<true>(a_src, k), operand_desc<true>(b_src, k), idesc, accum);
+                    }
+                    if (PAIR) umma_commit_2sm(empty_bar(stage));
+                    else umma_commit(empty_bar(stage));
                     if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
-                umma_commit(tfull_bar(acc));
+                if (PAIR) umma_commit_2sm(tfull_bar(acc));
+                else umma_commit(tfull_bar(acc));
             }
         }
     } else {
@@ -182,11 +205,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t my_out = out_base + grp * C::BUFS * BOX_BYTES;
         uint8_t* const my_out_gen = out_gen + grp * C::BUFS * BOX_BYTES;
         int iter = 0;
-        for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x, ++iter) {
+        for (int64_t L = worker; L < n_items; L += n_workers, ++iter) {
             const Item it = decode_item(p, L);
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
-            const int i0 = it.i_blk * BM, j0 = it.j_blk * BN;
+            const int i0 = it.i_blk * (PAIR ? 2 * BM : BM) + (int)rank * BM, j0 = it.j_blk * BN;
             const int64_t g_row = (int64_t)i0 + row;
             const bool row_ok = g_row < p.I;
             int n_boxes = BOXES;  // boxes that intersect the matrix
@@ -199,7 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (last_b < 0) {  // nothing to read: hand the accumulator straight back
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_leader(tempty_bar(acc));
+                    else mbar_arrive(tempty_bar(acc));
+                }
             }
 #pragma unroll 1
             for (int b = grp; b < n_boxes; b += EPI_GROUPS) {
@@ -225,7 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (b == last_b) {  // accumulator drained by this warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_leader(tempty_bar(acc));
+                        else mbar_arrive(tempty_bar(acc));
+                    }
                 }
                 if (store_thread) tma_store_wait_read<0>();  // the previous store of this group has read its buffer
                 named_bar_sync_dyn(1 + grp, 128);
@@ -256,40 +285,75 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's smem / TMEM must outlive the leader's last MMA
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <bool HAS_EPS, bool WITH_MU>
+template <bool HAS_EPS, bool WITH_MU, bool PAIR>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mm,
                   const Params& p, cudaStream_t st) {
-    auto kern = bayes_wgrad_kernel<HAS_EPS, WITH_MU>;
-    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<WITH_MU>::SMEM_BYTES));
+    auto kern = bayes_wgrad_kernel<HAS_EPS, WITH_MU, PAIR>;
+    constexpr int smem = Cfg<WITH_MU, PAIR>::SMEM_BYTES;
+    BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t n_items = p.S * p.splits * p.i_tiles * p.j_tiles;
-    const int64_t sms = bf_num_sms();
-    kern<<<(int)(n_items < sms ? n_items : sms), kThreads, Cfg<WITH_MU>::SMEM_BYTES, st>>>(ma, mb, mr, mm, p);
-    BF_LAUNCH_OK();
+    const int64_t workers = PAIR ? bf_num_sms() / 2 : bf_num_sms();
+    const int64_t use = n_items < workers ? n_items : workers;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(PAIR ? 2 * use : use));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    BF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mr, mm, p));
     return 0;
 }
 
 // ---- how many slices of the reduction: fill the persistent grid, keep items long enough that the
 // Philox epilogue (~10 us per 128x256 tile) stays hidden behind the next item's MMAs (0.22 us per k-step at peak)
-static int choose_splits(int64_t S, int64_t tiles, int k_steps) {
-    const int64_t sms = bf_num_sms();
+static int choose_splits(int64_t S, int64_t tiles, int k_steps, int64_t workers, double* cost_out) {
     const int64_t base = S * tiles;
     const double fixed = 14.0;  // per-item overhead in k-step units (pipeline fill + exposed part of the epilogue)
     int best = 1;
     double best_cost = 1e30;
     for (int sp = 1; sp <= 16; ++sp) {
         if (sp > 1 && k_steps / sp < 24) break;
-        const int64_t waves = (base * sp + sms - 1) / sms;
+        const int64_t waves = (base * sp + workers - 1) / workers;
         const double cost = (double)waves * ((double)((k_steps + sp - 1) / sp) + fixed) + 0.5 * sp;
         if (cost < best_cost - 1e-9) best_cost = cost, best = sp;
     }
+    if (cost_out) *cost_out = best_cost;
     return best;
+}
+
+// tile shape + slicing of one call: single CTAs on 128 x 256 tiles, or CTA pairs on 256 x 256 tiles (same time per
+// item, a third less operand traffic) when that does not cost waves.  BF_WGRAD_2CTA=0 / 2 forces single / pair.
+struct Plan {
+    bool pair;
+    int i_tiles, j_tiles, k_steps, splits;
+};
+static Plan make_plan(int64_t S, int64_t M, int64_t N, int64_t K) {
+    static const int mode = [] {
+        const char* e = getenv("BF_WGRAD_2CTA");
+        return e ? atoi(e) : 1;
+    }();
+    Plan a{}, b{};
+    double ca = 0, cb = 0;
+    const int ks = tc::cdiv(M, tc::BLOCK_K);
+    a.pair = false, a.i_tiles = tc::cdiv(N, BM), a.j_tiles = tc::cdiv(K, BN), a.k_steps = ks;
+    a.splits = choose_splits(S, (int64_t)a.i_tiles * a.j_tiles, ks, bf_num_sms(), &ca);
+    b.pair = true, b.i_tiles = tc::cdiv(N, 2 * BM), b.j_tiles = tc::cdiv(K, BN), b.k_steps = ks;
+    b.splits = choose_splits(S, (int64_t)b.i_tiles * b.j_tiles, ks, bf_num_sms() / 2, &cb);
+    if (mode == 0 || N < 2 * BM) return a;
+    if (mode == 2) return b;
+    return cb <= ca * 1.02 ? b : a;
 }
 
 constexpr int kRedThreads = 256;
@@ -421,13 +485,8 @@ __global__ void __launch_bounds__(kRedThreads) wgrad_reduce_kernel(const ReduceP
 
 }  // namespace wg
 
-static int64_t wgrad_partials(int64_t S, int64_t M, int64_t N, int64_t K) {
-    const int64_t tiles = (int64_t)tc::cdiv(N, wg::BM) * tc::cdiv(K, wg::BN);
-    return S * wg::choose_splits(S, tiles, tc::cdiv(M, tc::BLOCK_K));
-}
-
 int64_t bf_wgrad_fused_workspace_bytes_impl(int64_t S, int64_t M, int64_t N, int64_t K, int with_mu) {
-    return wgrad_partials(S, M, N, K) * N * K * (int64_t)sizeof(float) * (with_mu ? 2 : 1);
+    return S * wg::make_plan(S, M, N, K).splits * N * K * (int64_t)sizeof(float) * (with_mu ? 2 : 1);
 }
 
 int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t M, int64_t N, int64_t K,
@@ -443,8 +502,8 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     const bool eps = eps_in != nullptr, with_mu = grad_mu != nullptr;
     Params p{};
     p.S = S, p.I = N, p.J = K, p.R = M;
-    p.i_tiles = tc::cdiv(N, BM), p.j_tiles = tc::cdiv(K, BN), p.k_steps = tc::cdiv(M, tc::BLOCK_K);
-    p.splits = choose_splits(S, (int64_t)p.i_tiles * p.j_tiles, p.k_steps);
+    const Plan plan = make_plan(S, M, N, K);
+    p.i_tiles = plan.i_tiles, p.j_tiles = plan.j_tiles, p.k_steps = plan.k_steps, p.splits = plan.splits;
     p.eps_in = eps_in;
     p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.tensor_id = tensor_id;
     p.step_ptr = bf_step_counter();
@@ -458,10 +517,11 @@ int bf_linear_wgrad_fused_bf16(const void* gy, const void* x, int64_t S, int64_t
     if ((rc = tc::encode_map(&mb, x, S, M, K, tc::BLOCK_K))) return rc;
     if ((rc = tc::encode_map(&mr, part_rho, T, N, K, BM, true))) return rc;
     if ((rc = tc::encode_map(&mm, with_mu ? part_mu : part_rho, T, N, K, BM, true))) return rc;
-    if (with_mu)
-        rc = eps ? launch<true, true>(ma, mb, mr, mm, p, st) : launch<false, true>(ma, mb, mr, mm, p, st);
-    else
-        rc = eps ? launch<true, false>(ma, mb, mr, mm, p, st) : launch<false, false>(ma, mb, mr, mm, p, st);
+#define BF_WG_LAUNCH(PAIR)                                                                                        \
+    (with_mu ? (eps ? launch<true, true, PAIR>(ma, mb, mr, mm, p, st) : launch<false, true, PAIR>(ma, mb, mr, mm, p, st)) \
+             : (eps ? launch<true, false, PAIR>(ma, mb, mr, mm, p, st) : launch<false, false, PAIR>(ma, mb, mr, mm, p, st)))
+    rc = plan.pair ? BF_WG_LAUNCH(true) : BF_WG_LAUNCH(false);
+#undef BF_WG_LAUNCH
     if (rc) return rc;
 
     ReduceParams r{};

@@ -367,9 +367,19 @@ def run_ours(args):
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    def leave():
+        """End of a multi-rank run.  Tearing NCCL down while a CUDA graph that captured its collectives is still
+        alive can hang at exit: drop the graph first, and leave without running destructors."""
+        if world == 1:
+            return
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
 
     value = world * B / (ms / 1e3)
@@ -422,8 +432,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clk, "execution": graph_note,
             "grad_allreduce_bytes_per_step": sync.bytes_last_step}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":
