@@ -630,15 +630,16 @@ __global__ void __launch_bounds__(kThreads) sample_kl_multi_kernel(const MultiPa
 }
 
 // one block per output slot: sum the chunk partials of that slot in chunk order
-__global__ void __launch_bounds__(64) sample_kl_multi_finish_kernel(const float* __restrict__ partials,
+__global__ void __launch_bounds__(256) sample_kl_multi_finish_kernel(const float* __restrict__ partials,
                                                                     const int2* __restrict__ slot_ranges, int SC, int s0,
                                                                     int S, float* __restrict__ logq,
                                                                     float* __restrict__ logp) {
     const int slot = blockIdx.x;
     const int2 r = __ldg(slot_ranges + slot);  // chunks [r.x, r.y)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int v = warp; v < 2 * SC; v += 2) {
+    for (int v = warp; v < 2 * SC; v += 8) {  // one warp per value; fixed lane-strided order, then a shuffle tree
         double t = 0.0;
+#pragma unroll 4
         for (int c = r.x + lane; c < r.y; c += 32) t += (double)partials[(int64_t)c * 2 * SC + v];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -879,7 +880,7 @@ extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t
             default: sample_kl_multi_kernel<8><<<grid, kThreads, 0, st>>>(mp); break;
         }
         BF_LAUNCH_OK();
-        sample_kl_multi_finish_kernel<<<n_slots, 64, 0, st>>>(mp.partials, reinterpret_cast<const int2*>(slot_ranges), sc,
+        sample_kl_multi_finish_kernel<<<n_slots, 256, 0, st>>>(mp.partials, reinterpret_cast<const int2*>(slot_ranges), sc,
                                                              s0, S, logq_out, logp_out);
         BF_LAUNCH_OK();
         s0 += sc;

@@ -124,3 +124,30 @@ def advance_step(n: int = 1) -> None:
     if t is None:
         raise RuntimeError("enable_device_step(device) first")
     t.add_(n)
+
+
+@contextlib.contextmanager
+def hf_capture_compat():
+    """Use around `torch.cuda.graph(...)` when the host model is a HuggingFace transformer.
+
+    transformers treats "the CUDA stream is capturing" like tracing and then always
+    materialises a [B,1,T,T] attention mask (transformers/masking_utils.py,
+    `_ignore_bidirectional_mask_sdpa`), which pushes SDPA from the fused cuDNN kernel
+    onto the unfused math path (and into cuBLAS calls that cannot initialise while
+    capturing).  With `attention_mask=None` there is no data-dependent branch to
+    protect, so inside this context the eager behaviour (no mask) is kept.  No-op
+    when transformers is not importable."""
+    try:
+        import transformers.masking_utils as hf_masking
+    except Exception:  # pragma: no cover
+        yield
+        return
+    saved = getattr(hf_masking, "is_tracing", None)
+    if saved is None:
+        yield
+        return
+    hf_masking.is_tracing = lambda *a, **k: False
+    try:
+        yield
+    finally:
+        hf_masking.is_tracing = saved

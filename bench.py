@@ -276,18 +276,9 @@ def run_ours(args):
             graph = torch.cuda.CUDAGraph()
             optim.zero_grad(set_to_none=True)
             l0 = ops.stats["launches"]
-            # HF treats "CUDA stream is capturing" like tracing and then always materialises a [B,1,T,T]
-            # attention mask (transformers/masking_utils.py:_ignore_bidirectional_mask_sdpa), which pushes SDPA
-            # onto the unfused math path.  With attention_mask=None there is no data-dependent branch to protect,
-            # so keep the eager behaviour (no mask -> fused cuDNN attention) while capturing.
-            import transformers.masking_utils as hf_masking
-            hf_is_tracing = hf_masking.is_tracing
-            hf_masking.is_tracing = lambda *a, **k: False
-            try:
-                with torch.cuda.graph(graph, stream=side):  # same stream as the warm-up: handles/workspaces exist
-                    static_out = step_body(static_ids, static_labels)
-            finally:
-                hf_masking.is_tracing = hf_is_tracing
+            # bf.hf_capture_compat: keep HF on the mask-free fused-attention path while capturing (see its docstring)
+            with bf.hf_capture_compat(), torch.cuda.graph(graph, stream=side):  # same stream as the warm-up
+                static_out = step_body(static_ids, static_labels)
             launches_per_graph = ops.stats["launches"] - l0
 
             def step(ids, labels):  # noqa: F811

@@ -49,5 +49,12 @@ db = torch.empty(S, N, device=DEV)
 bws = torch.zeros(lib.bf_bias_grad_workspace_bytes(S, M, N), dtype=torch.uint8, device=DEV)
 for _ in range(2):
     lib.bf_bias_grad(gy.data_ptr(), BF_BF16, db.data_ptr(), S, M, N, bws.data_ptr(), st)
+# multi-tensor sample+KL over a 2 x (4096 x 4096 + bias) model, S = 4, MOPED prior, bf16 weights
+import bayeformers_b200 as bf
+net = torch.nn.Sequential(torch.nn.Linear(4096, 4096), torch.nn.Linear(4096, 4096))
+bm = bf.to_bayesian(net, delta=0.05, freeze=True, gemm_dtype="bf16").to(DEV)
+bf.enable_presample(bm)
+for _ in range(2):
+    bm._presampler.run(4)
 torch.cuda.synchronize()
 print("profile target done")

@@ -489,6 +489,101 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
 
 
 
+
+
+# ------------------------------------------------------------------ CUDA-graph replay == eager (BERT-base layers)
+def test_cuda_graph_replay_equals_eager_bert_layers():
+    """A captured training step (multi-tensor sampling, folded S-sample fwd, ELBO, bwd) replayed with the
+    device-resident step counter at d gives bit-identical logits and rho-gradients to the eager step that
+    draws the same Philox stream; a different counter gives a different draw.  BERT-base width, 2 layers."""
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(0)
+    cfg = BertConfig(num_labels=2, num_hidden_layers=2)
+    bf.manual_seed(4321)
+    bm = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True, gemm_dtype="bf16", kl_grad=True)
+    bf.accelerate_host_(bm)
+    bm = bm.to(DEV).eval()  # eval: dropout off (the layers still sample, quirk Q9)
+    bf.enable_presample(bm)
+    bf.cast_frequentist_(bm, torch.bfloat16)
+    counter = bf.enable_device_step(DEV)
+    try:
+        S, B, T = 4, 4, 128
+        ids = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(1)).to(DEV)
+        rho_params = [l.weight.rho for l in bm.bayesian_children]
+
+        def step():
+            for p in bm.parameters():
+                p.grad = None
+            with bf.mc_samples(S):
+                logits = bm(input_ids=ids.repeat(S, 1)).logits.float()
+            loss = logits.square().mean() + 1e-6 * (bm.log_variational_posterior() - bm.log_prior()).mean()
+            loss.backward()
+            return logits
+
+        RUN, D = 7, 3
+        # everything runs on one non-default stream: autograd binds each parameter's AccumulateGrad node to the
+        # stream of its first use, and the legacy default stream cannot be joined to a capturing stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            bm._presampler._runs = RUN - 1
+            counter.fill_(D)
+            want = step().detach().clone()
+            want_g = [p.grad.clone() for p in rho_params]
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in bm.parameters():
+            p.grad = None
+        bm._presampler._runs = RUN - 1  # the captured launch bakes host step RUN
+        g = torch.cuda.CUDAGraph()
+        with bf.hf_capture_compat(), torch.cuda.graph(g, stream=side):
+            static_logits = step()
+        with torch.cuda.stream(side):
+            counter.fill_(D)
+            g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_logits, want)
+        for p, w in zip(rho_params, want_g):
+            # cuDNN's attention backward accumulates dQ with atomics and rounds it to bf16: gradients agree to
+            # bf16 noise, not bitwise (the forward above is bit-exact)
+            assert rel_err(p.grad.cpu().numpy(), w.cpu().numpy()) < 1e-3
+        with torch.cuda.stream(side):
+            counter.fill_(D + 1)
+            g.replay()
+        torch.cuda.synchronize()
+        assert not torch.equal(static_logits, want)
+    finally:
+        bf.disable_device_step()
+
+# ------------------------------------------------------------------ user-loop helpers (section 8f row 4)
+def test_sample_bayesian_folded_equals_reference_style_loop():
+    """harness.sample_bayesian: one folded forward == the reference's sequential S-loop
+    (examples/bert_glue.py:56-73) when both consume the same eps."""
+    import copy
+    torch.manual_seed(11)
+    net = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8))
+    a = bf.to_bayesian(net, delta=0.05).to(DEV)
+    b = copy.deepcopy(a)
+    S, B = 5, 6
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 32, generator=gen).to(DEV)
+    for m in (a, b):
+        g2 = torch.Generator().manual_seed(9)
+        for layer in m.bayesian_children:
+            layer.weight.normal = FixedEps([torch.randn(layer.weight.mu.shape, generator=g2) for _ in range(S)])
+            layer.bias.normal = FixedEps([torch.randn(layer.bias.mu.shape, generator=g2) for _ in range(S)])
+    call = lambda out: out  # the model returns the logits tensor itself
+    raw_a, mean_a, lp_a, lq_a = bf.sample_bayesian(a, {"input": x}, S, select=call, fold=True)
+    raw_b, mean_b, lp_b, lq_b = bf.sample_bayesian(b, {"input": x}, S, select=call, fold=False)
+    assert raw_a.shape == (S, B, 8) and mean_a.shape == (B, 8)
+    assert rel_err(raw_a.detach().cpu().numpy(), raw_b.detach().cpu().numpy()) < FP32_TOL
+    assert abs(float(lp_a) - float(lp_b)) <= FP32_TOL * abs(float(lp_b))
+    assert abs(float(lq_a) - float(lq_b)) <= FP32_TOL * abs(float(lq_b))
+    stats = bf.predictive_stats(raw_a, torch.zeros(B, dtype=torch.long, device=DEV))
+    assert stats["probs"].shape == (B, 8) and float(stats["acc_std"]) >= 0.0
+
 # ------------------------------------------------------------------ multi-tensor sampling (section 8f row 2)
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_presample_equals_per_layer_path(mode):
