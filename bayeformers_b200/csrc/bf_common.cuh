@@ -114,8 +114,48 @@ __device__ __forceinline__ float4 bf_eps_quad(uint32_t q, uint32_t sample, uint3
 // ---------------------------------------------------------------------------
 // elementwise math of the variational parameters
 // ---------------------------------------------------------------------------
+// ---- MUFU-based transcendental helpers ------------------------------------------------------
+// The sample+KL kernels are issue-bound, not HBM-bound (profiles/README.md): libdevice's expf / log1pf /
+// logf cost ~80 instructions per element with their slow-path branches.  These keep ~1e-6 relative
+// accuracy (the parity bar is 1e-5 on sums, 1e-6 norm-wise on w) in ~25.
+__device__ __forceinline__ float bf_ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float bf_lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// exp(x) for x <= ~20: x*log2(e) split into a rounded product and its fma residual, so the error does
+// not grow with |x| the way __expf's does
+__device__ __forceinline__ float bf_exp(float x) {
+    const float t = x * 1.4426950408889634f;
+    float r = fmaf(x, 1.4426950408889634f, -t);
+    r = fmaf(x, 1.925963033500e-8f, r);  // low part of log2(e)
+    const float z = bf_ex2_approx(t);
+    return fmaf(z, r * 0.6931471805599453f, z);
+}
+// log(1 + z), z >= 0.  Small z: 2 atanh(s), s = z / (2 + z), odd series (s <= 0.2, truncation < 1e-8 relative);
+// otherwise lg2.approx(1 + z) whose 2^-22 absolute error is relative to a result >= 0.4.
+__device__ __forceinline__ float bf_log1p_pos(float z) {
+    if (z < 0.5f) {
+        const float s = z * bf_rcp_approx(2.0f + z);
+        const float s2 = s * s;
+        float p = fmaf(s2, 1.0f / 9.0f, 1.0f / 7.0f);
+        p = fmaf(p, s2, 0.2f);
+        p = fmaf(p, s2, 1.0f / 3.0f);
+        p = fmaf(p, s2, 1.0f);
+        return 2.0f * s * p;
+    }
+    return bf_lg2_approx(1.0f + z) * 0.6931471805599453f;
+}
+// log(x) for the per-element -log(sigma) term of a SUM of log-probs: absolute error ~2e-7
+__device__ __forceinline__ float bf_log_sum_term(float x) { return bf_lg2_approx(x) * 0.6931471805599453f; }
+
 // sigma = softplus(rho), beta=1, threshold=20 (torch F.softplus; gaussian.py:88)
-__device__ __forceinline__ float bf_softplus(float rho) { return rho > 20.0f ? rho : log1pf(expf(rho)); }
+__device__ __forceinline__ float bf_softplus(float rho) { return rho > 20.0f ? rho : bf_log1p_pos(bf_exp(rho)); }
 
 // d softplus / d rho as torch's softplus_backward computes it: z/(z+1), z = exp(rho)
 __device__ __forceinline__ float bf_softplus_grad(float rho) {

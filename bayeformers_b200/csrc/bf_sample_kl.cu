@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_kernel(const SampleKlP
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             sigma[j] = bf_softplus(rho[j]);
-            qc[j] = -BF_LOG_SQRT_2PI - logf(sigma[j]);
+            qc[j] = -BF_LOG_SQRT_2PI - bf_log_sum_term(sigma[j]);
             qiv[j] = bf_rcp_approx(2.0f * __fmul_rn(sigma[j], sigma[j]));
             if (PRIOR == BF_PRIOR_GAUSSIAN) {
                 if (p.prior_rho != nullptr) {
                     const float sp = bf_softplus(prho[j]);
-                    pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
+                    pc[j] = -BF_LOG_SQRT_2PI - bf_log_sum_term(sp);
                     piv[j] = bf_rcp_approx(2.0f * __fmul_rn(sp, sp));
                 } else {
                     pc[j] = p.prior_const_c, piv[j] = p.prior_const_iv;
@@ -267,12 +267,12 @@ __device__ __forceinline__ void derive_quad(const SampleKlParams& p, const RawQu
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         Q.sigma[j] = bf_softplus(rho[j]);
-        Q.qc[j] = -BF_LOG_SQRT_2PI - logf(Q.sigma[j]);
+        Q.qc[j] = -BF_LOG_SQRT_2PI - bf_log_sum_term(Q.sigma[j]);
         Q.qiv[j] = bf_rcp_approx(2.0f * __fmul_rn(Q.sigma[j], Q.sigma[j]));
         if (PRIOR == BF_PRIOR_GAUSSIAN) {
             if (p.prior_rho != nullptr) {
                 const float sp = bf_softplus(prho[j]);
-                Q.pc[j] = -BF_LOG_SQRT_2PI - logf(sp);
+                Q.pc[j] = -BF_LOG_SQRT_2PI - bf_log_sum_term(sp);
                 Q.piv[j] = bf_rcp_approx(2.0f * __fmul_rn(sp, sp));
             } else {  // constant prior sigma (MOPED: rho_p == 1 everywhere), folded on the host
                 Q.pc[j] = p.prior_const_c;
