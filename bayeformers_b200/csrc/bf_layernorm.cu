@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int kLnThreads = 512;  // backward: 1 block of 16 warps per SM (128 registers per thread)
+constexpr int kLnThreads = 384;  // backward: 1 block of 12 warps per SM (<= 168 registers per thread), 2 rows in flight per warp
 constexpr int kLnWarps = kLnThreads / 32;
 constexpr int kLnFwdThreads = 256;  // forward: 4 blocks of 8 warps per SM (<= 64 registers per thread)
 constexpr int kLnFwdWarps = kLnFwdThreads / 32;
@@ -156,14 +156,26 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const T* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = 0.0f;
 
-    for (int64_t m = (int64_t)blockIdx.x * kLnWarps + warp; m < M; m += (int64_t)nblk * kLnWarps) {
-        const T* xr = x + (row0 + m) * H;
-        const T* gr = gy + (row0 + m) * H;
-        Pack8<T> px[C], pg[C];
+    const int64_t m_step = (int64_t)nblk * kLnWarps;
+    int64_t m = (int64_t)blockIdx.x * kLnWarps + warp;
+    Pack8<T> nx[C], ng[C];  // software pipeline: the next row's loads are in flight while this row is reduced
+    if (m < M) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            px[c].load(xr + c * 256 + lane * 8);
-            pg[c].load(gr + c * 256 + lane * 8);
+            nx[c].load(x + (row0 + m) * H + c * 256 + lane * 8);
+            ng[c].load(gy + (row0 + m) * H + c * 256 + lane * 8);
+        }
+    }
+    for (; m < M; m += m_step) {
+        Pack8<T> px[C], pg[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) px[c] = nx[c], pg[c] = ng[c];
+        if (m + m_step < M) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                nx[c].load(x + (row0 + m + m_step) * H + c * 256 + lane * 8);
+                ng[c].load(gy + (row0 + m + m_step) * H + c * 256 + lane * 8);
+            }
         }
         const float mean = __ldg(mean_in + row0 + m), rstd = __ldg(rstd_in + row0 + m);
         float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
@@ -200,37 +212,48 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const T* __re
         }
     }
 
-    // ---- block tree over the 16 warps, at most 4 writer warps per round (32 KiB of shared memory at H = 1024) ----
+    // ---- block reduction: warps 4.. fold into warps 0..3 four at a time (32 KiB of shared memory at H = 1024),
+    // then warps 1..3 fold into warp 0.  Fixed order -> deterministic.
     constexpr int kRedRows = 4;
     __shared__ float red[kRedRows][2 * H];
     __shared__ bool is_last;
 #pragma unroll 1
-    for (int half = kLnWarps / 2; half >= 1; half >>= 1) {
-#pragma unroll 1
-        for (int off = 0; off < half; off += kRedRows) {
-            const int w_lo = half + off, r_lo = off;
-            const int cnt = (half - off) < kRedRows ? (half - off) : kRedRows;
-            if (warp >= w_lo && warp < w_lo + cnt) {
+    for (int base = kRedRows; base < kLnWarps + kRedRows; base += kRedRows) {
+        // round `base`: writers are warps [base, base+4) -- or, in the last round, warps [1, 4) folding into warp 0
+        const bool last = base >= kLnWarps;
+        const int w_lo = last ? 1 : base, w_hi = last ? kRedRows : base + kRedRows;
+        if (warp >= w_lo && warp < w_hi) {
 #pragma unroll
-                for (int c = 0; c < C; ++c)
+            for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        red[warp - w_lo][c * 256 + lane * 8 + j] = acc_g[c][j];
-                        red[warp - w_lo][H + c * 256 + lane * 8 + j] = acc_b[c][j];
-                    }
-            }
-            __syncthreads();
-            if (warp >= r_lo && warp < r_lo + cnt) {
-#pragma unroll
-                for (int c = 0; c < C; ++c)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        acc_g[c][j] += red[warp - r_lo][c * 256 + lane * 8 + j];
-                        acc_b[c][j] += red[warp - r_lo][H + c * 256 + lane * 8 + j];
-                    }
-            }
-            __syncthreads();
+                for (int j = 0; j < 8; ++j) {
+                    red[warp - w_lo][c * 256 + lane * 8 + j] = acc_g[c][j];
+                    red[warp - w_lo][H + c * 256 + lane * 8 + j] = acc_b[c][j];
+                }
         }
+        __syncthreads();
+        if (!last) {
+            if (warp < kRedRows) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc_g[c][j] += red[warp][c * 256 + lane * 8 + j];
+                        acc_b[c][j] += red[warp][H + c * 256 + lane * 8 + j];
+                    }
+            }
+        } else if (warp == 0) {
+#pragma unroll 1
+            for (int r = 0; r < kRedRows - 1; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc_g[c][j] += red[r][c * 256 + lane * 8 + j];
+                        acc_b[c][j] += red[r][H + c * 256 + lane * 8 + j];
+                    }
+        }
+        __syncthreads();
     }
     float* my_part = partial + ((int64_t)s * nblk + blockIdx.x) * 2 * H;
     if (warp == 0) {

@@ -688,16 +688,17 @@ def test_host_layernorm_shared_affine_matches_torch():
     assert rel_err(fast.bias.grad.cpu().numpy(), ref.bias.grad.cpu().numpy()) < 2e-5
 
 # ------------------------------------------------------------------ Embedding / LayerNorm (rows A9 / A10)
-def test_embedding_and_layernorm_against_composed_oracle():
+@pytest.mark.parametrize("H", [16, 256])  # 16: torch LayerNorm path, 256: native S-sample LayerNorm kernels
+def test_embedding_and_layernorm_against_composed_oracle(H):
     torch.manual_seed(0)
-    emb, ln = torch.nn.Embedding(50, 16, padding_idx=0), torch.nn.LayerNorm(16)
+    emb, ln = torch.nn.Embedding(50, H, padding_idx=0), torch.nn.LayerNorm(H)
     with torch.no_grad():
-        ln.weight.add_(0.1 * torch.randn(16)); ln.bias.add_(0.1 * torch.randn(16))
+        ln.weight.add_(0.1 * torch.randn(H)); ln.bias.add_(0.1 * torch.randn(H))
     be = bnn.Embedding.from_frequentist(emb, delta=0.05).to(DEV)
     bl = bnn.LayerNorm.from_frequentist(ln, delta=0.05).to(DEV)
     gen = torch.Generator().manual_seed(4)
     S = 3
-    e_emb, e_w, e_b = torch.randn(S, 50, 16, generator=gen), torch.randn(S, 16, generator=gen), torch.randn(S, 16, generator=gen)
+    e_emb, e_w, e_b = torch.randn(S, 50, H, generator=gen), torch.randn(S, H, generator=gen), torch.randn(S, H, generator=gen)
     be.weight.normal, bl.weight.normal, bl.bias.normal = FixedEps(list(e_emb)), FixedEps(list(e_w)), FixedEps(list(e_b))
     ids = torch.randint(0, 50, (4, 7), generator=gen)
     with bf.mc_samples(S):
@@ -710,9 +711,9 @@ def test_embedding_and_layernorm_against_composed_oracle():
     outs, lps, lqs = [], [], []
     for s in range(S):
         We, Ww, Wb = (O.gaussian_sample(m, r, e) for m, r, e in ((mu_e, rho_e, e_emb[s]), (mu_w, rho_w, e_w[s]), (mu_b, rho_b, e_b[s])))
-        outs.append(torch.nn.functional.layer_norm(torch.nn.functional.embedding(ids, We, padding_idx=0), (16,), Ww, Wb, ln.eps))
+        outs.append(torch.nn.functional.layer_norm(torch.nn.functional.embedding(ids, We, padding_idx=0), (H,), Ww, Wb, ln.eps))
         lqs.append(O.gaussian_log_prob(We.detach(), mu_e.detach(), rho_e.detach()))
-        lps.append(O.gaussian_log_prob(We.detach(), emb.weight.detach(), torch.ones(50, 16)))
+        lps.append(O.gaussian_log_prob(We.detach(), emb.weight.detach(), torch.ones(50, H)))
     ref = torch.cat(outs)
     ref.square().sum().backward()
     assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < FP32_TOL
