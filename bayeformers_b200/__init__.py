@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as tnn
 
-from . import nn, runtime  # noqa: F401  (bayeformers_b200.nn is part of the public surface)
+from . import nn, optim, runtime  # noqa: F401  (bayeformers_b200.nn is part of the public surface)
 from .nn import TORCH2BAYE, TORCH2BAYE_ALL
 from .nn.model import Model
 from .nn.parameters.base import Parameter

@@ -24,6 +24,12 @@ class BfTensorDesc(ctypes.Structure):
                 ("sigma1", c_float), ("sigma2", c_float), ("vec", c_int32)]
 
 
+class BfOptDesc(ctypes.Structure):
+    """`bf_opt_desc` of include/bayeformers_b200.h (fused clip + AdamW)."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", c_int64), ("dtype", c_int32), ("vec", c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/bayeformers_b200.h one to one
 SIGNATURES = {
     "bf_abi_version": (c_int32, []),
@@ -53,6 +59,10 @@ SIGNATURES = {
                                         c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                         c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
                                         c_int32, c_void_p, c_void_p]),
+    "bf_optim_chunk_elems": (c_int32, []),
+    "bf_clip_adamw_workspace_bytes": (c_int64, [c_int64]),
+    "bf_clip_adamw_step": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_float, c_float, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_bias_grad_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "bf_layernorm_supported": (c_int32, [c_int64]),
     "bf_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--kl-grad", type=int, default=1)
     ap.add_argument("--ref-batch", type=int, default=2, help="sequences per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-optim", type=int, default=1, help="bf.optim.ClipAdamW instead of clip_grad_norm_ + AdamW")
     ap.add_argument("--presample", type=int, default=1, help="one multi-tensor sample+KL launch per forward")
     ap.add_argument("--host-ln", type=int, default=1,
                     help="route the host model's frequentist LayerNorms through the native LayerNorm kernels")
@@ -189,6 +190,7 @@ def workload_config(args):
                         "training step (S-sample fwd + ELBO + bwd + clip + AdamW)",
             "seq_len": args.seq, "mc_samples": args.samples, "batch_per_gpu": args.batch,
             "global_batch": args.batch * args.gpus, "gemm": args.gemm, "kl_grad": bool(args.kl_grad),
+            "optimizer": "bf.optim.ClipAdamW (fused clip + AdamW)" if args.fused_optim else "clip_grad_norm_ + torch AdamW(fused)",
             "sampling": "multi-tensor (1 launch per forward)" if args.presample else "per layer",
             "host_layernorm": "native kernels (bf_layernorm_*)" if args.host_ln else "torch",
             "parallelism": f"dp{args.gpus} (batch sharded, identical Philox weights per rank, NCCL grad all-reduce)",
@@ -231,7 +233,10 @@ def run_ours(args):
         bf.cast_frequentist_(bm, torch.bfloat16)
     params = [p for p in bm.parameters() if p.requires_grad]
     use_graph = bool(args.graph) and not args.profile
-    optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True, capturable=use_graph)
+    if args.fused_optim:  # global-norm clip + AdamW in two launches (section 8f row 3)
+        optim = bf.optim.ClipAdamW(params, lr=2e-5, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0)
+    else:
+        optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True, capturable=use_graph)
     sync = parallel.GradSync(bm)
     bf.enable_device_step(dev)  # eps = f(seed, tensor, host_step + device_step, sample): graph replays draw fresh eps
 
@@ -253,7 +258,8 @@ def run_ours(args):
         loss = (lq - lp) / N_BATCHES + nll
         loss.backward()
         sync.finish()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if not args.fused_optim:
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
         optim.step()
         return loss, lp, lq
 

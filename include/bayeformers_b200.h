@@ -233,6 +233,38 @@ int bf_layernorm_bwd(const void* gy, const void* x, int32_t dtype, const float* 
                      const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, void* dx, float* dgamma,
                      float* dbeta, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Fused global-norm clipping + AdamW over all trainable tensors.
+ * Replaces clip_grad_norm_(params, max_norm) + AdamW.step() of the reference's
+ * training loop (examples/bert_glue.py:240-241); arithmetic of torch.optim.AdamW
+ * (decoupled weight decay, bias correction).
+ *
+ * descs      DEVICE array of per-tensor descriptors; `grad == NULL` skips a tensor
+ * chunks     DEVICE int32 pairs {tensor index, chunk index}; a chunk is
+ *            bf_optim_chunk_elems() consecutive elements of one tensor
+ * steps      DEVICE float[n_tensors], zero-initialised by the caller: per-tensor update counts
+ *            (torch semantics: a tensor without a gradient does not advance); incremented by the
+ *            call itself, device-resident so a captured CUDA graph advances them on replay
+ * max_norm   <= 0 disables clipping
+ * grad_norm_out  NULL or DEVICE float[1]: global L2 norm of the unclipped gradients
+ * workspace  bf_clip_adamw_workspace_bytes(n_chunks) bytes, contents irrelevant
+ * ------------------------------------------------------------------------- */
+typedef struct bf_opt_desc {
+    void* param;       /* [n] of dtype, updated in place */
+    const void* grad;  /* [n] of dtype */
+    float* exp_avg;    /* [n] fp32 */
+    float* exp_avg_sq; /* [n] fp32 */
+    int64_t n;
+    int32_t dtype; /* BF_F32 / BF_BF16 (param and grad) */
+    int32_t vec;   /* 1: n % 4 == 0 and all four pointers 16 B aligned (8 B for bf16 param / grad) */
+} bf_opt_desc;
+
+int32_t bf_optim_chunk_elems(void);
+int64_t bf_clip_adamw_workspace_bytes(int64_t n_chunks);
+int bf_clip_adamw_step(const bf_opt_desc* descs, const int32_t* chunks, int32_t n_chunks, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, float max_norm, float* steps,
+                       float* grad_norm_out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

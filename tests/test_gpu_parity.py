@@ -491,6 +491,67 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
 
 
 
+
+# ------------------------------------------------------------------ fused clip + AdamW (section 8f row 3)
+@pytest.mark.parametrize("max_norm", [None, 0.5])
+def test_clip_adamw_matches_torch_cpu(max_norm):
+    """bf.optim.ClipAdamW == clip_grad_norm_ + torch.optim.AdamW (the reference loop's optimizer step,
+    examples/bert_glue.py:240-241) evaluated by torch on the CPU, over several steps and ragged sizes."""
+    gen = torch.Generator().manual_seed(17)
+    shapes = [(1,), (7,), (33, 5), (128, 64), (16385,), (3, 16384)]
+    ref = [torch.nn.Parameter(torch.randn(sh, generator=gen)) for sh in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    o_mine = bf.optim.ClipAdamW(mine, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1, max_grad_norm=max_norm)
+    for it in range(4):
+        grads = [torch.randn(sh, generator=gen) * (3.0 if it % 2 else 0.01) for sh in shapes]
+        for p, q, g in zip(ref, mine, grads):
+            p.grad, q.grad = g.clone(), g.clone().to(DEV)
+        if it == 2:  # a tensor without a gradient is skipped by both
+            ref[1].grad, mine[1].grad = None, None
+        norm_ref = (torch.nn.utils.clip_grad_norm_(ref, max_norm) if max_norm is not None
+                    else torch.sqrt(sum((p.grad.double() ** 2).sum() for p in ref if p.grad is not None)))
+        o_ref.step()
+        norm = o_mine.step()
+        assert abs(float(norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+        for p, q in zip(ref, mine):
+            assert rel_err(q.detach().cpu().numpy(), p.detach().numpy()) < 2e-6
+    for i, p in enumerate(ref):
+        st = o_ref.state[p]
+        assert rel_err(o_mine.exp_avg[i].cpu().numpy(), st["exp_avg"].numpy()) < 1e-5
+        assert rel_err(o_mine.exp_avg_sq[i].cpu().numpy(), st["exp_avg_sq"].numpy()) < 1e-5
+
+
+def test_clip_adamw_bf16_params_and_graph_capture():
+    """bf16 parameters (fp32 moments) follow the fp32 update to bf16 rounding; step() is capturable."""
+    gen = torch.Generator().manual_seed(3)
+    w = torch.randn(64, 256, generator=gen)
+    ref = torch.nn.Parameter(w.clone())
+    q = torch.nn.Parameter(w.clone().to(DEV).bfloat16())
+    o_ref = torch.optim.AdamW([ref], lr=1e-2, weight_decay=0.0)
+    o = bf.optim.ClipAdamW([q], lr=1e-2, weight_decay=0.0)
+    g = torch.randn(64, 256, generator=gen)
+    ref.grad = g.bfloat16().float()
+    q.grad = g.to(DEV).bfloat16()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        o.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    ref.data = ref.data.bfloat16().float()
+    o_ref.step()
+    assert rel_err(q.detach().float().cpu().numpy(), ref.detach().numpy()) < 4e-3
+    graph = torch.cuda.CUDAGraph()
+    before = q.detach().clone()
+    with torch.cuda.graph(graph, stream=side):
+        o.step()
+    with torch.cuda.stream(side):
+        graph.replay()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert float(o.step_count[0]) == 3.0 and not torch.equal(before, q.detach())  # 1 eager + 2 replays
+
 # ------------------------------------------------------------------ CUDA-graph replay == eager (BERT-base layers)
 def test_cuda_graph_replay_equals_eager_bert_layers():
     """A captured training step (multi-tensor sampling, folded S-sample fwd, ELBO, bwd) replayed with the
