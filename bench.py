@@ -388,12 +388,14 @@ def run_ours(args):
     g_calls = sum(v["calls"] for v in gemm.values())
     peak_tf = pk["bf16_tflops_sustained"]
     ach_tf = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tc::bayes_gemm_kernel (fwd + dgrad + fused wgrad, all layers)",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 contractions: tc2::bayes_gemm2_kernel (fwd, dgrad; cta_group::2) + wg::bayes_wgrad_kernel (fused wgrad), all layers",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step; the peak is cuBLAS "
+                               "running back to back for 4 s under the power cap, these launches are interleaved with "
+                               "lighter kernels and can clock higher, so frac may slightly exceed 1)",
                 # dram__bytes_read+write of the profiled FFN-shape fwd launch (S=4, M=4096, N=3072, K=768; algorithmic
                 # operand+result bytes 145 MB, most of the bf16 result still in L2 at kernel end):
-                # profiles/r01_ncu_full_kernels.md row 5
+                # profiles/r01b_ncu_full_kernels_cta_pairs.md row 5
                 "traffic": 92.0e6, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
                 "share_of_step": g_ms / kern_steps / ms,
                 "timing": "CUDA events around every launch on the launching stream" +

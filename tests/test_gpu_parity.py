@@ -384,6 +384,50 @@ def test_tiny_bert_bf16_mode_within_1e2():
     assert rel_err(bm.log_prior().cpu().numpy(), g["log_prior"]) < FP32_TOL
 
 
+
+def test_tiny_bert_qa_span_head_matches_oracle_loop():
+    """BASELINE configs[3] shape in miniature: BertForQuestionAnswering (span head, start/end logits),
+    S samples folded through harness.sample_bayesian vs the oracle's sequential S-loop on the CPU
+    (pattern of examples/bert_squad.py:190-212) with the same eps."""
+    from transformers import BertConfig, BertForQuestionAnswering
+    torch.manual_seed(7)
+    cfg = BertConfig(vocab_size=120, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                     intermediate_size=128, max_position_embeddings=64)
+    model = BertForQuestionAnswering(cfg).eval()
+    gen = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("bias"):
+                p.add_(torch.randn(p.shape, generator=gen) * 0.02)
+    S, B, Tn = 3, 2, 24
+    ids = torch.randint(0, 120, (B, Tn), generator=gen)
+    lin_names = [n for n, m in model.named_modules() if m.__class__ is torch.nn.Linear]
+    shapes = {n: dict(model.named_modules())[n] for n in lin_names}
+    eps = {(s, n): (torch.randn(shapes[n].weight.shape, generator=gen), torch.randn(shapes[n].bias.shape, generator=gen))
+           for s in range(S) for n in lin_names}
+    # ours: folded forward
+    bm = bf.to_bayesian(model, delta=0.05, freeze=True).eval().to(DEV)
+    for n, m in bm.model.named_modules():
+        if isinstance(m, bnn.Linear):
+            m.weight.normal = FixedEps([eps[(s, n)][0] for s in range(S)])
+            m.bias.normal = FixedEps([eps[(s, n)][1] for s in range(S)])
+    (raw_start, raw_end), (start, end), lp, lq = bf.sample_bayesian(
+        bm, {"input_ids": ids.to(DEV)}, S, select=("start_logits", "end_logits"))
+    assert raw_start.shape == (S, B, Tn) and start.shape == (B, Tn)
+    # oracle: sequential S-loop, one eps queue in layer execution order (weight then bias)
+    queue = [e for s in range(S) for n in lin_names for e in eps[(s, n)]]
+    om = O.oracle_convert(model, 0.05, True, eps=O.EpsSource(preset=queue)).eval()
+    st, en, lps, lqs = [], [], [], []
+    with torch.no_grad():
+        for s in range(S):
+            out = om(input_ids=ids)
+            st.append(out.start_logits), en.append(out.end_logits)
+            lps.append(O.model_log_prior(om)), lqs.append(O.model_log_variational_posterior(om))
+    assert rel_err(raw_start.detach().cpu().numpy(), torch.stack(st).numpy()) < 5 * FP32_TOL
+    assert rel_err(raw_end.detach().cpu().numpy(), torch.stack(en).numpy()) < 5 * FP32_TOL
+    assert abs(float(lp) - float(torch.stack(lps).mean())) <= FP32_TOL * abs(float(torch.stack(lps).mean()))
+    assert abs(float(lq) - float(torch.stack(lqs).mean())) <= FP32_TOL * abs(float(torch.stack(lqs).mean()))
+
 # ------------------------------------------------------------------ kl_grad extension
 def test_kl_grad_true_flows_through_model_scalars():
     torch.manual_seed(0)
