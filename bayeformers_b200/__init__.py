@@ -55,16 +55,37 @@ def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:
     return model
 
 
-def accelerate_host_(model: tnn.Module) -> tnn.Module:
-    """Opt-in: route the host model's remaining frequentist `nn.LayerNorm`s
-    (exact class, 1-D normalized_shape) through the native S-sample LayerNorm
-    kernels with a shared affine.  Parameters are kept (same tensors, fp32);
-    state_dict names do not change.  In place; returns the model."""
+def _is_exact_gelu(fn) -> bool:
+    if isinstance(fn, tnn.GELU):
+        return getattr(fn, "approximate", "none") == "none"
+    name = type(fn).__name__
+    if name == "GELUActivation":  # transformers.activations: exact erf GELU unless use_gelu_python
+        return getattr(fn, "act", None) is tnn.functional.gelu
+    return fn is tnn.functional.gelu
+
+
+def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True) -> tnn.Module:
+    """Opt-in plumbing for the frequentist code AROUND the Bayesian layers of a host model.  In place; parameters,
+    state_dict names and numerics (to rounding) are unchanged.
+
+    layernorm  route the remaining frequentist `nn.LayerNorm`s (exact class, 1-D normalized_shape) through the
+               native S-sample LayerNorm kernels with a shared affine (fp32 master gamma / beta).
+    fuse_gelu  HuggingFace feed-forward blocks of the form `x = self.dense(x); x = self.intermediate_act_fn(x)`
+               (BertIntermediate and its clones) whose `dense` is a Bayesian Linear and whose activation is the
+               exact GELU: move the activation INTO the layer (`dense.activation = "gelu"`, fused tensor-core
+               epilogue) and replace the module's activation by the identity."""
     from .nn.layers.layernorm import HostLayerNorm
+    from .nn.layers.linear import Linear
 
     for mod in model.modules():
-        if mod.__class__ is tnn.LayerNorm and mod.elementwise_affine and len(mod.normalized_shape) == 1:
+        if layernorm and mod.__class__ is tnn.LayerNorm and mod.elementwise_affine and len(mod.normalized_shape) == 1:
             mod.__class__ = HostLayerNorm
+        if fuse_gelu and isinstance(getattr(mod, "dense", None), Linear) and hasattr(mod, "intermediate_act_fn"):
+            children = dict(mod.named_children())
+            only_dense_and_act = set(children) <= {"dense", "intermediate_act_fn"}
+            if only_dense_and_act and mod.dense.activation is None and _is_exact_gelu(mod.intermediate_act_fn):
+                mod.dense.activation = "gelu"
+                mod.intermediate_act_fn = tnn.Identity()
     return model
 
 

@@ -54,6 +54,12 @@ SIGNATURES = {
                                   c_int32, c_void_p]),
     "bf_linear_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
                                   c_void_p]),
+    "bf_linear_fwd_gelu_supported": (c_int32, [c_int64, c_int64, c_int64, c_int64]),
+    "bf_linear_fwd_gelu": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                     c_int64, c_void_p]),
+    "bf_gelu_bwd_bias_grad_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_gelu_bwd_bias_grad": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                        c_void_p]),
     "bf_linear_wgrad_fused_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int32]),
     "bf_linear_wgrad_fused": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                         c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,

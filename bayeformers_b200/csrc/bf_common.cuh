@@ -114,6 +114,33 @@ __device__ __forceinline__ float4 bf_eps_quad(uint32_t q, uint32_t sample, uint3
 // ---------------------------------------------------------------------------
 // elementwise math of the variational parameters
 // ---------------------------------------------------------------------------
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issued instruction) ----
+typedef unsigned long long bf_f2;  // two floats in one 64-bit register pair
+__device__ __forceinline__ bf_f2 bf_pack2(float a, float b) {
+    bf_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void bf_unpack2(bf_f2 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ bf_f2 bf_fma2(bf_f2 a, bf_f2 b, bf_f2 c) {
+    bf_f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ bf_f2 bf_mul2(bf_f2 a, bf_f2 b) {
+    bf_f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ bf_f2 bf_add2(bf_f2 a, bf_f2 b) {
+    bf_f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ bf_f2 bf_splat2(float c) { return bf_pack2(c, c); }
+
 // ---- MUFU-based transcendental helpers ------------------------------------------------------
 // The sample+KL kernels are issue-bound, not HBM-bound (profiles/README.md): libdevice's expf / log1pf /
 // logf cost ~80 instructions per element with their slow-path branches.  These keep ~1e-6 relative

@@ -1,0 +1,465 @@
+// S-sample Linear forward with the bias + GELU epilogue fused (CTA-pair tcgen05 kernel), and the matching
+// fused backward elementwise pass.
+//
+// Extension of bnn.Linear (`activation="gelu"`): y = gelu(x w^T + b).  In the reference the activation is a
+// separate module after the layer (F.linear, bayeformers/nn/layers/linear.py:104, followed by the host model's
+// GELU); fusing it into the producing kernel removes one full read + write of the [S*M, N] activation in the
+// forward pass and, in the backward pass, merges GELU' with the bias-gradient column sums (one pass over gy).
+//
+//   forward : z = x w^T + b (bf16, kept for backward),  y = gelu(z) (bf16)     -- both TMA-stored from the epilogue
+//   backward: gz = gy * gelu'(z),  db[s][n] = sum_m gz[s][m][n]                -- bf_gelu_bwd_bias_grad
+//
+// GELU is the exact (erf) form HF BERT uses.  erf comes from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// bf16 resolution), evaluated on packed fp32 pairs (FFMA2).  Measured at the BERT-base FFN shape (S=4, M=32768,
+// 3072x768): plain forward 448 us, this kernel 745 us (598 us with the GELU arithmetic removed, i.e. the second
+// 805 MB result write costs 150 us and the epilogue arithmetic another 150 us: with 12 k-steps per tile the epilogue,
+// not the MMA stream, is the critical path), against 448 + ~440 us for the separate GELU pass it replaces.
+//
+// Kernel structure = bf_gemm_tc2.cu (cluster of 2, cta_group::2, UMMA 256x256x16, leader issues, multicast commits)
+// with 8 epilogue warps in two groups (group g takes the 64-column boxes b with b % 2 == g), 5 stages, and two
+// staging buffers (z, y) per group.
+#include "bf_tc.cuh"
+
+namespace act {
+using namespace tc;
+
+constexpr int BLOCK_M = 128, BLOCK_N = 256, LOAD_N = 128;
+constexpr int kStages = 5;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = LOAD_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BOX_COLS = 64;                 // bf16 columns per TMA-store box (128 B rows)
+constexpr int BOX_BYTES = BLOCK_M * 128;     // 16 KiB
+constexpr int BOXES = BLOCK_N / BOX_COLS;    // 4
+constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int kThreads = 32 * (2 + EPI_WARPS);
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr int OUT_BYTES = EPI_GROUPS * 2 * BOX_BYTES;  // (z, y) per group
+constexpr int BIAS_BYTES = BLOCK_N * 4;
+constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + OUT_BYTES + 256 + BIAS_BYTES;
+
+struct Params {
+    int64_t S, I, J, R;
+    int i_pairs, j_tiles, k_steps;
+    const float* bias;  // [S][J], required
+};
+struct Item {
+    int s, i_pair, j_blk;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
+    Item it;
+    it.j_blk = (int)(L % p.j_tiles);
+    const int64_t q = L / p.j_tiles;
+    it.i_pair = (int)(q % p.i_pairs);
+    it.s = (int)(q / p.i_pairs);
+    return it;
+}
+
+// erf(x), Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = bf_rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = bf_ex2_approx(-1.4426950408889634f * ax * ax);
+    const float r = fmaf(-p * t, e, 1.0f);
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erf_as(z * 0.70710678118654752f)); }
+// the same GELU on two values at once with packed fp32 arithmetic (FFMA2 / FMUL2): the forward epilogue has to stay
+// cheaper than the 12 k-steps of MMA of a 768-deep tile, and this halves its FMA issue count
+__device__ __forceinline__ bf_f2 gelu_erf2(bf_f2 z2) {
+    float x0, x1, d0, d1, q0, q1, r0, r1;
+    bf_unpack2(bf_mul2(z2, bf_splat2(0.70710678118654752f)), x0, x1);
+    const bf_f2 ax2 = bf_pack2(fabsf(x0), fabsf(x1));
+    bf_unpack2(bf_fma2(bf_splat2(0.3275911f), ax2, bf_splat2(1.0f)), d0, d1);
+    const bf_f2 t2 = bf_pack2(bf_rcp_approx(d0), bf_rcp_approx(d1));
+    bf_f2 p2 = bf_fma2(bf_splat2(1.061405429f), t2, bf_splat2(-1.453152027f));
+    p2 = bf_fma2(p2, t2, bf_splat2(1.421413741f));
+    p2 = bf_fma2(p2, t2, bf_splat2(-0.284496736f));
+    p2 = bf_fma2(p2, t2, bf_splat2(0.254829592f));
+    bf_unpack2(bf_mul2(bf_mul2(ax2, ax2), bf_splat2(-1.4426950408889634f)), q0, q1);
+    const bf_f2 ne2 = bf_pack2(-bf_ex2_approx(q0), -bf_ex2_approx(q1));
+    bf_unpack2(bf_fma2(bf_mul2(p2, t2), ne2, bf_splat2(1.0f)), r0, r1);  // |erf|
+    const bf_f2 erf2 = bf_pack2(copysignf(r0, x0), copysignf(r1, x1));
+    return bf_mul2(z2, bf_fma2(erf2, bf_splat2(0.5f), bf_splat2(0.5f)));
+}
+// d gelu / dz = Phi(z) + z * phi(z) on two values; phi shares its exponential with erf: exp(-z^2/2) = exp(-x^2), x = z/sqrt 2
+__device__ __forceinline__ bf_f2 gelu_erf_grad2(bf_f2 z2) {
+    float x0, x1, d0, d1, q0, q1, r0, r1;
+    bf_unpack2(bf_mul2(z2, bf_splat2(0.70710678118654752f)), x0, x1);
+    const bf_f2 ax2 = bf_pack2(fabsf(x0), fabsf(x1));
+    bf_unpack2(bf_fma2(bf_splat2(0.3275911f), ax2, bf_splat2(1.0f)), d0, d1);
+    const bf_f2 t2 = bf_pack2(bf_rcp_approx(d0), bf_rcp_approx(d1));
+    bf_f2 p2 = bf_fma2(bf_splat2(1.061405429f), t2, bf_splat2(-1.453152027f));
+    p2 = bf_fma2(p2, t2, bf_splat2(1.421413741f));
+    p2 = bf_fma2(p2, t2, bf_splat2(-0.284496736f));
+    p2 = bf_fma2(p2, t2, bf_splat2(0.254829592f));
+    bf_unpack2(bf_mul2(bf_mul2(ax2, ax2), bf_splat2(-1.4426950408889634f)), q0, q1);
+    const float e0 = bf_ex2_approx(q0), e1 = bf_ex2_approx(q1);
+    bf_unpack2(bf_fma2(bf_mul2(p2, t2), bf_pack2(-e0, -e1), bf_splat2(1.0f)), r0, r1);  // |erf|
+    const bf_f2 cdf2 = bf_fma2(bf_pack2(copysignf(r0, x0), copysignf(r1, x1)), bf_splat2(0.5f), bf_splat2(0.5f));
+    return bf_fma2(z2, bf_mul2(bf_pack2(e0, e1), bf_splat2(0.3989422804014327f)), cdf2);
+}
+__device__ __forceinline__ float gelu_erf_grad(float z) {
+    const float cdf = 0.5f * (1.0f + erf_as(z * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * bf_ex2_approx(-0.72134752044448170f * z * z);  // exp(-z^2/2)/sqrt(2 pi)
+    return fmaf(z, pdf, cdf);
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    uint4 u;
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<const uint32_t*>(&p0), u.y = *reinterpret_cast<const uint32_t*>(&p1);
+    u.z = *reinterpret_cast<const uint32_t*>(&p2), u.w = *reinterpret_cast<const uint32_t*>(&p3);
+    return u;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    bayes_gemm2_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_y,
+                            const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t out_base = smem_base + kStages * STAGE_BYTES;
+    uint8_t* const out_gen = smem_gen + kStages * STAGE_BYTES;
+    const uint32_t bar_base = out_base + OUT_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    volatile uint32_t* const tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(out_gen + OUT_BYTES + 8 * (2 * kStages + 4));
+    float* const bias_gen = reinterpret_cast<float*>(out_gen + OUT_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_z);
+        tma_prefetch_desc(&map_y);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 2 * EPI_WARPS);  // leader's copy: epilogue warps of both CTAs
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t L = cluster_id; L < n_items; L += n_clusters) {
+                const Item it = decode_item(p, L);
+                const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+                const int j0 = it.j_blk * BLOCK_N + (int)rank * LOAD_N;
+                for (int ks = 0; ks < p.k_steps; ++ks) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    tma_load_3d_2sm(a_dst, &map_a, full_bar(stage), ks * BLOCK_K, i0, it.s);
+                    tma_load_3d_2sm(a_dst + A_BYTES, &map_b, full_bar(stage), ks * BLOCK_K, j0, it.s);
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(false, false, 2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ks = 0; ks < p.k_steps; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + stage * STAGE_BYTES;
+                    const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_2sm(d_tmem, operand_desc<false>(a_src, k), operand_desc<false>(b_src, k), idesc,
+                                      (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(empty_bar(stage));
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+                umma_commit_2sm(tfull_bar(acc));
+            }
+        }
+    } else {
+        // ===================== epilogue: 2 groups x 4 warps, own TMEM half =====================
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const bool store_thread = ((warp - 2) & 3) == 0 && lane == 0;
+        const int et = threadIdx.x - 64;  // 0..255 over both groups
+        const uint32_t my_out = out_base + grp * 2 * BOX_BYTES;
+        uint8_t* const my_out_gen = out_gen + grp * 2 * BOX_BYTES;
+        int iter = 0;
+        for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
+            const Item it = decode_item(p, L);
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M, j0 = it.j_blk * BLOCK_N;
+            // stage this tile's 256 bias values once (all rows use the same ones)
+            named_bar_sync_dyn(3, EPI_WARPS * 32);  // both groups are done reading the previous tile's slice
+            {
+                const int64_t jc = (int64_t)j0 + et;
+                bias_gen[et] = jc < p.J ? __ldg(p.bias + (int64_t)it.s * p.J + jc) : 0.0f;
+            }
+            named_bar_sync_dyn(3, EPI_WARPS * 32);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            int n_boxes = BOXES;
+            if ((int64_t)j0 + BLOCK_N > p.J) n_boxes = (int)((p.J - j0 + BOX_COLS - 1) / BOX_COLS);
+            int last_b = -1;
+            for (int b = grp; b < n_boxes; b += EPI_GROUPS) last_b = b;
+            if (last_b < 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+            }
+#pragma unroll 1
+            for (int b = grp; b < n_boxes; b += EPI_GROUPS) {
+                uint32_t r[2][32];
+                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS), r[0]);
+                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS + 32), r[1]);
+                if (store_thread) tma_store_wait_read<0>();  // this group's previous (z, y) stores have read smem
+                tmem_ld_wait();
+                if (b == last_b) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+                }
+                named_bar_sync_dyn(1 + grp, 128);
+                uint8_t* const z_row = my_out_gen + row * 128;
+                uint8_t* const y_row = z_row + BOX_BYTES;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4* bp = reinterpret_cast<const float4*>(bias_gen + b * BOX_COLS + h * 32);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {  // 8 columns = one 16-byte chunk of the bf16 row
+                        const float4 b0 = bp[2 * t], b1 = bp[2 * t + 1];
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint32_t zw[4], yw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float z0, z1, y0, y1;
+                            bf_unpack2(bf_add2(bf_pack2(__uint_as_float(r[h][8 * t + 2 * e]), __uint_as_float(r[h][8 * t + 2 * e + 1])),
+                                               bf_pack2(bv[2 * e], bv[2 * e + 1])), z0, z1);
+                            const __nv_bfloat162 zb = __floats2bfloat162_rn(z0, z1);
+                            zw[e] = *reinterpret_cast<const uint32_t*>(&zb);
+                            // gelu of the bf16-ROUNDED pre-activation: backward recomputes gelu' from the stored z
+                            bf_unpack2(gelu_erf2(bf_pack2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u))), y0, y1);
+                            const __nv_bfloat162 yb = __floats2bfloat162_rn(y0, y1);
+                            yw[e] = *reinterpret_cast<const uint32_t*>(&yb);
+                        }
+                        const int ch = h * 4 + t;
+                        *reinterpret_cast<uint4*>(z_row + ((ch ^ (row & 7)) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+                        *reinterpret_cast<uint4*>(y_row + ((ch ^ (row & 7)) << 4)) = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+                    }
+                }
+                fence_proxy_async();
+                named_bar_sync_dyn(1 + grp, 128);
+                if (store_thread) {
+                    tma_store_3d(&map_z, my_out, j0 + b * BOX_COLS, i0, it.s);
+                    tma_store_3d(&map_y, my_out + BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (store_thread) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ backward: gz = gy * gelu'(z), db = colsum(gz)
+constexpr int kBwThreads = 256, kBwWarps = 8, kBwCols = 256;  // 32 lanes x 8 bf16 columns
+
+__global__ void __launch_bounds__(kBwThreads) gelu_bwd_bias_grad_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                                        const __nv_bfloat16* __restrict__ z,
+                                                                        __nv_bfloat16* __restrict__ gz,
+                                                                        float* __restrict__ db,
+                                                                        float* __restrict__ partial,
+                                                                        unsigned int* __restrict__ counters, int64_t M,
+                                                                        int64_t N, int64_t rows_per_slab) {
+    const int s = blockIdx.y, slab = blockIdx.z, n_slabs = gridDim.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * kBwCols + lane * 8;
+    const int64_t base = (int64_t)s * M * N;
+    const int64_t m_lo = (int64_t)slab * rows_per_slab;
+    const int64_t m_hi = m_lo + rows_per_slab < M ? m_lo + rows_per_slab : M;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    if (c0 < N) {  // N % 8 == 0
+        // one 16-byte chunk: 8 (gy, z) pairs -> 8 products (packed fp32 math), accumulated per column
+        auto chunk = [&](const uint4& g, const uint4& zz, float (&o)[8]) {
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bf_f2 g2 = bf_pack2(__uint_as_float(gw[i] << 16), __uint_as_float(gw[i] & 0xffff0000u));
+                const bf_f2 z2 = bf_pack2(__uint_as_float(zw[i] << 16), __uint_as_float(zw[i] & 0xffff0000u));
+                bf_unpack2(bf_mul2(g2, gelu_erf_grad2(z2)), o[2 * i], o[2 * i + 1]);
+                acc[2 * i] += o[2 * i], acc[2 * i + 1] += o[2 * i + 1];
+            }
+        };
+        int64_t m = m_lo + warp;
+        for (; m + kBwWarps < m_hi; m += 2 * kBwWarps) {  // 2 rows in flight per warp
+            const int64_t o0 = base + m * N + c0, o1 = o0 + (int64_t)kBwWarps * N;
+            const uint4 g0 = __ldcs(reinterpret_cast<const uint4*>(gy + o0)), z0 = __ldcs(reinterpret_cast<const uint4*>(z + o0));
+            const uint4 g1 = __ldcs(reinterpret_cast<const uint4*>(gy + o1)), z1 = __ldcs(reinterpret_cast<const uint4*>(z + o1));
+            float o[8];
+            chunk(g0, z0, o);
+            __stcs(reinterpret_cast<uint4*>(gz + o0), pack8_bf16(o));
+            chunk(g1, z1, o);
+            __stcs(reinterpret_cast<uint4*>(gz + o1), pack8_bf16(o));
+        }
+        for (; m < m_hi; m += kBwWarps) {
+            const int64_t o0 = base + m * N + c0;
+            const uint4 g0 = __ldcs(reinterpret_cast<const uint4*>(gy + o0)), z0 = __ldcs(reinterpret_cast<const uint4*>(z + o0));
+            float o[8];
+            chunk(g0, z0, o);
+            __stcs(reinterpret_cast<uint4*>(gz + o0), pack8_bf16(o));
+        }
+    }
+    // NOTE: db sums the fp32 products before they are rounded to bf16 for gz (more accurate than summing gz)
+    __shared__ float red[kBwWarps][kBwCols];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int64_t cb = blockIdx.x, n_cb = gridDim.x;
+    {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kBwWarps; ++w) t += red[w][threadIdx.x];
+        partial[(((int64_t)s * n_cb + cb) * n_slabs + slab) * kBwCols + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(counters + s * n_cb + cb, 1u);
+        is_last = (done == (unsigned int)n_slabs - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    {
+        const volatile float* pp = partial + ((int64_t)s * n_cb + cb) * n_slabs * kBwCols + threadIdx.x;
+        float t = 0.0f;
+        for (int k = 0; k < n_slabs; ++k) t += pp[(int64_t)k * kBwCols];
+        const int64_t c = cb * kBwCols + threadIdx.x;
+        if (c < N) db[(int64_t)s * N + c] = t;
+    }
+    if (threadIdx.x == 0) counters[s * n_cb + cb] = 0u;
+}
+
+inline void bw_grid(int64_t S, int64_t M, int64_t N, int& n_cb, int& n_slabs, int64_t& rps) {
+    n_cb = (int)((N + kBwCols - 1) / kBwCols);
+    const int64_t target = (int64_t)bf_num_sms() * 4;
+    int64_t slabs = target / (S * n_cb);
+    const int64_t max_slabs = (M + 63) / 64;
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    if (slabs > 65535) slabs = 65535;
+    rps = (M + slabs - 1) / slabs;
+    n_slabs = (int)((M + rps - 1) / rps);
+}
+
+}  // namespace act
+
+extern "C" int bf_linear_fwd_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K) {
+    if (N % 8 != 0 || K % 8 != 0 || M < 256) return 0;
+    const int64_t pair_tiles = S * ((M + 255) / 256) * ((N + 255) / 256);
+    return pair_tiles >= bf_num_sms() / 2 ? 1 : 0;
+}
+
+// z[s] = x[s] w[s]^T + bias[s] (bf16), y[s] = gelu(z[s]) (bf16)
+extern "C" int bf_linear_fwd_gelu(const void* x, const void* w, const float* bias, void* z, void* y, int64_t S,
+                                  int64_t M, int64_t N, int64_t K, void* stream) {
+    using namespace act;
+    BF_CHECK_ARG(x && w && bias && z && y, "null pointer (the fused GELU forward needs a bias)");
+    BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1");
+    BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "bf16 path needs K % 8 == 0 and N % 8 == 0");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ma, mb, mz, my;
+    int rc;
+    if ((rc = tc::encode_map(&ma, x, S, M, K, BLOCK_M))) return rc;
+    if ((rc = tc::encode_map(&mb, w, S, N, K, LOAD_N))) return rc;
+    if ((rc = tc::encode_map(&mz, z, S, M, N, BLOCK_M))) return rc;
+    if ((rc = tc::encode_map(&my, y, S, M, N, BLOCK_M))) return rc;
+    Params p{};
+    p.S = S, p.I = M, p.J = N, p.R = K;
+    p.i_pairs = tc::cdiv(M, 2 * BLOCK_M), p.j_tiles = tc::cdiv(N, BLOCK_N), p.k_steps = tc::cdiv(K, tc::BLOCK_K);
+    p.bias = bias;
+    BF_CUDA_OK(cudaFuncSetAttribute(bayes_gemm2_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
+    const int64_t pairs = bf_num_sms() / 2;
+    const int grid = 2 * (int)(n_items < pairs ? n_items : pairs);
+    bayes_gemm2_gelu_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mz, my, p);
+    BF_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int64_t bf_gelu_bwd_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N) {
+    S = S < 1 ? 1 : S, M = M < 1 ? 1 : M, N = N < 1 ? 1 : N;
+    int n_cb, n_slabs;
+    int64_t rps;
+    act::bw_grid(S, M, N, n_cb, n_slabs, rps);
+    return ((S * n_cb * 4 + 255) / 256) * 256 + S * n_cb * (int64_t)n_slabs * act::kBwCols * 4;
+}
+
+// gz = gy * gelu'(z) (bf16), db[s][n] = sum_m gz[s][m][n] (fp32).  workspace zero-filled once.
+extern "C" int bf_gelu_bwd_bias_grad(const void* gy, const void* z, void* gz, float* db, int64_t S, int64_t M,
+                                     int64_t N, void* workspace, void* stream) {
+    using namespace act;
+    BF_CHECK_ARG(gy && z && gz && db && workspace, "null pointer");
+    BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 8 && N % 8 == 0, "needs N % 8 == 0");
+    BF_CHECK_ARG(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gz)) & 15u) == 0,
+                 "gy, z, gz must be 16 B aligned");
+    int n_cb, n_slabs;
+    int64_t rps;
+    bw_grid(S, M, N, n_cb, n_slabs, rps);
+    const int64_t cnt = ((S * n_cb * 4 + 255) / 256) * 256;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + cnt);
+    dim3 grid((unsigned)n_cb, (unsigned)S, (unsigned)n_slabs);
+    gelu_bwd_bias_grad_kernel<<<grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(z),
+        reinterpret_cast<__nv_bfloat16*>(gz), db, partial, counters, M, N, rps);
+    BF_LAUNCH_OK();
+    return 0;
+}

@@ -39,6 +39,9 @@ class Linear(BayesianLayer):
         else:
             self.bias = NoneParameter()
             self.bias_prior = NoneParameter()
+        # extension (default None = the reference's plain affine map): "gelu" applies the exact GELU inside the
+        # layer, fused into the tensor-core epilogue (forward) and into the bias-gradient pass (backward)
+        self.activation: Optional[str] = None
         self._init_scalars()
 
     def forward(self, input: Tensor) -> Tensor:
@@ -52,11 +55,13 @@ class Linear(BayesianLayer):
             pre = None
         if pre is not None:
             spec = ops.LinearSpec(S=S, gemm_dtype=self._gemm_dtype(), kl_grad=kl_grad, w_prior=w_prior, b_prior=b_prior,
-                                  w_stream=pre[5], b_stream=pre[6], presampled=pre[1:5])
+                                  w_stream=pre[5], b_stream=pre[6], presampled=pre[1:5],
+                                  activation=self.activation)
         else:
             spec = ops.LinearSpec(S=S, gemm_dtype=self._gemm_dtype(), kl_grad=kl_grad, w_prior=w_prior,
                                   b_prior=b_prior, w_stream=self.weight.next_stream(S),
-                                  b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec())
+                                  b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec(),
+                                  activation=self.activation)
         self._last_streams = (spec.w_stream, spec.b_stream)  # identity of this forward's eps draw (tests, debugging)
         y, logq, logp = ops.BayesLinear.apply(
             input, self.weight.mu, self.weight.rho,

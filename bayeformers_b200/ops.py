@@ -231,6 +231,7 @@ class LinearSpec:
     w_stream: StreamSpec
     b_stream: StreamSpec = field(default_factory=StreamSpec)
     presampled: Optional[Tuple] = None  # (W[S,N,K], b[S,N] or None, logq[S], logp[S]) from presample.Presampler
+    activation: Optional[str] = None    # None | "gelu": y = act(x w^T + b) with the activation fused where possible
 
 
 def tc_eligible(N: int, K: int) -> bool:
@@ -281,14 +282,29 @@ class BayesLinear(torch.autograd.Function):
                 b = sample_kl_forward(b_mu.detach(), b_rho.detach(), b_prior, spec.b_stream, S, torch.float32, logq,
                                       logp, True)
         out_dtype = x.dtype if (use_tc and x.dtype in (torch.float32, torch.bfloat16)) else torch.float32
+        act = spec.activation
+        if act not in (None, "gelu"):
+            raise ValueError(f"unsupported activation {act!r}")
+        z = None  # pre-activation kept for backward when an activation is applied
+        fused_act = (act == "gelu" and use_tc and has_bias and out_dtype == torch.bfloat16 and M > 0
+                     and bool(lib.bf_linear_fwd_gelu_supported(S, M, N, K)))
         y = torch.empty((S, M, N), dtype=out_dtype, device=dev)
-        if M > 0:
+        if fused_act:
+            z = torch.empty((S, M, N), dtype=torch.bfloat16, device=dev)
+            rc = _timed("gemm_fwd_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_fwd_gelu(
+                _ptr(xg), _ptr(W), _ptr(b), _ptr(z), _ptr(y), S, M, N, K, _stream(dev)))
+            _lib.check(rc, "bf_linear_fwd_gelu")
+            stats["launches"] += 1
+        elif M > 0:
             rc = _timed("gemm_fwd_" + ("tc" if use_tc else "f32"), 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_fwd(
                 _ptr(xg), _ptr(W), _ptr(b), _ptr(y), S, M, N, K, _dt(cdt), _dt(out_dtype), _stream(dev)))
             _lib.check(rc, "bf_linear_fwd")
             stats["launches"] += 1
-        ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho)
-        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape))
+        if act == "gelu" and not fused_act:  # shapes the fused kernel does not take: same maths, separate pass
+            z = y
+            y = torch.nn.functional.gelu(z)
+        ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z)
+        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape), fused_act)
         if not spec.kl_grad:
             ctx.mark_non_differentiable(logq, logp)
         if x.dtype != out_dtype:
@@ -298,8 +314,8 @@ class BayesLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, glq, glp):
         lib = _lib.load()
-        xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho = ctx.saved_tensors
-        spec, use_tc, M, x_dtype, x_shape = ctx.meta
+        xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z = ctx.saved_tensors
+        spec, use_tc, M, x_dtype, x_shape, fused_act = ctx.meta
         S = spec.S
         N, K = w_mu.shape
         dev = xg.device
@@ -315,8 +331,21 @@ class BayesLinear(torch.autograd.Function):
 
         g_x = g_wmu = g_wrho = g_bmu = g_brho = None
         have_gy = gy is not None and M > 0
+        db = None
         if have_gy:
             gyc = gy.reshape(S, M, N).to(cdt).contiguous()
+            if z is not None and fused_act:
+                # gz = gy * gelu'(z) and the bias gradient's column sums in ONE pass over gy
+                gz = torch.empty_like(gyc)
+                db = torch.empty((S, N), dtype=torch.float32, device=dev)
+                bws = _workspace("gelu_bwd", dev, lib.bf_gelu_bwd_bias_grad_workspace_bytes(S, M, N))
+                rc = _timed("gelu_bwd_bias_grad", float(3 * S * M * N * 2), dev, lambda: lib.bf_gelu_bwd_bias_grad(
+                    _ptr(gyc), _ptr(z), _ptr(gz), _ptr(db), S, M, N, _ptr(bws), st))
+                _lib.check(rc, "bf_gelu_bwd_bias_grad")
+                stats["launches"] += 1
+                gyc = gz
+            elif z is not None:
+                gyc = torch.ops.aten.gelu_backward(gyc, z.reshape(S, M, N).to(cdt)).contiguous()
             if ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 dx = torch.empty((S, M, K), dtype=dx_dtype, device=dev)
@@ -326,7 +355,7 @@ class BayesLinear(torch.autograd.Function):
                 _lib.check(rc, "bf_linear_dgrad")
                 stats["launches"] += 1
                 g_x = dx.view(x_shape).to(x_dtype)
-            if has_bias:
+            if has_bias and db is None:
                 db = torch.empty((S, N), dtype=torch.float32, device=dev)
                 bws = _workspace("bias_grad", dev, lib.bf_bias_grad_workspace_bytes(S, M, N))
                 rc = _timed("bias_grad", float(S * M * N * gyc.element_size()), dev,

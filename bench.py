@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-optim", type=int, default=1, help="bf.optim.ClipAdamW instead of clip_grad_norm_ + AdamW")
     ap.add_argument("--presample", type=int, default=1, help="one multi-tensor sample+KL launch per forward")
+    ap.add_argument("--fuse-gelu", type=int, default=1,
+                    help="move the FFN GELU into the Bayesian Linear (fused tensor-core epilogue)")
     ap.add_argument("--host-ln", type=int, default=1,
                     help="route the host model's frequentist LayerNorms through the native LayerNorm kernels")
     ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
@@ -192,6 +194,7 @@ def workload_config(args):
             "global_batch": args.batch * args.gpus, "gemm": args.gemm, "kl_grad": bool(args.kl_grad),
             "optimizer": "bf.optim.ClipAdamW (fused clip + AdamW)" if args.fused_optim else "clip_grad_norm_ + torch AdamW(fused)",
             "sampling": "multi-tensor (1 launch per forward)" if args.presample else "per layer",
+            "ffn_gelu": "fused into bnn.Linear (epilogue + GELU'/bias-grad pass)" if args.fuse_gelu else "torch",
             "host_layernorm": "native kernels (bf_layernorm_*)" if args.host_ln else "torch",
             "parallelism": f"dp{args.gpus} (batch sharded, identical Philox weights per rank, NCCL grad all-reduce)",
             "l2": "working set (0.7 GB sampled weights + activations) far exceeds the 126 MB L2; no explicit flush"}
@@ -220,8 +223,9 @@ def run_ours(args):
     model, cfg = build_bert(args.layers)
     bf.manual_seed(1234)
     bm = bf.to_bayesian(model, delta=0.05, freeze=True, gemm_dtype=args.gemm, kl_grad=bool(args.kl_grad))
-    if args.host_ln:
-        bf.accelerate_host_(bm)  # same parameters and numerics, native fwd/bwd kernels (fp32 gamma/beta)
+    if args.host_ln or args.fuse_gelu:
+        # same parameters and numerics: native LayerNorm kernels (fp32 gamma/beta); FFN GELU fused into the layer
+        bf.accelerate_host_(bm, layernorm=bool(args.host_ln), fuse_gelu=bool(args.fuse_gelu))
     bm = bm.to(dev).train()
     if args.presample:
         bf.enable_presample(bm)

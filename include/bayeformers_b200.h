@@ -182,6 +182,21 @@ int bf_linear_dgrad(const void* gy, const void* w, void* dx, int64_t S, int64_t 
 int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t M, int64_t N, int64_t K,
                     int32_t dtype, void* stream);
 
+/* Extension: forward with the bias + GELU (exact, erf form) epilogue fused, for layers used as
+ * y = gelu(F.linear(x, w, b)) (linear.py:104 followed by the host model's activation), and the matching
+ * backward elementwise pass.  bf16 tensor-core path only, bias required.
+ *   bf_linear_fwd_gelu      z[s] = x[s] w[s]^T + bias[s]  (bf16, kept for backward),  y[s] = gelu(z[s])  (bf16)
+ *   bf_gelu_bwd_bias_grad   gz = gy * gelu'(z) (bf16),  db[s][j] = sum_m gz[s][m][j] (fp32; replaces bf_bias_grad)
+ * bf_linear_fwd_gelu_supported: 1 when the CTA-pair kernel takes the shape (enough 256 x 256 tiles), else the
+ * caller composes bf_linear_fwd with a separate GELU.  workspace of bf_gelu_bwd_bias_grad:
+ * bf_gelu_bwd_bias_grad_workspace_bytes(S, M, N) bytes, zero-filled once. */
+int bf_linear_fwd_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K);
+int bf_linear_fwd_gelu(const void* x, const void* w, const float* bias, void* z, void* y, int64_t S, int64_t M,
+                       int64_t N, int64_t K, void* stream);
+int64_t bf_gelu_bwd_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N);
+int bf_gelu_bwd_bias_grad(const void* gy, const void* z, void* gz, float* db, int64_t S, int64_t M, int64_t N,
+                          void* workspace, void* stream);
+
 /* wgrad with the variational backward fused into its epilogue: the raw weight
  * gradients of the S samples never reach HBM (unless mu is trainable).  The
  * tensor-core epilogue regenerates the eps tile of each (sample, output tile)

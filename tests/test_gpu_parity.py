@@ -536,6 +536,70 @@ def test_fused_wgrad_epilogue_equals_unfused_path(S, M, N, K, kl):
 
 
 
+
+# ------------------------------------------------------------------ bias + GELU epilogue (extension of bnn.Linear)
+@pytest.mark.parametrize("S,M,N,K", [(2, 2560, 3072, 768), (4, 1280, 520, 264), (1, 300, 64, 32)])
+def test_linear_gelu_fused_vs_separate_and_f64(S, M, N, K):
+    """activation="gelu": fused tensor-core epilogue + fused GELU'/bias-grad pass (large shapes) or the composed
+    fallback (small ones) against y = gelu(x w^T + b) evaluated in float64, forward and backward."""
+    torch.manual_seed(S * 7 + N)
+    lin = torch.nn.Linear(K, N)
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+    layer = bnn.Linear.from_frequentist(lin, delta=0.05).to(DEV)
+    layer.gemm_dtype, layer.activation = torch.bfloat16, "gelu"
+    gen = torch.Generator().manual_seed(1)
+    eps_w = [torch.randn(N, K, generator=gen) for _ in range(S)]
+    eps_b = [torch.randn(N, generator=gen) for _ in range(S)]
+    layer.weight.normal, layer.bias.normal = FixedEps(eps_w), FixedEps(eps_b)
+    x = torch.randn(S * M, K, generator=gen).to(DEV).bfloat16().requires_grad_()
+    gy = torch.randn(S * M, N, generator=gen).to(DEV).bfloat16()
+    with bf.mc_samples(S):
+        y = layer(x)
+    assert y.dtype == torch.bfloat16
+    y.backward(gy)
+    # float64 reference on the device, one sample at a time, from the same bf16-rounded operands
+    mu_w, rho_w = layer.weight.mu.detach().double(), layer.weight.rho.detach().double().requires_grad_()
+    mu_b, rho_b = layer.bias.mu.detach().double(), layer.bias.rho.detach().double().requires_grad_()
+    xr = x.detach().double().requires_grad_()
+    outs = []
+    for s in range(S):
+        w = (mu_w + torch.nn.functional.softplus(rho_w) * eps_w[s].to(DEV).double())
+        w = w + (w.detach().float().bfloat16().double() - w.detach())  # bf16-rounded sample, straight-through
+        b = mu_b + torch.nn.functional.softplus(rho_b) * eps_b[s].to(DEV).double()
+        outs.append(torch.nn.functional.gelu(xr[s * M:(s + 1) * M] @ w.T + b))
+    ref = torch.cat(outs)
+    ref.backward(gy.double())
+    assert rel_err(y.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) < BF16_TOL
+    assert rel_err(x.grad.float().cpu().numpy(), xr.grad.cpu().numpy()) < BF16_TOL
+    assert rel_err(layer.weight.rho.grad.cpu().numpy(), rho_w.grad.cpu().numpy()) < BF16_TOL
+    assert rel_err(layer.bias.rho.grad.cpu().numpy(), rho_b.grad.cpu().numpy()) < BF16_TOL
+
+
+def test_accelerate_host_fuses_hf_gelu_block():
+    """accelerate_host_(fuse_gelu=True) on a HF BERT layer: same logits (bf16 tolerance) as the unfused model."""
+    import copy
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(2)
+    cfg = BertConfig(num_labels=2, num_hidden_layers=1)
+    base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True, gemm_dtype="bf16")
+    fused = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=True)
+    inter = fused.model.bert.encoder.layer[0].intermediate
+    assert inter.dense.activation == "gelu" and isinstance(inter.intermediate_act_fn, torch.nn.Identity)
+    S, B, Tn = 2, 8, 128
+    ids = torch.randint(0, cfg.vocab_size, (B, Tn), generator=torch.Generator().manual_seed(3)).to(DEV)
+    outs = []
+    for m in (base, fused):
+        m = m.to(DEV).eval()
+        bf.cast_frequentist_(m, torch.bfloat16)
+        gen = torch.Generator().manual_seed(5)
+        for l in m.bayesian_children:
+            l.weight.normal = FixedEps([torch.randn(l.weight.mu.shape, generator=gen) for _ in range(S)])
+            l.bias.normal = FixedEps([torch.randn(l.bias.mu.shape, generator=gen) for _ in range(S)])
+        with bf.mc_samples(S):
+            outs.append(m(input_ids=ids.repeat(S, 1)).logits.float())
+    assert rel_err(outs[1].detach().cpu().numpy(), outs[0].detach().cpu().numpy()) < BF16_TOL
+
 # ------------------------------------------------------------------ fused clip + AdamW (section 8f row 3)
 @pytest.mark.parametrize("max_norm", [None, 0.5])
 def test_clip_adamw_matches_torch_cpu(max_norm):
