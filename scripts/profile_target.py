@@ -49,8 +49,22 @@ db = torch.empty(S, N, device=DEV)
 bws = torch.zeros(lib.bf_bias_grad_workspace_bytes(S, M, N), dtype=torch.uint8, device=DEV)
 for _ in range(2):
     lib.bf_bias_grad(gy.data_ptr(), BF_BF16, db.data_ptr(), S, M, N, bws.data_ptr(), st)
-# multi-tensor sample+KL over a 2 x (4096 x 4096 + bias) model, S = 4, MOPED prior, bf16 weights
+# fused bias+GELU forward and GELU'/bias-grad backward at the FFN-up shape
+z = torch.empty(S, M, N, device=DEV, dtype=torch.bfloat16); gz = torch.empty_like(z)
+bias = torch.randn(S, N, device=DEV)
+gws = torch.zeros(lib.bf_gelu_bwd_bias_grad_workspace_bytes(S, M, N), dtype=torch.uint8, device=DEV)
+for _ in range(2):
+    lib.bf_linear_fwd_gelu(x.data_ptr(), w.data_ptr(), bias.data_ptr(), z.data_ptr(), y.data_ptr(), S, M, N, K, st)
+    lib.bf_gelu_bwd_bias_grad(gy.data_ptr(), z.data_ptr(), gz.data_ptr(), db.data_ptr(), S, M, N, gws.data_ptr(), st)
+# fused clip + AdamW over 2 x 16.8 M fp32 parameters
 import bayeformers_b200 as bf
+pp = [torch.nn.Parameter(torch.randn(4096, 4096, device=DEV)) for _ in range(2)]
+opt = bf.optim.ClipAdamW(pp, lr=1e-3, max_grad_norm=1.0)
+for q in pp:
+    q.grad = torch.randn_like(q)
+for _ in range(2):
+    opt.step()
+# multi-tensor sample+KL over a 2 x (4096 x 4096 + bias) model, S = 4, MOPED prior, bf16 weights
 net = torch.nn.Sequential(torch.nn.Linear(4096, 4096), torch.nn.Linear(4096, 4096))
 bm = bf.to_bayesian(net, delta=0.05, freeze=True, gemm_dtype="bf16").to(DEV)
 bf.enable_presample(bm)
