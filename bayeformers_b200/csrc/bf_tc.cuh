@@ -129,9 +129,12 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// arrive on the leader CTA's copy of a barrier (works from either CTA of the pair)
+// arrive on the leader CTA's copy of a barrier (works from either CTA of the pair).  No cluster-scope release:
+// what the waiter consumes is TMEM (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync on this side
+// and tcgen05.fence::after_thread_sync on the other), not generic memory -- a `.release.cluster` arrive costs a
+// cluster-wide memory barrier per warp per tile (9 % of the fused-GELU kernel's stall samples in ncu).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
