@@ -64,7 +64,8 @@ def _is_exact_gelu(fn) -> bool:
     return fn is tnn.functional.gelu
 
 
-def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True) -> tnn.Module:
+def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True,
+                     fuse_residual: bool = False) -> tnn.Module:
     """Opt-in plumbing for the frequentist code AROUND the Bayesian layers of a host model.  In place; parameters,
     state_dict names and numerics (to rounding) are unchanged.
 
@@ -73,10 +74,19 @@ def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool 
     fuse_gelu  HuggingFace feed-forward blocks of the form `x = self.dense(x); x = self.intermediate_act_fn(x)`
                (BertIntermediate and its clones) whose `dense` is a Bayesian Linear and whose activation is the
                exact GELU: move the activation INTO the layer (`dense.activation = "gelu"`, fused tensor-core
-               epilogue) and replace the module's activation by the identity."""
+               epilogue) and replace the module's activation by the identity.
+    fuse_residual  HuggingFace output blocks `LayerNorm(dropout(dense(x)) + input_tensor)` (BertSelfOutput,
+               BertOutput and their clones) whose `dense` is a Bayesian Linear: dropout + residual add + LayerNorm
+               run as one kernel pass each way, the dropout mask comes from the Philox counter stream (never
+               stored), and the pass also yields `dense`'s bias gradient (nn/layers/fused.py)."""
+    from .nn.layers.fused import fuse_output_block_, is_output_block
     from .nn.layers.layernorm import HostLayerNorm
     from .nn.layers.linear import Linear
 
+    if fuse_residual:
+        for mod in list(model.modules()):
+            if is_output_block(mod):
+                fuse_output_block_(mod)
     for mod in model.modules():
         if layernorm and mod.__class__ is tnn.LayerNorm and mod.elementwise_affine and len(mod.normalized_shape) == 1:
             mod.__class__ = HostLayerNorm

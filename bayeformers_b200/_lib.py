@@ -77,6 +77,15 @@ SIGNATURES = {
     "bf_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "bf_resln_supported": (c_int32, [c_int64]),
+    "bf_resln_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                               c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "bf_resln_bwd_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_resln_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                               c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    "bf_dropout_mask": (c_int32, [c_void_p, c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p]),
 }
 
 _lib = None

@@ -45,7 +45,9 @@ class LayerNorm(BayesianLayer):
             self.bias_prior = NoneParameter()
         self._init_scalars()
 
-    def forward(self, input: Tensor) -> Tensor:
+    def sample_affine(self):
+        """Draw gamma_s / beta_s for the current mc_samples and publish the layer's log-probs
+        (weight then bias, as Linear does).  Returns (w [S, H] fp32, b [S, H] fp32 or None, S)."""
         S = runtime.get_mc_samples()
         kl_grad = self._kl_grad()
         wp = prior_spec_of(self.weight_prior)
@@ -58,6 +60,10 @@ class LayerNorm(BayesianLayer):
                                                self.bias.next_stream(S), S, torch.float32, kl_grad)
             logq, logp = logq + lq_b, logp + lp_b
         self._publish(logq, logp, S, kl_grad)
+        return w, b, S
+
+    def forward(self, input: Tensor) -> Tensor:
+        w, b, S = self.sample_affine()
         if len(self.normalized_shape) == 1 and ops.layernorm_supported(input, self.normalized_shape):
             if input.shape[0] % S != 0:
                 raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")

@@ -42,6 +42,9 @@ class Linear(BayesianLayer):
         # extension (default None = the reference's plain affine map): "gelu" applies the exact GELU inside the
         # layer, fused into the tensor-core epilogue (forward) and into the bias-gradient pass (backward)
         self.activation: Optional[str] = None
+        # one-shot hand-off set by a fused consumer of this layer's output (layers/fused.py): a list its backward
+        # fills with the row sums of the output gradient, so this layer's backward skips its own bias-gradient pass
+        self._bias_grad_box: Optional[list] = None
         self._init_scalars()
 
     def forward(self, input: Tensor) -> Tensor:
@@ -62,6 +65,7 @@ class Linear(BayesianLayer):
                                   b_prior=b_prior, w_stream=self.weight.next_stream(S),
                                   b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec(),
                                   activation=self.activation)
+        spec.bias_grad_box, self._bias_grad_box = self._bias_grad_box, None
         self._last_streams = (spec.w_stream, spec.b_stream)  # identity of this forward's eps draw (tests, debugging)
         y, logq, logp = ops.BayesLinear.apply(
             input, self.weight.mu, self.weight.rho,

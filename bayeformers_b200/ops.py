@@ -232,6 +232,7 @@ class LinearSpec:
     b_stream: StreamSpec = field(default_factory=StreamSpec)
     presampled: Optional[Tuple] = None  # (W[S,N,K], b[S,N] or None, logq[S], logp[S]) from presample.Presampler
     activation: Optional[str] = None    # None | "gelu": y = act(x w^T + b) with the activation fused where possible
+    bias_grad_box: Optional[list] = None  # filled by ResidualLayerNormFn.backward with sum_m gy[s][m][:] ([S, N] fp32)
 
 
 def tc_eligible(N: int, K: int) -> bool:
@@ -355,6 +356,12 @@ class BayesLinear(torch.autograd.Function):
                 _lib.check(rc, "bf_linear_dgrad")
                 stats["launches"] += 1
                 g_x = dx.view(x_shape).to(x_dtype)
+            if has_bias and db is None and spec.bias_grad_box:
+                # the consumer of y (fused dropout + residual + LayerNorm backward) already reduced gy over rows
+                cand = spec.bias_grad_box.pop()
+                spec.bias_grad_box.clear()
+                if cand is not None and tuple(cand.shape) == (S, N) and cand.dtype == torch.float32:
+                    db = cand
             if has_bias and db is None:
                 db = torch.empty((S, N), dtype=torch.float32, device=dev)
                 bws = _workspace("bias_grad", dev, lib.bf_bias_grad_workspace_bytes(S, M, N))
@@ -452,6 +459,100 @@ class LayerNormFn(torch.autograd.Function):
         dg = dgamma.view(g_shape).to(g_dtype) if ctx.needs_input_grad[1] else None
         db = dbeta.view(g_shape).to(b_dtype) if (dbeta is not None and ctx.needs_input_grad[2]) else None
         return dx.view(gy.shape), dg, db, None, None
+
+
+@dataclass
+class DropoutSpec:
+    """Identity of one dropout draw: keep mask = f(seed, site_id, step [+ device step], element)."""
+    p: float = 0.0
+    seed: int = 0
+    site_id: int = 0
+    step: int = 0
+
+
+class ResidualLayerNormFn(torch.autograd.Function):
+    """y = layer_norm(dropout_p(h) + r) * gamma_s + beta_s in one pass each way
+    (`bf_resln_fwd` / `bf_resln_bwd`): the code around a Bayesian Linear in a
+    transformer output block.  gamma / beta: fp32 [S, H] (sampled, row A10) or [H]
+    (shared).  The dropout mask is regenerated from its Philox counter in backward.
+    `bias_grad_box` (a list) receives sum_m dh[s][m][:] for the Linear that made h."""
+
+    @staticmethod
+    def forward(ctx, h, r, gamma, beta, S: int, eps: float, drop: DropoutSpec, bias_grad_box):
+        _require_cuda(h, "input")
+        lib = _lib.load()
+        dev = h.device
+        H = h.shape[-1]
+        rows = h.numel() // H
+        if r.shape != h.shape or r.dtype != h.dtype:
+            raise ValueError(f"residual {tuple(r.shape)}/{r.dtype} does not match input {tuple(h.shape)}/{h.dtype}")
+        if rows % S != 0:
+            raise ValueError(f"{rows} rows are not a multiple of mc_samples={S}")
+        M = rows // S
+        hc, rc_ = h.detach().contiguous(), r.detach().contiguous()
+        g = gamma.detach().to(torch.float32).contiguous()
+        b = None if beta is None else beta.detach().to(torch.float32).contiguous()
+        stride = H if g.dim() == 2 and g.shape[0] == S and S > 1 else 0
+        if g.numel() != (S * H if stride else H):
+            raise ValueError(f"affine of shape {tuple(gamma.shape)} does not match S={S}, H={H}")
+        z, y = torch.empty_like(hc), torch.empty_like(hc)
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        nbytes = float(rows * H * hc.element_size() * 4)
+        rc = _timed("resln_fwd", nbytes, dev, lambda: lib.bf_resln_fwd(
+            _ptr(hc), _ptr(rc_), _dt(hc.dtype), _ptr(g), _ptr(b), stride, S, M, H, float(eps), float(drop.p), drop.seed,
+            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), _stream(dev)))
+        _lib.check(rc, "bf_resln_fwd")
+        stats["launches"] += 1
+        ctx.save_for_backward(z, g, mean, rstd)
+        ctx.meta = (S, M, H, stride, gamma.shape, gamma.dtype, None if beta is None else beta.dtype, drop, bias_grad_box)
+        return y.view(h.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        z, g, mean, rstd = ctx.saved_tensors
+        S, M, H, stride, g_shape, g_dtype, b_dtype, drop, box = ctx.meta
+        dev = z.device
+        gyc = gy.contiguous().to(z.dtype)
+        dz = torch.empty_like(z)
+        dh = torch.empty_like(z) if drop.p > 0 else None
+        Sa = S if stride else 1
+        dgamma = torch.empty((Sa, H), dtype=torch.float32, device=dev)
+        dbeta = torch.empty((Sa, H), dtype=torch.float32, device=dev) if b_dtype is not None else None
+        dbias = torch.empty((S, H), dtype=torch.float32, device=dev) if box is not None else None
+        ws = _workspace("resln_bwd", dev, lib.bf_resln_bwd_workspace_bytes(S, M, H))
+        nbytes = float(z.numel() * z.element_size() * (4 if dh is not None else 3))
+        rc = _timed("resln_bwd", nbytes, dev, lambda: lib.bf_resln_bwd(
+            _ptr(gyc), _ptr(z), _dt(z.dtype), _ptr(g), stride, _ptr(mean), _ptr(rstd), S, M, H, float(drop.p), drop.seed,
+            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dz), _ptr(dh), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(ws),
+            _stream(dev)))
+        _lib.check(rc, "bf_resln_bwd")
+        stats["launches"] += 1
+        if box is not None:
+            box.clear()
+            box.append(dbias)
+        dzv = dz.view(gy.shape)
+        dhv = dzv if dh is None else dh.view(gy.shape)
+        dg = dgamma.view(g_shape).to(g_dtype) if ctx.needs_input_grad[2] else None
+        db = dbeta.view(g_shape).to(b_dtype) if (dbeta is not None and ctx.needs_input_grad[3]) else None
+        return dhv, dzv, dg, db, None, None, None, None
+
+
+def dropout_mask(n: int, drop: DropoutSpec, device) -> torch.Tensor:
+    """The keep mask (uint8, 1 = kept) `ResidualLayerNormFn` applies to a flat tensor of n elements -- tests."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    rc = lib.bf_dropout_mask(_ptr(out), n, float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _stream(dev))
+    _lib.check(rc, "bf_dropout_mask")
+    return out
+
+
+def resln_supported(h: torch.Tensor, r: torch.Tensor) -> bool:
+    """Shapes / dtypes the fused dropout + residual + LayerNorm kernels take."""
+    return (h.is_cuda and r.is_cuda and h.shape == r.shape and h.dtype == r.dtype
+            and h.dtype in (torch.float32, torch.bfloat16) and bool(_lib.load().bf_resln_supported(int(h.shape[-1]))))
 
 
 def layernorm_supported(x: torch.Tensor, normalized_shape) -> bool:

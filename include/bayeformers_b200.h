@@ -249,6 +249,40 @@ int bf_layernorm_bwd(const void* gy, const void* x, int32_t dtype, const float* 
                      float* dbeta, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Fused  y = LayerNorm(dropout(h) + r)  around a Bayesian Linear (the "output"
+ * blocks of a transformer host model: dense -> dropout -> LayerNorm(h + input),
+ * e.g. transformers' BertSelfOutput / BertOutput).  The LayerNorm is the S-sample
+ * LayerNorm above (per-sample affine) or the host model's
+ * frequentist one (affine_stride == 0).
+ *
+ *   fwd : z = dropout_p(h) + r (kept for bwd, rounded to `dtype`), y = LN(z)*gamma_s + beta_s
+ *   bwd : dz (gradient of r), dh = dz * keep / (1 - p) (gradient of h),
+ *         dgamma, dbeta, and dbias[s][:] = sum_m dh[s][m][:]  -- the bias gradient of the
+ *         Linear that produced h, so that layer skips its bf_bias_grad pass
+ *
+ * The keep mask is never stored: keep(e) = u16(e) >= round(p * 65536), where the 8 u16 of
+ * elements [8k, 8k+8) are the 16-bit halves (low half first) of the four words of
+ * Philox4x32-10(counter = (k & 0xffffffff, k >> 32, 0x80000000 | site_id, step [+ device
+ * step counter]), key = seed); backward regenerates it.  bf_dropout_mask writes that
+ * mask as bytes (for tests).  p_drop == 0 switches dropout off (dh may be NULL; dh == dz).
+ *
+ * h, r, z, y, gy, dz, dh  [S*M, H] of `dtype`; gamma, beta, mean, rstd as for bf_layernorm_*
+ * dbias      [S, H] fp32 or NULL;  dgamma / dbeta  [S, H] (affine_stride != 0) or [H]
+ * workspace  bf_resln_bwd_workspace_bytes(S, M, H) bytes, zero-filled once
+ * ------------------------------------------------------------------------- */
+int bf_resln_supported(int64_t H);
+int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
+                 int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop, uint64_t seed,
+                 uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd, void* stream);
+int64_t bf_resln_bwd_workspace_bytes(int64_t S, int64_t M, int64_t H);
+int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
+                 const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop, uint64_t seed,
+                 uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma, float* dbeta, float* dbias,
+                 void* workspace, void* stream);
+int bf_dropout_mask(uint8_t* out, int64_t n, float p_drop, uint64_t seed, uint32_t step, uint32_t site_id,
+                    void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Fused global-norm clipping + AdamW over all trainable tensors.
  * Replaces clip_grad_norm_(params, max_norm) + AdamW.step() of the reference's
  * training loop (examples/bert_glue.py:240-241); arithmetic of torch.optim.AdamW

@@ -82,3 +82,30 @@ KAT_PHILOX4X32_10 = [
     ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
      (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
 ]
+
+
+def dropout_keep_mask(n: int, p: float, seed: int, step: int, site_id: int) -> np.ndarray:
+    """Keep mask (uint8, 1 = kept) of the fused dropout + residual + LayerNorm kernels
+    (include/bayeformers_b200.h, bf_resln_fwd / bf_dropout_mask).  The reference's
+    examples use torch's nn.Dropout inside the HF host model; this states the
+    counter-based replacement so that backward regenerates the mask instead of storing it.
+
+    Contract
+        counter = (k & 0xffffffff, k >> 32, 0x80000000 | site_id, step)    k = flat_element_index >> 3
+        out     = philox4x32_10(counter, key = seed) -> (r0, r1, r2, r3)
+        u16 of element 8k + 2i     = r_i & 0xffff
+        u16 of element 8k + 2i + 1 = r_i >> 16
+        keep    = u16 >= min(floor(p * 65536 + 0.5), 65535);  p <= 0 keeps everything
+    """
+    if p <= 0:
+        return np.ones(n, dtype=np.uint8)
+    thr = min(int(np.floor(np.float32(p).astype(np.float64) * 65536.0 + 0.5)), 65535)
+    no = (n + 7) // 8
+    k = np.arange(no, dtype=np.uint64)
+    r = philox4x32_10(k & MASK32, k >> np.uint64(32), 0x80000000 | (site_id & 0x7FFFFFFF), step,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = np.empty((no, 8), dtype=np.uint32)
+    for i in range(4):
+        u[:, 2 * i] = r[i] & np.uint32(0xFFFF)
+        u[:, 2 * i + 1] = r[i] >> np.uint32(16)
+    return (u.reshape(-1)[:n] >= thr).astype(np.uint8)

@@ -893,6 +893,138 @@ def test_embedding_and_layernorm_against_composed_oracle(H):
     assert rel_err(bl.bias.mu.grad.cpu().numpy(), mu_b.grad.numpy()) < 1e-4
 
 
+# ------------------------------------------------------------------ fused dropout + residual + LayerNorm (output blocks)
+def test_dropout_mask_matches_oracle_contract():
+    for n, p, seed, step, site in [(8 * 1000, 0.1, 1234, 0, 1), (4099, 0.5, 0xDEADBEEFCAFEF00D, 9, 77), (5, 0.25, 3, 2, 1)]:
+        got = ops.dropout_mask(n, ops.DropoutSpec(p, seed, site, step), DEV).cpu().numpy()
+        assert np.array_equal(got, P.dropout_keep_mask(n, p, seed, step, site))  # integer work: bit-exact
+    n = 1 << 22
+    m = ops.dropout_mask(n, ops.DropoutSpec(0.1, 5, 3, 1), DEV).float()
+    assert abs(float(m.mean()) - 0.9) < 5 * np.sqrt(0.09 / n) + 1e-5
+    m2 = ops.dropout_mask(n, ops.DropoutSpec(0.1, 5, 3, 2), DEV).float()  # next step: independent mask
+    assert abs(float((m * m2).mean()) - 0.81) < 1e-3
+    assert bool(ops.dropout_mask(1000, ops.DropoutSpec(0.0, 5, 3, 1), DEV).all())
+
+
+@pytest.mark.parametrize("S,M,H,shared", [(1, 7, 256, True), (3, 33, 768, False), (4, 1000, 768, True),
+                                          (2, 129, 1024, False), (4, 515, 1024, True), (1, 4096, 512, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_resln_vs_torch_fp64(S, M, H, shared, dtype, p):
+    """bf_resln_fwd/bwd through ops.ResidualLayerNormFn against float64 torch:
+    y = layer_norm(h * keep / (1 - p) + r) per sample, with the keep mask the kernel regenerates."""
+    gen = torch.Generator().manual_seed(S * 1000 + M + H)
+    h = (torch.randn(S * M, H, generator=gen) * 1.5).to(dtype)
+    r = (torch.randn(S * M, H, generator=gen) + 0.3).to(dtype)
+    gamma = 1 + 0.1 * torch.randn(H if shared else (S, H), generator=gen)
+    beta = 0.1 * torch.randn(H if shared else (S, H), generator=gen)
+    gy = torch.randn(S * M, H, generator=gen).to(dtype)
+    spec = ops.DropoutSpec(p=p, seed=99, site_id=11, step=4)
+    hd, rd = h.to(DEV).requires_grad_(), r.to(DEV).requires_grad_()
+    gd, bd = gamma.to(DEV).requires_grad_(), beta.to(DEV).requires_grad_()
+    box = []
+    y = ops.ResidualLayerNormFn.apply(hd, rd, gd, bd, S, 1e-12, spec, box)
+    y.backward(gy.to(DEV))
+    keep = ops.dropout_mask(S * M * H, spec, DEV).cpu().view(S * M, H).double()
+    h64, r64 = h.double().requires_grad_(), r.double().requires_grad_()
+    g64, b64 = gamma.double().requires_grad_(), beta.double().requires_grad_()
+    z64 = h64 * keep / (1.0 - np.float32(p).astype(np.float64)) + r64
+    y64 = torch.cat([torch.nn.functional.layer_norm(z64[s * M:(s + 1) * M], (H,), g64 if shared else g64[s],
+                                                    b64 if shared else b64[s], 1e-12) for s in range(S)])
+    y64.backward(gy.double())
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert y.dtype == dtype
+    assert rel_err(y.detach().float().cpu().numpy(), y64.detach().numpy()) < tol
+    assert rel_err(hd.grad.float().cpu().numpy(), h64.grad.numpy()) < tol
+    assert rel_err(rd.grad.float().cpu().numpy(), r64.grad.numpy()) < tol
+    atol = 2e-5 if dtype == torch.float32 else 1e-2  # bf16: z is rounded before it is normalised
+    assert rel_err(gd.grad.cpu().numpy(), g64.grad.numpy()) < atol
+    assert rel_err(bd.grad.cpu().numpy(), b64.grad.numpy()) < 2e-5
+    # the bias gradient handed to the producing Linear: per-sample column sums of dh
+    assert len(box) == 1 and tuple(box[0].shape) == (S, H)
+    assert rel_err(box[0].cpu().numpy(), h64.grad.view(S, M, H).sum(1).numpy()) < (2e-5 if dtype == torch.float32 else 2e-3)
+    if p > 0:  # dropped positions carry exactly zero gradient
+        assert bool((hd.grad.cpu()[keep == 0] == 0).all())
+    # deterministic: a second run gives the same bits
+    hd2, rd2 = h.to(DEV).requires_grad_(), r.to(DEV).requires_grad_()
+    gd2, bd2 = gamma.to(DEV).requires_grad_(), beta.to(DEV).requires_grad_()
+    box2 = []
+    y2 = ops.ResidualLayerNormFn.apply(hd2, rd2, gd2, bd2, S, 1e-12, spec, box2)
+    y2.backward(gy.to(DEV))
+    assert torch.equal(y, y2) and torch.equal(hd.grad, hd2.grad) and torch.equal(rd.grad, rd2.grad)
+    assert torch.equal(gd.grad, gd2.grad) and torch.equal(bd.grad, bd2.grad) and torch.equal(box[0], box2[0])
+
+
+@pytest.mark.parametrize("mode,bayes_ln", [("fp32", False), ("bf16", False), ("fp32", True)])
+def test_accelerate_host_fuses_hf_output_blocks(mode, bayes_ln):
+    """accelerate_host_(fuse_residual=True) on HF BERT layers: with dropout off the fused model reproduces the
+    unfused one (logits, log-probs and every gradient incl. the bias gradients handed over by the fused
+    backward); with dropout on, the block equals its manual composition under the regenerated mask."""
+    import copy
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(2)
+    cfg = BertConfig(num_labels=2, num_hidden_layers=2, hidden_size=256, intermediate_size=512, num_attention_heads=4)
+    layers = bnn.TORCH2BAYE_ALL if bayes_ln else None
+    base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=False, gemm_dtype=mode, kl_grad=True,
+                          layers=layers)
+    fused = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, fuse_residual=True)
+    blocks = [m for m in fused.modules() if type(m).__name__.startswith("Fused")]
+    assert len(blocks) == 4 and list(fused.state_dict()) == list(base.state_dict())
+    S, B, Tn = 2, 4, 16
+    ids = torch.randint(0, cfg.vocab_size, (B, Tn), generator=torch.Generator().manual_seed(3)).to(DEV)
+    outs = []
+    for m in (base, fused):
+        m = m.to(DEV).eval()  # eval(): dropout off, so both models compute the same function
+        if mode == "bf16":
+            bf.cast_frequentist_(m, torch.bfloat16)
+        gen = torch.Generator().manual_seed(5)
+        for l in m.bayesian_children:
+            for g in (l.weight, getattr(l, "bias", None)):
+                if isinstance(g, bnn.Gaussian):
+                    g.normal = FixedEps([torch.randn(g.mu.shape, generator=gen) for _ in range(S)])
+        with bf.mc_samples(S):
+            logits = m(input_ids=ids.repeat(S, 1)).logits.float()
+        lp, lq = m.log_prior(), m.log_variational_posterior()
+        (logits.square().sum() + 1e-3 * (lq - lp).sum()).backward()
+        outs.append((logits.detach(), lp.detach(), lq.detach(), {n: p.grad for n, p in m.named_parameters() if p.grad is not None}))
+    tol = FP32_TOL * 10 if mode == "fp32" else BF16_TOL  # fp32: different (still fp32) summation orders through 2 layers
+    assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < tol
+    assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < FP32_TOL
+    assert rel_err(outs[1][2].cpu().numpy(), outs[0][2].cpu().numpy()) < FP32_TOL
+    assert outs[0][3].keys() == outs[1][3].keys()
+    gtol = 1e-3 if mode == "fp32" else 5e-2
+    for n in outs[0][3]:
+        assert rel_err(outs[1][3][n].float().cpu().numpy(), outs[0][3][n].float().cpu().numpy()) < gtol, n
+    # dropout on: one block against its manual composition with the mask the kernels regenerate
+    blk = blocks[1].train()
+    H = cfg.hidden_size
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    x = torch.randn(S * B * Tn, cfg.intermediate_size, device=DEV, dtype=dt)
+    res = torch.randn(S * B * Tn, H, device=DEV, dtype=dt)
+    gen = torch.Generator().manual_seed(6)
+    eps_w = [torch.randn(blk.dense.weight.mu.shape, generator=gen) for _ in range(S)]
+    eps_b = [torch.randn(blk.dense.bias.mu.shape, generator=gen) for _ in range(S)]
+    ln = blk.LayerNorm
+    eps_ln = [[torch.randn(H, generator=gen) for _ in range(S)] for _ in range(2)] if bayes_ln else None
+
+    def arm():
+        blk.dense.weight.normal, blk.dense.bias.normal = FixedEps(list(eps_w)), FixedEps(list(eps_b))
+        if bayes_ln:
+            ln.weight.normal, ln.bias.normal = FixedEps(list(eps_ln[0])), FixedEps(list(eps_ln[1]))
+
+    arm()
+    with bf.mc_samples(S):
+        y = blk(x, res)
+    spec = blk._last_dropout
+    assert spec.p == pytest.approx(cfg.hidden_dropout_prob)
+    keep = ops.dropout_mask(y.numel(), spec, DEV).view_as(y)
+    arm()
+    with bf.mc_samples(S):
+        h = blk.dense(x)
+        want = ln(h * keep.to(h.dtype) / (1 - spec.p) + res)
+    assert rel_err(y.detach().float().cpu().numpy(), want.detach().float().cpu().numpy()) < (FP32_TOL if mode == "fp32" else BF16_TOL)
+
+
 # ------------------------------------------------------------------ BASELINE-size properties (config 2: 4096x4096)
 def test_full_size_properties_config2():
     n, S = 4096 * 4096, 4

@@ -222,6 +222,33 @@ def test_accelerate_host_swaps_layernorm_and_fuses_hf_gelu():
     assert other.model[0].dense.activation is None and isinstance(other.model[0].intermediate_act_fn, torch.nn.ReLU)
 
 
+def test_accelerate_host_fuses_output_blocks():
+    import copy
+    from transformers import BertConfig, BertForSequenceClassification
+    cfg = BertConfig(num_labels=2, num_hidden_layers=2, hidden_size=64, num_attention_heads=4, intermediate_size=128)
+    bm = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True)
+    keys = list(bm.state_dict())
+    bf.accelerate_host_(bm, fuse_residual=True)
+    layer = bm.model.bert.encoder.layer[1]
+    for blk in (layer.attention.output, layer.output):
+        assert type(blk).__name__.startswith("Fused") and isinstance(blk, torch.nn.Module)
+        assert type(blk).__mro__[2].__name__ in ("BertSelfOutput", "BertOutput")
+    sites = [m._bf_site for m in bm.modules() if hasattr(m, "_bf_site")]
+    assert len(sites) == 4 and len(set(sites)) == 4  # one dropout stream per block
+    assert list(bm.state_dict()) == keys  # checkpoint names unchanged
+    assert type(copy.deepcopy(bm).model.bert.encoder.layer[0].output).__name__ == "FusedBertOutput"
+    # a block whose dense is not Bayesian, or with extra children, is left alone
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense, self.LayerNorm, self.dropout = torch.nn.Linear(8, 8), torch.nn.LayerNorm(8), torch.nn.Dropout(0.1)
+    plain = bf.accelerate_host_(torch.nn.Sequential(Block()), fuse_residual=True)
+    assert type(plain[0]) is Block
+    # CPU tensors: the stock forward of the block runs up to the Bayesian Linear, which refuses (no CPU path)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer.output(torch.randn(2, 128), torch.randn(2, 64))
+
+
 def test_harness_fold_pick_and_predictive_stats():
     from bayeformers_b200 import harness
     x = torch.arange(6).view(2, 3)

@@ -150,6 +150,19 @@ def test_philox_normal_moments_and_streams():
     assert np.array_equal(P.philox_normal(1001, 7, 0, 0, 0), P.philox_normal(4096, 7, 0, 0, 0)[:1001])
 
 
+def test_dropout_mask_contract():
+    """keep = u16 >= round(p * 65536) on the 16-bit halves of the Philox words (first word pinned by the KAT)."""
+    m = P.dropout_keep_mask(1 << 20, 0.1, seed=11, step=2, site_id=5)
+    assert abs(m.mean() - 0.9) < 5 * np.sqrt(0.09 / m.size) + 1e-5
+    r = P.philox4x32_10(0, 0, 0x80000000 | 5, 2, 11, 0)
+    thr = int(np.floor(np.float32(0.1).astype(np.float64) * 65536 + 0.5))
+    first = [(int(r[i]) >> sh) & 0xFFFF for i in range(4) for sh in (0, 16)]
+    assert list(m[:8]) == [int(u >= thr) for u in first]
+    assert np.array_equal(P.dropout_keep_mask(1001, 0.1, 11, 2, 5), m[:1001])  # prefix property
+    assert not np.array_equal(P.dropout_keep_mask(4096, 0.1, 11, 3, 5), m[:4096])  # next step: new mask
+    assert P.dropout_keep_mask(100, 0.0, 1, 1, 1).all()
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/bayeformers"), reason="live reference only in the build container")
 def test_oracle_convert_matches_live_reference():
     import sys
