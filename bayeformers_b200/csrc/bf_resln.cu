@@ -20,6 +20,8 @@
 // One warp owns one row, held in registers as 16-byte chunks (H = 256*C, lane l holds elements
 // [c*256 + l*8, +8)); statistics are two-pass fp32 on the stored (rounded) z so that backward sees
 // exactly the values forward normalised.  Reductions are fixed-order two-stage (no float atomics).
+#include <cstdlib>
+
 #include "bf_common.cuh"
 
 namespace {
@@ -34,6 +36,9 @@ template <>
 struct Pack8<__nv_bfloat16> {
     uint4 u;
     __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = __ldcs(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void load_smem(const char* row, int c, int lane) {
+        u = *reinterpret_cast<const uint4*>(row + c * 512 + lane * 16);
+    }
     __device__ __forceinline__ void get(float (&v)[8]) const {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -71,6 +76,11 @@ struct Pack8<float> {
     __device__ __forceinline__ void load(const float* p) {
         a = __ldcs(reinterpret_cast<const float4*>(p));
         b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    }
+    // fp32 is the parity mode: the 32-byte lane stride costs a 2-way bank conflict, accepted
+    __device__ __forceinline__ void load_smem(const char* row, int c, int lane) {
+        a = *reinterpret_cast<const float4*>(row + c * 1024 + lane * 32);
+        b = *reinterpret_cast<const float4*>(row + c * 1024 + lane * 32 + 16);
     }
     __device__ __forceinline__ void get(float (&v)[8]) const {
         v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
@@ -200,101 +210,27 @@ __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
 }
 
 // ------------------------------------------------------------------ backward
-// workspace: [S + 1 counters, padded to 256 B][S][nblk][3][H] block partials [S][2][H] per-sample affine sums
+// Tail shared by both backward kernels: block reduction of the three column accumulators through shared
+// memory (kRedRows warps' worth at a time, fixed order), per-block partial, then the last block of each sample
+// (and, for a shared affine, the last of those) adds the partials in a fixed order.  `red_raw`: kRedRows*3*H floats.
 template <int C>
-struct BwdCfg {
-    static constexpr int kThreads = C <= 2 ? 384 : 256;  // register budget: 3 x C x 8 accumulators per thread
+struct RedCfg {
+    static constexpr int kRedRows = C <= 3 ? 4 : 2;  // <= 48 KB
 };
 
-template <typename T, int C, bool kDrop>
-__global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
-    resln_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ z, const float* __restrict__ gamma,
-                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dz,
-                     T* __restrict__ dh, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ sample_part,
-                     unsigned int* __restrict__ counters, int64_t M, int64_t affine_stride, int S, DropSpec drop) {
+template <int C, int kThreads>
+__device__ __forceinline__ void bwd_finish(float (&acc_g)[C][8], float (&acc_b)[C][8], float (&acc_h)[C][8],
+                                           float* red_raw, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                           float* __restrict__ dbias, float* __restrict__ partial,
+                                           float* __restrict__ sample_part, unsigned int* __restrict__ counters,
+                                           int64_t affine_stride, int S) {
+    constexpr int kRedRows = RedCfg<C>::kRedRows;
+    // ---- block reduction through shared memory, 4 warps' worth at a time; fixed order -> deterministic
     constexpr int H = 256 * C;
-    constexpr int kThreads = BwdCfg<C>::kThreads;
     constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.y, nblk = gridDim.x;
-    const float* g = gamma + (int64_t)s * affine_stride;
-    const int64_t row0 = (int64_t)s * M;
-    const uint32_t step = drop.step + (drop.step_ptr ? *drop.step_ptr : 0u);
-    float acc_g[C][8], acc_b[C][8], acc_h[C][8];  // sum gy*xhat, sum gy, sum dh
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = acc_h[c][j] = 0.0f;
-
-    const int64_t m_step = (int64_t)nblk * kWarps;
-    int64_t m = (int64_t)blockIdx.x * kWarps + warp;
-    Pack8<T> nz[C], ng[C];  // the next row's loads are in flight while this row is reduced
-    if (m < M) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            nz[c].load(z + (row0 + m) * H + c * 256 + lane * 8);
-            ng[c].load(gy + (row0 + m) * H + c * 256 + lane * 8);
-        }
-    }
-    for (; m < M; m += m_step) {
-        const int64_t row = row0 + m;
-        Pack8<T> pz[C], pg[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) pz[c] = nz[c], pg[c] = ng[c];
-        if (m + m_step < M) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                nz[c].load(z + (row + m_step) * H + c * 256 + lane * 8);
-                ng[c].load(gy + (row + m_step) * H + c * 256 + lane * 8);
-            }
-        }
-        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-        float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float zv[8], gv[8], gm[8];
-            pz[c].get(zv);
-            pg[c].get(gv);
-            ld8f(g + c * 256 + lane * 8, gm);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (zv[j] - mean) * rstd;
-                const float a = gv[j] * gm[j];
-                s1 += a;
-                s2 = fmaf(a, xh, s2);
-                acc_g[c][j] = fmaf(gv[j], xh, acc_g[c][j]);
-                acc_b[c][j] += gv[j];
-            }
-        }
-        const float c1 = bf_warp_sum(s1) * (1.0f / H), c2 = bf_warp_sum(s2) * (1.0f / H);
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float zv[8], gv[8], gm[8], o[8];
-            pz[c].get(zv);
-            pg[c].get(gv);
-            ld8f(g + c * 256 + lane * 8, gm);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (zv[j] - mean) * rstd;
-                o[j] = rstd * (gv[j] * gm[j] - c1 - xh * c2);
-            }
-            Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
-            if (kDrop) {
-                float mk[8];
-                drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] *= mk[j];
-                Pack8<T>::store(dh + row * H + c * 256 + lane * 8, o);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc_h[c][j] += o[j];
-        }
-    }
-
-    // ---- block reduction through shared memory, 4 warps' worth at a time; fixed order -> deterministic
-    constexpr int kRedRows = C <= 3 ? 4 : 2;  // <= 48 KB of static shared memory
-    __shared__ float red[kRedRows][3 * H];
+    float(*red)[3 * H] = reinterpret_cast<float(*)[3 * H]>(red_raw);
     __shared__ bool is_last;
 #pragma unroll 1
     for (int base = kRedRows; base < kWarps + kRedRows; base += kRedRows) {
@@ -408,23 +344,274 @@ __global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
     if (threadIdx.x == 0) counters[S] = 0u;
 }
 
+
+// workspace: [S + 1 counters, padded to 256 B][S][nblk][3][H] block partials [S][2][H] per-sample affine sums
 template <int C>
-inline int bwd_blocks(int64_t S, int64_t M) {
-    constexpr int kWarps = BwdCfg<C>::kThreads / 32;
+struct BwdCfg {
+    static constexpr int kThreads = C <= 2 ? 384 : 256;  // register budget: 3 x C x 8 accumulators per thread
+};
+
+template <typename T, int C, bool kDrop>
+__global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
+    resln_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ z, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dz,
+                     T* __restrict__ dh, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ sample_part,
+                     unsigned int* __restrict__ counters, int64_t M, int64_t affine_stride, int S, DropSpec drop) {
+    constexpr int H = 256 * C;
+    constexpr int kThreads = BwdCfg<C>::kThreads;
+    constexpr int kWarps = kThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.y, nblk = gridDim.x;
+    const float* g = gamma + (int64_t)s * affine_stride;
+    const int64_t row0 = (int64_t)s * M;
+    const uint32_t step = drop.step + (drop.step_ptr ? *drop.step_ptr : 0u);
+    float acc_g[C][8], acc_b[C][8], acc_h[C][8];  // sum gy*xhat, sum gy, sum dh
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = acc_h[c][j] = 0.0f;
+
+    const int64_t m_step = (int64_t)nblk * kWarps;
+    int64_t m = (int64_t)blockIdx.x * kWarps + warp;
+    Pack8<T> nz[C], ng[C];  // the next row's loads are in flight while this row is reduced
+    if (m < M) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            nz[c].load(z + (row0 + m) * H + c * 256 + lane * 8);
+            ng[c].load(gy + (row0 + m) * H + c * 256 + lane * 8);
+        }
+    }
+    for (; m < M; m += m_step) {
+        const int64_t row = row0 + m;
+        Pack8<T> pz[C], pg[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) pz[c] = nz[c], pg[c] = ng[c];
+        if (m + m_step < M) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                nz[c].load(z + (row + m_step) * H + c * 256 + lane * 8);
+                ng[c].load(gy + (row + m_step) * H + c * 256 + lane * 8);
+            }
+        }
+        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+        float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float zv[8], gv[8], gm[8];
+            pz[c].get(zv);
+            pg[c].get(gv);
+            ld8f(g + c * 256 + lane * 8, gm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (zv[j] - mean) * rstd;
+                const float a = gv[j] * gm[j];
+                s1 += a;
+                s2 = fmaf(a, xh, s2);
+                acc_g[c][j] = fmaf(gv[j], xh, acc_g[c][j]);
+                acc_b[c][j] += gv[j];
+            }
+        }
+        const float c1 = bf_warp_sum(s1) * (1.0f / H), c2 = bf_warp_sum(s2) * (1.0f / H);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float zv[8], gv[8], gm[8], o[8];
+            pz[c].get(zv);
+            pg[c].get(gv);
+            ld8f(g + c * 256 + lane * 8, gm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (zv[j] - mean) * rstd;
+                o[j] = rstd * (gv[j] * gm[j] - c1 - xh * c2);
+            }
+            Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
+            if (kDrop) {
+                float mk[8];
+                drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] *= mk[j];
+                Pack8<T>::store(dh + row * H + c * 256 + lane * 8, o);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_h[c][j] += o[j];
+        }
+    }
+
+    constexpr int kRedRows = RedCfg<C>::kRedRows;
+    __shared__ float red[kRedRows * 3 * H];
+    bwd_finish<C, kThreads>(acc_g, acc_b, acc_h, red, dgamma, dbeta, dbias, partial, sample_part, counters, affine_stride,
+                            S);
+}
+
+// ---- staged backward: the rows travel global -> shared memory as 1-D bulk async copies (TMA unit, completion on an
+// mbarrier) into a per-warp ring of kStages rows, so the bytes in flight no longer depend on registers
+// (12 warps x kStages x 2 rows of H elements, ~100+ KB per SM) and 12 warps fit the register file
+template <typename T, int C>
+struct StagedCfg {
+    static constexpr int kThreads = C <= 3 ? 384 : 256;  // C = 4: 96 accumulators need > 168 registers, i.e. <= 2 warps per SM sub-partition
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kRowBytes = 256 * C * (int)sizeof(T);
+    static constexpr int kStages = sizeof(T) == 2 ? 4 : 2;
+    static constexpr int kRingBytes = kWarps * kStages * 2 * kRowBytes;
+    static constexpr int kRedBytes = RedCfg<C>::kRedRows * 3 * 256 * C * (int)sizeof(float);
+    static constexpr int kBarBytes = kWarps * kStages * 8;
+    static constexpr int kSmemBytes = (kRingBytes > kRedBytes ? kRingBytes : kRedBytes) + kBarBytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rl_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void rl_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rl_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void rl_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <typename T, int C, bool kDrop>
+__global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
+    resln_bwd_staged_kernel(const T* __restrict__ gy, const T* __restrict__ z, const float* __restrict__ gamma,
+                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dz,
+                            T* __restrict__ dh, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            float* __restrict__ dbias, float* __restrict__ partial, float* __restrict__ sample_part,
+                            unsigned int* __restrict__ counters, int64_t M, int64_t affine_stride, int S, DropSpec drop) {
+    using Cfg = StagedCfg<T, C>;
+    constexpr int H = 256 * C;
+    constexpr int kWarps = Cfg::kWarps, kStages = Cfg::kStages, kRowBytes = Cfg::kRowBytes;
+    extern __shared__ __align__(128) char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.y, nblk = gridDim.x;
+    const float* g = gamma + (int64_t)s * affine_stride;
+    const int64_t row0 = (int64_t)s * M;
+    const uint32_t step = drop.step + (drop.step_ptr ? *drop.step_ptr : 0u);
+    char* ring = smem + (size_t)warp * kStages * 2 * kRowBytes;  // this warp's [kStages][z row, gy row]
+    const uint32_t bars = smem_u32(smem + (Cfg::kSmemBytes - Cfg::kBarBytes)) + warp * kStages * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) rl_mbar_init(bars + st * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    float acc_g[C][8], acc_b[C][8], acc_h[C][8];  // sum gy*xhat, sum gy, sum dh
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = acc_h[c][j] = 0.0f;
+
+    const int64_t m_step = (int64_t)nblk * kWarps;
+    const int64_t m_first = (int64_t)blockIdx.x * kWarps + warp;
+    if (lane == 0) {  // prologue: fill the ring
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) {
+            const int64_t mm = m_first + st * m_step;
+            if (mm < M) {
+                rl_mbar_expect_tx(bars + st * 8, 2 * kRowBytes);
+                rl_bulk_load(smem_u32(ring + (st * 2) * kRowBytes), z + (row0 + mm) * H, kRowBytes, bars + st * 8);
+                rl_bulk_load(smem_u32(ring + (st * 2 + 1) * kRowBytes), gy + (row0 + mm) * H, kRowBytes, bars + st * 8);
+            }
+        }
+    }
+    int st = 0;
+    uint32_t parity = 0;
+    for (int64_t m = m_first; m < M; m += m_step) {
+        const int64_t row = row0 + m;
+        rl_mbar_wait(bars + st * 8, parity);
+        const char* zr = ring + (st * 2) * kRowBytes;
+        const char* gr = zr + kRowBytes;
+        Pack8<T> pz[C], pg[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            pz[c].load_smem(zr, c, lane);
+            pg[c].load_smem(gr, c, lane);
+        }
+        __syncwarp();  // every lane has its copy of the row in registers: the slot can be refilled
+        if (lane == 0) {
+            const int64_t mn = m + (int64_t)kStages * m_step;
+            if (mn < M) {
+                rl_mbar_expect_tx(bars + st * 8, 2 * kRowBytes);
+                rl_bulk_load(smem_u32(ring + (st * 2) * kRowBytes), z + (row0 + mn) * H, kRowBytes, bars + st * 8);
+                rl_bulk_load(smem_u32(ring + (st * 2 + 1) * kRowBytes), gy + (row0 + mn) * H, kRowBytes, bars + st * 8);
+            }
+        }
+        if (++st == kStages) st = 0, parity ^= 1u;
+
+        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+        float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float zv[8], gv[8], gm[8];
+            pz[c].get(zv);
+            pg[c].get(gv);
+            ld8f(g + c * 256 + lane * 8, gm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (zv[j] - mean) * rstd;
+                const float a = gv[j] * gm[j];
+                s1 += a;
+                s2 = fmaf(a, xh, s2);
+                acc_g[c][j] = fmaf(gv[j], xh, acc_g[c][j]);
+                acc_b[c][j] += gv[j];
+            }
+        }
+        const float c1 = bf_warp_sum(s1) * (1.0f / H), c2 = bf_warp_sum(s2) * (1.0f / H);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float zv[8], gv[8], gm[8], o[8];
+            pz[c].get(zv);
+            pg[c].get(gv);
+            ld8f(g + c * 256 + lane * 8, gm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (zv[j] - mean) * rstd;
+                o[j] = rstd * (gv[j] * gm[j] - c1 - xh * c2);
+            }
+            Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
+            if (kDrop) {
+                float mk[8];
+                drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] *= mk[j];
+                Pack8<T>::store(dh + row * H + c * 256 + lane * 8, o);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_h[c][j] += o[j];
+        }
+    }
+    __syncthreads();  // all warps are done with their rings: the reduction scratch aliases them
+    bwd_finish<C, Cfg::kThreads>(acc_g, acc_b, acc_h, reinterpret_cast<float*>(smem), dgamma, dbeta, dbias, partial,
+                                 sample_part, counters, affine_stride, S);
+}
+
+inline int bwd_blocks_w(int64_t S, int64_t M, int kWarps) {
     int64_t per = bf_num_sms() / S;  // one block per SM, spread over the samples
     if (per < 1) per = 1;
     const int64_t need = (M + kWarps - 1) / kWarps;
     if (per > need) per = need;
     return (int)(per < 1 ? 1 : per);
 }
-inline int bwd_blocks_h(int64_t S, int64_t M, int64_t H) {
-    switch (H / 256) {
-        case 1: return bwd_blocks<1>(S, M);
-        case 2: return bwd_blocks<2>(S, M);
-        case 3: return bwd_blocks<3>(S, M);
-        default: return bwd_blocks<4>(S, M);
-    }
+template <int C>
+inline int bwd_blocks(int64_t S, int64_t M) {
+    return bwd_blocks_w(S, M, BwdCfg<C>::kThreads / 32);
 }
+// upper bound over both backward kernels (the workspace is sized with it): fewer warps per block -> more blocks
+inline int bwd_blocks_h(int64_t S, int64_t M, int64_t H) { return bwd_blocks_w(S, M, H / 256 <= 2 ? 12 : 8); }
+static_assert(StagedCfg<float, 4>::kSmemBytes <= 227 * 1024, "staged ring exceeds shared memory");
 inline int64_t counters_bytes(int64_t S) { return (((S + 1) * 4 + 255) / 256) * 256; }
 
 DropSpec make_drop(float p, uint64_t seed, uint32_t step, uint32_t site) {
@@ -453,33 +640,70 @@ int launch_fwd_c(const void* h, const void* r, const float* gamma, const float* 
     return 0;
 }
 
+inline bool use_staged_bwd() {
+    static const int v = [] {
+        const char* e = getenv("BF_RESLN_BWD");  // "regs": force the register-prefetch kernel (A/B timing, debugging)
+        return (e && e[0] == 'r') ? 0 : 1;
+    }();
+    return v != 0;
+}
+
 template <typename T, int C>
 int launch_bwd_c(const void* gy, const void* z, const float* gamma, const float* mean, const float* rstd, void* dz,
                  void* dh, float* dgamma, float* dbeta, float* dbias, void* ws, int64_t S, int64_t M, int64_t astride,
                  const DropSpec& d, cudaStream_t st) {
-    const int nblk = bwd_blocks<C>(S, M);
     constexpr int H = 256 * C;
+    using SC = StagedCfg<T, C>;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(z)) & 15u) == 0;
+    const bool staged = aligned && use_staged_bwd();
+    const int nblk = staged ? bwd_blocks_w(S, M, SC::kWarps) : bwd_blocks<C>(S, M);
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + counters_bytes(S));
     float* sample_part = partial + S * (int64_t)nblk * 3 * H;
     dim3 grid((unsigned)nblk, (unsigned)S);
+    const T* gyp = reinterpret_cast<const T*>(gy);
+    const T* zp = reinterpret_cast<const T*>(z);
+    T* dzp = reinterpret_cast<T*>(dz);
+    T* dhp = reinterpret_cast<T*>(dh);
+    if (staged) {
+        static bool attr_done[2] = {false, false};
+        auto* k1 = resln_bwd_staged_kernel<T, C, true>;
+        auto* k0 = resln_bwd_staged_kernel<T, C, false>;
+        const int which = d.threshold ? 1 : 0;
+        if (!attr_done[which]) {
+            BF_CUDA_OK(cudaFuncSetAttribute(which ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::kSmemBytes));
+            attr_done[which] = true;
+        }
+        if (d.threshold)
+            k1<<<grid, SC::kThreads, SC::kSmemBytes, st>>>(gyp, zp, gamma, mean, rstd, dzp, dhp, dgamma, dbeta, dbias, partial,
+                                                          sample_part, counters, M, astride, (int)S, d);
+        else
+            k0<<<grid, SC::kThreads, SC::kSmemBytes, st>>>(gyp, zp, gamma, mean, rstd, dzp, nullptr, dgamma, dbeta, dbias,
+                                                          partial, sample_part, counters, M, astride, (int)S, d);
+        return 0;
+    }
     if (d.threshold)
-        resln_bwd_kernel<T, C, true><<<grid, BwdCfg<C>::kThreads, 0, st>>>(
-            reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(z), gamma, mean, rstd, reinterpret_cast<T*>(dz),
-            reinterpret_cast<T*>(dh), dgamma, dbeta, dbias, partial, sample_part, counters, M, astride, (int)S, d);
+        resln_bwd_kernel<T, C, true><<<grid, BwdCfg<C>::kThreads, 0, st>>>(gyp, zp, gamma, mean, rstd, dzp, dhp, dgamma,
+                                                                           dbeta, dbias, partial, sample_part, counters, M,
+                                                                           astride, (int)S, d);
     else
-        resln_bwd_kernel<T, C, false><<<grid, BwdCfg<C>::kThreads, 0, st>>>(
-            reinterpret_cast<const T*>(gy), reinterpret_cast<const T*>(z), gamma, mean, rstd, reinterpret_cast<T*>(dz),
-            nullptr, dgamma, dbeta, dbias, partial, sample_part, counters, M, astride, (int)S, d);
+        resln_bwd_kernel<T, C, false><<<grid, BwdCfg<C>::kThreads, 0, st>>>(gyp, zp, gamma, mean, rstd, dzp, nullptr, dgamma,
+                                                                            dbeta, dbias, partial, sample_part, counters, M,
+                                                                            astride, (int)S, d);
     return 0;
 }
 
+#define BF_RESLN_CASE(FN, T, CC, ...)               \
+    case CC: {                                      \
+        const int rc_ = FN<T, CC>(__VA_ARGS__);     \
+        if (rc_ != 0) return rc_;                   \
+    } break;
 #define BF_RESLN_DISPATCH(FN, T, ...)                 \
     switch (H / 256) {                                \
-        case 1: FN<T, 1>(__VA_ARGS__); break;         \
-        case 2: FN<T, 2>(__VA_ARGS__); break;         \
-        case 3: FN<T, 3>(__VA_ARGS__); break;         \
-        case 4: FN<T, 4>(__VA_ARGS__); break;         \
+        BF_RESLN_CASE(FN, T, 1, __VA_ARGS__)          \
+        BF_RESLN_CASE(FN, T, 2, __VA_ARGS__)          \
+        BF_RESLN_CASE(FN, T, 3, __VA_ARGS__)          \
+        BF_RESLN_CASE(FN, T, 4, __VA_ARGS__)          \
         default: bf_set_error("resln: H/256 must be 1..4"); return BF_ERR_UNSUPPORTED; \
     }
 

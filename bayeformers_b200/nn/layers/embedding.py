@@ -48,6 +48,10 @@ class Embedding(BayesianLayer):
                   scale_grad_by_freq=self.scale_grad_by_freq)
         if S == 1:
             return F.embedding(input, w[0], **kw)
+        rows = runtime.get_folded_rows()
+        if input.shape[0] == 1 and rows is not None and rows % S == 0:
+            # broadcast ids (e.g. HF position_ids [1, T]): every folded row looks its ids up in ITS sample's table
+            input = input.expand(rows, *input.shape[1:])
         if input.shape[0] % S != 0:
             raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
         chunks = input.view(S, input.shape[0] // S, *input.shape[1:])

@@ -29,10 +29,20 @@ class Model(Module):
     def forward(self, *args, **kwargs) -> Any:
         if self.model is None:
             raise NotImplementedError("Forward pass not implemented yet")
+        from .. import runtime
+        S = runtime.get_mc_samples()
         if self._presampler is not None:
             # extension: draw every Bayesian Linear's weights for this forward in one multi-tensor launch
-            from .. import runtime
-            self._presampler.run(runtime.get_mc_samples())
+            self._presampler.run(S)
+        if S > 1:
+            # folded forward: remember S*B so Bayesian layers can expand broadcast inputs (leading dimension 1)
+            lead = next((int(v.shape[0]) for v in list(args) + list(kwargs.values())
+                         if torch.is_tensor(v) and v.dim() >= 1), None)
+            runtime.set_folded_rows(lead)
+            try:
+                return self.model.forward(*args, **kwargs)
+            finally:
+                runtime.set_folded_rows(None)
         return self.model.forward(*args, **kwargs)
 
     @property

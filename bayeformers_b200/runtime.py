@@ -66,6 +66,17 @@ def mc_samples(S: int):
         _state.mc_samples = prev
 
 
+def set_folded_rows(rows: Optional[int]) -> None:
+    """Leading dimension (S*B) of the folded batch of the forward in flight; set by `bnn.Model.forward`
+    so that layers fed a broadcast input of leading dimension 1 (HuggingFace passes `position_ids` of
+    shape [1, T] to its position embedding) can expand it to the folded batch."""
+    _state.folded_rows = rows
+
+
+def get_folded_rows() -> Optional[int]:
+    return getattr(_state, "folded_rows", None)
+
+
 def set_kl_grad(flag: bool) -> None:
     _global["kl_grad"] = bool(flag)
 
