@@ -382,19 +382,22 @@ __global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
             ng[c].load(gy + (row0 + m) * H + c * 256 + lane * 8);
         }
     }
+    float mean_n = 0.0f, rstd_n = 0.0f;  // the row statistics travel one iteration ahead as well
+    if (m < M) mean_n = __ldg(mean_in + row0 + m), rstd_n = __ldg(rstd_in + row0 + m);
     for (; m < M; m += m_step) {
         const int64_t row = row0 + m;
         Pack8<T> pz[C], pg[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) pz[c] = nz[c], pg[c] = ng[c];
+        const float mean = mean_n, rstd = rstd_n;
         if (m + m_step < M) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 nz[c].load(z + (row + m_step) * H + c * 256 + lane * 8);
                 ng[c].load(gy + (row + m_step) * H + c * 256 + lane * 8);
             }
+            mean_n = __ldg(mean_in + row + m_step), rstd_n = __ldg(rstd_in + row + m_step);
         }
-        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
         float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -448,7 +451,10 @@ __global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
 // (12 warps x kStages x 2 rows of H elements, ~100+ KB per SM) and 12 warps fit the register file
 template <typename T, int C>
 struct StagedCfg {
-    static constexpr int kThreads = C <= 3 ? 384 : 256;  // C = 4: 96 accumulators need > 168 registers, i.e. <= 2 warps per SM sub-partition
+    // C >= 3: 72+ accumulators, two packed rows and the prefetched row statistics need > 168 registers, i.e. at most
+    // 2 warps per SM sub-partition (with 12 warps ptxas spilled the prefetched mean / rstd right behind their loads,
+    // which turned the prefetch back into a stall: ncu source page, 16 % of the samples on that STL)
+    static constexpr int kThreads = C <= 2 ? 384 : 256;
     static constexpr int kWarps = kThreads / 32;
     static constexpr int kRowBytes = 256 * C * (int)sizeof(T);
     static constexpr int kStages = sizeof(T) == 2 ? 4 : 2;
@@ -508,11 +514,13 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
     }
     __syncwarp();
 
-    float acc_g[C][8], acc_b[C][8], acc_h[C][8];  // sum gy*xhat, sum gy, sum dh
+    // column accumulators as packed fp32 pairs (FFMA2 / FADD2: two IEEE fp32 operations per issued instruction --
+    // this kernel is issue-bound, not HBM-bound, see profiles/): sum gy*xhat, sum gy, sum dh
+    bf_f2 acc_g2[C][4], acc_b2[C][4], acc_h2[C][4];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = acc_h[c][j] = 0.0f;
+        for (int j = 0; j < 4; ++j) acc_g2[c][j] = acc_b2[c][j] = acc_h2[c][j] = bf_splat2(0.0f);
 
     const int64_t m_step = (int64_t)nblk * kWarps;
     const int64_t m_first = (int64_t)blockIdx.x * kWarps + warp;
@@ -529,8 +537,12 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
     }
     int st = 0;
     uint32_t parity = 0;
+    float mean_n = 0.0f, rstd_n = 0.0f;  // row statistics: plain loads issued one iteration ahead
+    if (m_first < M) mean_n = __ldg(mean_in + row0 + m_first), rstd_n = __ldg(rstd_in + row0 + m_first);
     for (int64_t m = m_first; m < M; m += m_step) {
         const int64_t row = row0 + m;
+        const float mean = mean_n, rstd = rstd_n;
+        if (m + m_step < M) mean_n = __ldg(mean_in + row + m_step), rstd_n = __ldg(rstd_in + row + m_step);
         rl_mbar_wait(bars + st * 8, parity);
         const char* zr = ring + (st * 2) * kRowBytes;
         const char* gr = zr + kRowBytes;
@@ -551,8 +563,10 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
         }
         if (++st == kStages) st = 0, parity ^= 1u;
 
-        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-        float s1 = 0.0f, s2 = 0.0f;  // sum a, sum a*xhat with a = gy*gamma
+        // pass 1: xhat and a = gy*gamma stay in registers (packed), row sums of a and a*xhat
+        const bf_f2 nmean2 = bf_splat2(-mean), rstd2 = bf_splat2(rstd);
+        bf_f2 xh2[C][4], a2[C][4];
+        bf_f2 s1_2 = bf_splat2(0.0f), s2_2 = bf_splat2(0.0f);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             float zv[8], gv[8], gm[8];
@@ -560,39 +574,55 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
             pg[c].get(gv);
             ld8f(g + c * 256 + lane * 8, gm);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (zv[j] - mean) * rstd;
-                const float a = gv[j] * gm[j];
-                s1 += a;
-                s2 = fmaf(a, xh, s2);
-                acc_g[c][j] = fmaf(gv[j], xh, acc_g[c][j]);
-                acc_b[c][j] += gv[j];
+            for (int j = 0; j < 4; ++j) {
+                const bf_f2 g2 = bf_pack2(gv[2 * j], gv[2 * j + 1]);
+                xh2[c][j] = bf_mul2(bf_add2(bf_pack2(zv[2 * j], zv[2 * j + 1]), nmean2), rstd2);  // (z - mean) * rstd
+                a2[c][j] = bf_mul2(g2, bf_pack2(gm[2 * j], gm[2 * j + 1]));
+                s1_2 = bf_add2(s1_2, a2[c][j]);
+                s2_2 = bf_fma2(a2[c][j], xh2[c][j], s2_2);
+                acc_g2[c][j] = bf_fma2(g2, xh2[c][j], acc_g2[c][j]);
+                acc_b2[c][j] = bf_add2(acc_b2[c][j], g2);
             }
         }
-        const float c1 = bf_warp_sum(s1) * (1.0f / H), c2 = bf_warp_sum(s2) * (1.0f / H);
+        float s1a, s1b, s2a, s2b;
+        bf_unpack2(s1_2, s1a, s1b);
+        bf_unpack2(s2_2, s2a, s2b);
+        const float c1 = bf_warp_sum(s1a + s1b) * (1.0f / H), c2 = bf_warp_sum(s2a + s2b) * (1.0f / H);
+        // pass 2: dz = rstd * (a - c1 - xhat*c2), dh = dz * keep / (1 - p)
+        const bf_f2 nc1_2 = bf_splat2(-c1), nc2_2 = bf_splat2(-c2);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float zv[8], gv[8], gm[8], o[8];
-            pz[c].get(zv);
-            pg[c].get(gv);
-            ld8f(g + c * 256 + lane * 8, gm);
+            float o[8];
+            bf_f2 o2[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (zv[j] - mean) * rstd;
-                o[j] = rstd * (gv[j] * gm[j] - c1 - xh * c2);
+            for (int j = 0; j < 4; ++j) {
+                o2[j] = bf_mul2(bf_fma2(xh2[c][j], nc2_2, bf_add2(a2[c][j], nc1_2)), rstd2);
+                bf_unpack2(o2[j], o[2 * j], o[2 * j + 1]);
             }
             Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
             if (kDrop) {
                 float mk[8];
                 drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] *= mk[j];
+                for (int j = 0; j < 4; ++j) {
+                    o2[j] = bf_mul2(o2[j], bf_pack2(mk[2 * j], mk[2 * j + 1]));
+                    bf_unpack2(o2[j], o[2 * j], o[2 * j + 1]);
+                }
                 Pack8<T>::store(dh + row * H + c * 256 + lane * 8, o);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc_h[c][j] += o[j];
+            for (int j = 0; j < 4; ++j) acc_h2[c][j] = bf_add2(acc_h2[c][j], o2[j]);
         }
     }
+    float acc_g[C][8], acc_b[C][8], acc_h[C][8];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bf_unpack2(acc_g2[c][j], acc_g[c][2 * j], acc_g[c][2 * j + 1]);
+            bf_unpack2(acc_b2[c][j], acc_b[c][2 * j], acc_b[c][2 * j + 1]);
+            bf_unpack2(acc_h2[c][j], acc_h[c][2 * j], acc_h[c][2 * j + 1]);
+        }
     __syncthreads();  // all warps are done with their rings: the reduction scratch aliases them
     bwd_finish<C, Cfg::kThreads>(acc_g, acc_b, acc_h, reinterpret_cast<float*>(smem), dgamma, dbeta, dbias, partial,
                                  sample_part, counters, affine_stride, S);
