@@ -12,6 +12,8 @@
 // eps lives only in registers.  Reductions are deterministic: per-thread
 // sequential -> warp shuffle tree -> block tree -> fixed-order final pass by
 // the last block to finish (no float atomics).
+#include <cstdlib>
+
 #include "bf_common.cuh"
 
 namespace {
@@ -61,6 +63,9 @@ template <>
 __device__ __forceinline__ void store1<float>(float* p, float a) { *p = a; }
 template <>
 __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float a) { *p = __float2bfloat16_rn(a); }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // one element, one sample: returns w and adds the two log-prob terms
 template <int PRIOR>
@@ -284,6 +289,49 @@ __device__ __forceinline__ void derive_quad(const SampleKlParams& p, const RawQu
     }
 }
 
+// ---- packed fp32x2 form of the per-sample arithmetic (Gaussian prior or none) ---------------------------------
+// The kernels are issue-bound (profiles/): FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issued instruction,
+// and the sample-independent constants (-log sqrt(2 pi) - log sigma, prior ditto) are summed once per element instead
+// of once per element-sample.  Every product / sum keeps the reference's separate roundings (w = mu + eps*sigma is
+// mul.rn then add.rn), only the ORDER in which the log-prob terms are added differs (fp32 sums -> double at the end).
+struct QuadPacked {
+    bf_f2 mu[2], nmu[2], sigma[2], nqiv[2], npmu[2], npiv[2];
+};
+
+template <int PRIOR>
+__device__ __forceinline__ void pack_quad(const QuadShared& Q, QuadPacked& P, float& qc_sum, float& pc_sum) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        P.mu[h] = bf_pack2(Q.mu[2 * h], Q.mu[2 * h + 1]);
+        P.nmu[h] = bf_pack2(-Q.mu[2 * h], -Q.mu[2 * h + 1]);
+        P.sigma[h] = bf_pack2(Q.sigma[2 * h], Q.sigma[2 * h + 1]);
+        P.nqiv[h] = bf_pack2(-Q.qiv[2 * h], -Q.qiv[2 * h + 1]);
+        if (PRIOR == BF_PRIOR_GAUSSIAN) {
+            P.npmu[h] = bf_pack2(-Q.pmu[2 * h], -Q.pmu[2 * h + 1]);
+            P.npiv[h] = bf_pack2(-Q.piv[2 * h], -Q.piv[2 * h + 1]);
+        }
+    }
+    qc_sum += (Q.qc[0] + Q.qc[1]) + (Q.qc[2] + Q.qc[3]);
+    if (PRIOR == BF_PRIOR_GAUSSIAN) pc_sum += (Q.pc[0] + Q.pc[1]) + (Q.pc[2] + Q.pc[3]);
+}
+
+// one quad, one sample: w[4]; q2 / p2 accumulate -(w-mu)^2/(2 sigma^2) and -(w-mu_p)^2/(2 sigma_p^2) as lane pairs
+template <int PRIOR>
+__device__ __forceinline__ void quad_sample_packed(const QuadPacked& P, const float (&e)[4], bf_f2& q2, bf_f2& p2,
+                                                   float (&w)[4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const bf_f2 w2 = bf_add2(P.mu[h], bf_mul2(bf_pack2(e[2 * h], e[2 * h + 1]), P.sigma[h]));
+        const bf_f2 d2 = bf_add2(w2, P.nmu[h]);
+        q2 = bf_fma2(bf_mul2(d2, d2), P.nqiv[h], q2);
+        if (PRIOR == BF_PRIOR_GAUSSIAN) {
+            const bf_f2 dp2 = bf_add2(w2, P.npmu[h]);
+            p2 = bf_fma2(bf_mul2(dp2, dp2), P.npiv[h], p2);
+        }
+        bf_unpack2(w2, w[2 * h], w[2 * h + 1]);
+    }
+}
+
 template <int PRIOR, typename WT, int SC, bool HAS_EPS, int QPT>
 __global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const SampleKlParams p) {
     float q_acc[SC], p_acc[SC];
@@ -301,13 +349,21 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const Samp
     for (int u = 0; u < QPT; ++u)
         if (qb + u * stride < nquad) load_raw<PRIOR>(p, (qb + u * stride) << 2, raw[u]);
 
+    bf_f2 q2[SC], p2[SC];  // packed partial sums (Gaussian prior / none: see quad_sample_packed)
+    float qc_sum = 0.0f, pc_sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < SC; ++s) q2[s] = p2[s] = bf_splat2(0.0f);
     for (; qb < nquad; qb += stride * QPT) {
         QuadShared Q[QPT];
+        QuadPacked QP[QPT];
         bool live[QPT];
 #pragma unroll
         for (int u = 0; u < QPT; ++u) {
             live[u] = qb + u * stride < nquad;
-            if (live[u]) derive_quad<PRIOR>(p, raw[u], Q[u]);
+            if (live[u]) {
+                derive_quad<PRIOR>(p, raw[u], Q[u]);
+                if (PRIOR != BF_PRIOR_MIXTURE) pack_quad<PRIOR>(Q[u], QP[u], qc_sum, pc_sum);
+            }
         }
         // prefetch the next iteration's parameters: their latency hides behind this iteration's Philox work
 #pragma unroll
@@ -332,11 +388,27 @@ __global__ void __launch_bounds__(kThreads) sample_kl_fwd_fast_kernel(const Samp
                     e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
                 }
                 float w[4];
+                if (PRIOR != BF_PRIOR_MIXTURE) {
+                    quad_sample_packed<PRIOR>(QP[u], e, q2[s], p2[s], w);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    w[j] = element_terms<PRIOR>(Q[u].mu[j], Q[u].sigma[j], Q[u].qc[j], Q[u].qiv[j], e[j], Q[u].pmu[j],
-                                                Q[u].pc[j], Q[u].piv[j], p.mix, q_acc[s], p_acc[s]);
+                    for (int j = 0; j < 4; ++j)
+                        w[j] = element_terms<PRIOR>(Q[u].mu[j], Q[u].sigma[j], Q[u].qc[j], Q[u].qiv[j], e[j], Q[u].pmu[j],
+                                                    Q[u].pc[j], Q[u].piv[j], p.mix, q_acc[s], p_acc[s]);
+                }
                 if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * p.w_stride + i0, w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+    if (PRIOR != BF_PRIOR_MIXTURE) {
+#pragma unroll
+        for (int s = 0; s < SC; ++s) {
+            float a, b;
+            bf_unpack2(q2[s], a, b);
+            q_acc[s] += (a + b) + qc_sum;
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                bf_unpack2(p2[s], a, b);
+                p_acc[s] += (a + b) + pc_sum;
             }
         }
     }
@@ -510,6 +582,7 @@ struct MultiParams {
     uint32_t k0, k1, step;
     const uint32_t* step_ptr;
     char* w_base;  // when set, descs[].w_out are byte offsets from it
+    int prefetch;  // 0: none, 1: prefetch.global.L1 of the next iteration's parameters, 2: prefetch.global.L2
 };
 
 template <int PRIOR, typename WT, int SC>
@@ -535,15 +608,10 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
         p.mix.log_s1 = logf(d.sigma1), p.mix.log_s2 = logf(d.sigma2);
         p.mix.inv_var1 = 1.0f / v1, p.mix.inv_var2 = 1.0f / v2;
     }
-    const bool vec = d.vec != 0;
-    for (int64_t q = q_begin + threadIdx.x; q < q_end; q += kThreads) {
-        const int64_t i0 = q << 2;
-        QuadShared Q;
-        if (vec) {
-            RawQuad R;
-            load_raw<PRIOR>(p, i0, R);
-            derive_quad<PRIOR>(p, R, Q);
-        } else {
+    if (d.vec == 0) {
+        // ragged / unaligned tensors (biases of odd length, ...): scalar, bounds-checked
+        for (int64_t q = q_begin + threadIdx.x; q < q_end; q += kThreads) {
+            const int64_t i0 = q << 2;
             RawQuad R;
             float t[4][4];
 #pragma unroll
@@ -558,29 +626,88 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
             R.rho = make_float4(t[1][0], t[1][1], t[1][2], t[1][3]);
             R.pmu = make_float4(t[2][0], t[2][1], t[2][2], t[2][3]);
             R.prho = make_float4(t[3][0], t[3][1], t[3][2], t[3][3]);
+            QuadShared Q;
             derive_quad<PRIOR>(p, R, Q);
-        }
 #pragma unroll
-        for (int s = 0; s < SC; ++s) {
-            const int sg = mp.s0 + s;
-            const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, d.tensor_id, step + d.step, mp.k0, mp.k1);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-            float w[4];
-            if (vec) {
+            for (int s = 0; s < SC; ++s) {
+                const int sg = mp.s0 + s;
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, d.tensor_id, step + d.step, mp.k0, mp.k1);
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i0 + j < n) {
+                        const float w = element_terms<PRIOR>(Q.mu[j], Q.sigma[j], Q.qc[j], Q.qiv[j], e[j], Q.pmu[j], Q.pc[j],
+                                                             Q.piv[j], p.mix, q_acc[s], p_acc[s]);
+                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * d.w_stride + i0 + j, w);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // vector path: 16-byte loads / stores, full quads only
+    bf_f2 q2[SC], p2[SC];  // packed partial sums (see quad_sample_packed)
+    float qc_sum = 0.0f, pc_sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < SC; ++s) q2[s] = p2[s] = bf_splat2(0.0f);
+    for (int64_t q = q_begin + threadIdx.x; q < q_end; q += kThreads) {
+        const int64_t i0 = q << 2;
+        RawQuad R;
+        load_raw<PRIOR>(p, i0, R);
+        if (mp.prefetch && q + kThreads < q_end) {
+            // the next iteration's parameter lines: without this every iteration exposes the full DRAM latency at
+            // 16 resident warps per SM (ncu source page: 21 % of all stall samples on the first use of rho)
+            const int64_t in = (q + kThreads) << 2;
+            if (mp.prefetch == 1) {
+                prefetch_l1(d.mu + in), prefetch_l1(d.rho + in);
+                if (PRIOR == BF_PRIOR_GAUSSIAN) prefetch_l1(d.prior_mu + in);
+            } else {
+                prefetch_l2(d.mu + in), prefetch_l2(d.rho + in);
+                if (PRIOR == BF_PRIOR_GAUSSIAN) prefetch_l2(d.prior_mu + in);
+            }
+        }
+        if (PRIOR != BF_PRIOR_MIXTURE) {
+            QuadPacked QP;
+            {
+                QuadShared Q;
+                derive_quad<PRIOR>(p, R, Q);
+                pack_quad<PRIOR>(Q, QP, qc_sum, pc_sum);
+            }
+#pragma unroll
+            for (int s = 0; s < SC; ++s) {
+                const int sg = mp.s0 + s;
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, d.tensor_id, step + d.step, mp.k0, mp.k1);
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                float w[4];
+                quad_sample_packed<PRIOR>(QP, e, q2[s], p2[s], w);
+                if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * d.w_stride + i0, w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            QuadShared Q;
+            derive_quad<PRIOR>(p, R, Q);
+#pragma unroll
+            for (int s = 0; s < SC; ++s) {
+                const int sg = mp.s0 + s;
+                const float4 v = bf_eps_quad((uint32_t)q, (uint32_t)sg, d.tensor_id, step + d.step, mp.k0, mp.k1);
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                float w[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     w[j] = element_terms<PRIOR>(Q.mu[j], Q.sigma[j], Q.qc[j], Q.qiv[j], e[j], Q.pmu[j], Q.pc[j], Q.piv[j],
                                                 p.mix, q_acc[s], p_acc[s]);
                 if (w_out != nullptr) store4<WT>(w_out + (int64_t)sg * d.w_stride + i0, w[0], w[1], w[2], w[3]);
-            } else {
+            }
+        }
+    }
+    if (PRIOR != BF_PRIOR_MIXTURE) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (i0 + j < n) {
-                        w[j] = element_terms<PRIOR>(Q.mu[j], Q.sigma[j], Q.qc[j], Q.qiv[j], e[j], Q.pmu[j], Q.pc[j],
-                                                    Q.piv[j], p.mix, q_acc[s], p_acc[s]);
-                        if (w_out != nullptr) store1<WT>(w_out + (int64_t)sg * d.w_stride + i0 + j, w[j]);
-                    }
-                }
+        for (int s = 0; s < SC; ++s) {
+            float a, b;
+            bf_unpack2(q2[s], a, b);
+            q_acc[s] += (a + b) + qc_sum;
+            if (PRIOR == BF_PRIOR_GAUSSIAN) {
+                bf_unpack2(p2[s], a, b);
+                p_acc[s] += (a + b) + pc_sum;
             }
         }
     }
@@ -867,6 +994,13 @@ extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t
     mp.k0 = (uint32_t)(seed & 0xffffffffu), mp.k1 = (uint32_t)(seed >> 32), mp.step = step;
     mp.step_ptr = bf_step_counter();
     mp.w_base = reinterpret_cast<char*>(w_base);
+    {
+        static const int mode = [] {
+            const char* e = getenv("BF_SK_PREFETCH");  // A/B switch: 0 none, 1 L1 (default), 2 L2
+            return e ? atoi(e) : 1;
+        }();
+        mp.prefetch = mode;
+    }
     const int64_t cap = (int64_t)bf_num_sms() * kFwdBlocksPerSm;
     const int grid = (int)(n_chunks < cap ? n_chunks : cap);
     for (int s0 = 0; s0 < S;) {

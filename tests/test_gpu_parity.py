@@ -131,8 +131,10 @@ def test_sample_kl_forward_vs_oracle(n, S, prior_kind):
         lq, lp = float(O.gaussian_log_prob(w_o, mu, rho)), float(O.prior_log_prob(w_o, prior_o))
         assert abs(float(logq[s]) - lq) <= FP32_TOL * max(abs(lq), 1e-3)
         assert abs(float(logp[s]) - lp) <= FP32_TOL * max(abs(lp), 1e-3)
-    # log-probs are computed from the fp32 sample even when w is stored as bf16
-    assert torch.equal(logq, logq_b) and torch.equal(logp, logp_b)
+    # log-probs are computed from the fp32 sample even when w is stored as bf16 (a bf16-rounded sample would move them
+    # by ~4e-3 relative).  Not bitwise: for tiny n the two dtypes can take different kernels (16-byte alignment of the
+    # sample rows), whose fp32 partial sums are grouped differently.
+    assert torch.allclose(logq, logq_b, rtol=2e-6, atol=0) and torch.allclose(logp, logp_b, rtol=2e-6, atol=0)
 
 
 def test_sample_kl_edge_cases():
