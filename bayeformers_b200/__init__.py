@@ -65,7 +65,7 @@ def _is_exact_gelu(fn) -> bool:
 
 
 def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True,
-                     fuse_residual: bool = False) -> tnn.Module:
+                     fuse_residual: bool = False, grad_sinks: bool = False) -> tnn.Module:
     """Opt-in plumbing for the frequentist code AROUND the Bayesian layers of a host model.  In place; parameters,
     state_dict names and numerics (to rounding) are unchanged.
 
@@ -78,11 +78,20 @@ def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool 
     fuse_residual  HuggingFace output blocks `LayerNorm(dropout(dense(x)) + input_tensor)` (BertSelfOutput,
                BertOutput and their clones) whose `dense` is a Bayesian Linear: dropout + residual add + LayerNorm
                run as one kernel pass each way, the dropout mask comes from the Philox counter stream (never
-               stored), and the pass also yields `dense`'s bias gradient (nn/layers/fused.py)."""
+               stored), and the pass also yields `dense`'s bias gradient (nn/layers/fused.py).
+    grad_sinks (needs fuse_residual; process-wide switch) an input that feeds Bayesian Linear layers and the residual
+               of a fused output block gets its gradient accumulated in place: the block's backward writes its part
+               first, the Linear dgrad kernels add theirs into that buffer by TMA reduce-add, and autograd's separate
+               add passes disappear.  Valid when such an input has no further consumers (HF BERT); a tensor hook
+               raises otherwise (runtime.GradSink)."""
     from .nn.layers.fused import fuse_output_block_, is_output_block
     from .nn.layers.layernorm import HostLayerNorm
     from .nn.layers.linear import Linear
 
+    if grad_sinks and not fuse_residual:
+        raise ValueError("grad_sinks=True needs fuse_residual=True")
+    if grad_sinks:
+        runtime.enable_grad_sinks(True)  # process-wide; runtime.enable_grad_sinks(False) switches it off again
     if fuse_residual:
         for mod in list(model.modules()):
             if is_output_block(mod):

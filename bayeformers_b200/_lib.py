@@ -52,6 +52,8 @@ SIGNATURES = {
                                 c_int32, c_int32, c_void_p]),
     "bf_linear_dgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
                                   c_int32, c_void_p]),
+    "bf_linear_dgrad_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
+                                             c_int32, c_void_p]),
     "bf_linear_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
                                   c_void_p]),
     "bf_linear_fwd_gelu_supported": (c_int32, [c_int64, c_int64, c_int64, c_int64]),

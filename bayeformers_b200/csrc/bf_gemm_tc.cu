@@ -41,6 +41,7 @@ struct Params {
     int64_t S, I, J, R;  // batch, rows of D, cols of D, reduction length
     int i_tiles, j_tiles, k_steps;
     const float* bias;  // [S][J] or null
+    int accumulate;     // 1: the result tile is ADDED to D (TMA reduce-add) instead of stored
 };
 
 struct Item {
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
                 named_bar_sync<1, EPI_WARPS * 32>();
                 if (store_thread) {
-                    tma_store_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    if (p.accumulate) tma_reduce_add_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    else tma_store_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
                     tma_store_commit();
                 }
             }
@@ -289,7 +291,7 @@ static int launch_out(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
 
 int bf_linear_fwd_bf16_2cta(const void*, const void*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int32_t,
                             cudaStream_t);
-int bf_linear_dgrad_bf16_2cta(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, cudaStream_t);
+int bf_linear_dgrad_bf16_2cta(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, int, cudaStream_t);
 
 // CTA-pair (cta_group::2, 256 x 256 tiles) kernels of bf_gemm_tc2.cu when there are enough 256 x 256 tiles to give
 // every SM pair one (measured: 3-10 % faster than the single-CTA kernel from there on, slower below);
@@ -325,10 +327,10 @@ int bf_linear_fwd_bf16(const void* x, const void* w, const float* bias, void* y,
 
 // dx[s] = gy[s] w[s]
 int bf_linear_dgrad_bf16(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N, int64_t K,
-                         int32_t dx_dtype, cudaStream_t st) {
+                         int32_t dx_dtype, int accumulate, cudaStream_t st) {
     using namespace tc;
     BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "bf16 path needs K % 8 == 0 and N % 8 == 0");
-    if (use_cta_pairs(S, M, K)) return bf_linear_dgrad_bf16_2cta(gy, w, dx, S, M, N, K, dx_dtype, st);
+    if (use_cta_pairs(S, M, K)) return bf_linear_dgrad_bf16_2cta(gy, w, dx, S, M, N, K, dx_dtype, accumulate, st);
     CUtensorMap ma, mb, mo;
     int rc;
     if ((rc = encode_map(&ma, gy, S, M, N, BLOCK_M))) return rc;  // A: K-major over r = N
@@ -337,6 +339,7 @@ int bf_linear_dgrad_bf16(const void* gy, const void* w, void* dx, int64_t S, int
     Params p{};
     p.S = S, p.I = M, p.J = K, p.R = N;
     p.i_tiles = cdiv(M, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(N, BLOCK_K);
+    p.accumulate = accumulate;
     return launch_out<false, true>(ma, mb, mo, p, dx_dtype == BF_F32, st);
 }
 

@@ -39,6 +39,7 @@ struct Params {
     int64_t S, I, J, R;
     int i_pairs, j_tiles, k_steps;  // i_pairs: 256-row tile rows
     const float* bias;
+    int accumulate;  // 1: the result tile is ADDED to D (TMA reduce-add) instead of stored
 };
 
 struct Item {
@@ -246,7 +247,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 fence_proxy_async();
                 named_bar_sync<1, EPI_WARPS * 32>();
                 if (store_thread) {
-                    tma_store_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    if (p.accumulate) tma_reduce_add_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    else tma_store_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
                     tma_store_commit();
                 }
             }
@@ -307,7 +309,7 @@ int bf_linear_fwd_bf16_2cta(const void* x, const void* w, const float* bias, voi
 
 // dx[s] = gy[s] w[s]   (CTA-pair kernel)
 int bf_linear_dgrad_bf16_2cta(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N, int64_t K,
-                              int32_t dx_dtype, cudaStream_t st) {
+                              int32_t dx_dtype, int accumulate, cudaStream_t st) {
     using namespace tc2;
     CUtensorMap ma, mb, mo;
     int rc;
@@ -317,5 +319,6 @@ int bf_linear_dgrad_bf16_2cta(const void* gy, const void* w, void* dx, int64_t S
     Params p{};
     p.S = S, p.I = M, p.J = K, p.R = N;
     p.i_pairs = tc::cdiv(M, 2 * BLOCK_M), p.j_tiles = tc::cdiv(K, BLOCK_N), p.k_steps = tc::cdiv(N, tc::BLOCK_K);
+    p.accumulate = accumulate;
     return launch_out<false, true>(ma, mb, mo, p, dx_dtype == BF_F32, st);
 }

@@ -7,7 +7,7 @@ int bf_linear_fwd_f32(const float*, const float*, const float*, float*, int64_t,
 int bf_linear_dgrad_f32(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int bf_linear_wgrad_f32(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int bf_linear_fwd_bf16(const void*, const void*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, cudaStream_t);
-int bf_linear_dgrad_bf16(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, cudaStream_t);
+int bf_linear_dgrad_bf16(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int32_t, int, cudaStream_t);
 int bf_linear_wgrad_bf16(const void*, const void*, float*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 int64_t bf_wgrad_fused_workspace_bytes_impl(int64_t S, int64_t M, int64_t N, int64_t K, int with_mu);
 int bf_linear_wgrad_fused_bf16(const void*, const void*, int64_t, int64_t, int64_t, int64_t, const float*, const float*,
@@ -47,7 +47,16 @@ extern "C" int bf_linear_dgrad(const void* gy, const void* w, void* dx, int64_t 
         return 0;
     }
     BF_CHECK_ARG(dx_dtype == BF_F32 || dx_dtype == BF_BF16, "bad dx_dtype");
-    return bf_linear_dgrad_bf16(gy, w, dx, S, M, N, K, dx_dtype, st);
+    return bf_linear_dgrad_bf16(gy, w, dx, S, M, N, K, dx_dtype, 0, st);
+}
+
+extern "C" int bf_linear_dgrad_accumulate(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N,
+                                          int64_t K, int32_t dtype, int32_t dx_dtype, void* stream) {
+    BF_CHECK_ARG(gy && w && dx, "null pointer");
+    BF_CHECK_SHAPE();
+    BF_CHECK_ARG(dtype == BF_BF16, "accumulating dgrad exists for the bf16 tensor-core path only");
+    BF_CHECK_ARG(dx_dtype == BF_F32 || dx_dtype == BF_BF16, "bad dx_dtype");
+    return bf_linear_dgrad_bf16(gy, w, dx, S, M, N, K, dx_dtype, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t M, int64_t N, int64_t K,

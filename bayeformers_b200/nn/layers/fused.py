@@ -57,7 +57,8 @@ class FusedOutputMixin:
         self._bf_calls = getattr(self, "_bf_calls", 0) + 1
         spec = ops.DropoutSpec(p=p, seed=runtime.seed(), site_id=self._bf_site, step=self._bf_calls & 0xFFFFFFFF)
         self._last_dropout = spec  # identity of this forward's mask (tests, debugging)
-        return ops.ResidualLayerNormFn.apply(h, input_tensor, gamma, beta, S, ln.eps, spec, box)
+        sink = runtime.sink_for(input_tensor, create=False) if runtime.grad_sinks_enabled() else None
+        return ops.ResidualLayerNormFn.apply(h, input_tensor, gamma, beta, S, ln.eps, spec, box, sink)
 
 
 def is_output_block(mod: nn.Module) -> bool:

@@ -66,6 +66,8 @@ class Linear(BayesianLayer):
                                   b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec(),
                                   activation=self.activation)
         spec.bias_grad_box, self._bias_grad_box = self._bias_grad_box, None
+        if runtime.grad_sinks_enabled() and torch.is_grad_enabled() and input.requires_grad:
+            spec.sink = runtime.sink_for(input, create=True)
         self._last_streams = (spec.w_stream, spec.b_stream)  # identity of this forward's eps draw (tests, debugging)
         y, logq, logp = ops.BayesLinear.apply(
             input, self.weight.mu, self.weight.rho,

@@ -31,6 +31,7 @@ class Model(Module):
             raise NotImplementedError("Forward pass not implemented yet")
         from .. import runtime
         S = runtime.get_mc_samples()
+        runtime.reset_sinks()  # gradient sinks are per forward
         if self._presampler is not None:
             # extension: draw every Bayesian Linear's weights for this forward in one multi-tensor launch
             self._presampler.run(S)

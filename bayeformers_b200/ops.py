@@ -17,7 +17,7 @@ from ._lib import BF_BF16, BF_F32, BF_PRIOR_GAUSSIAN, BF_PRIOR_MIXTURE, BF_PRIOR
 _workspaces: Dict[Tuple, torch.Tensor] = {}
 
 # ---- instrumentation (bench.py): kernel-launch counter and optional per-call CUDA-event timing
-stats = {"launches": 0}
+stats = {"launches": 0, "dgrad_accumulated": 0}
 _timing = {"on": False, "records": []}
 
 
@@ -233,6 +233,7 @@ class LinearSpec:
     presampled: Optional[Tuple] = None  # (W[S,N,K], b[S,N] or None, logq[S], logp[S]) from presample.Presampler
     activation: Optional[str] = None    # None | "gelu": y = act(x w^T + b) with the activation fused where possible
     bias_grad_box: Optional[list] = None  # filled by ResidualLayerNormFn.backward with sum_m gy[s][m][:] ([S, N] fp32)
+    sink: Optional[object] = None         # runtime.GradSink of the input: add dx into its buffer instead of returning it
 
 
 def tc_eligible(N: int, K: int) -> bool:
@@ -349,13 +350,26 @@ class BayesLinear(torch.autograd.Function):
                 gyc = torch.ops.aten.gelu_backward(gyc, z.reshape(S, M, N).to(cdt)).contiguous()
             if ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
-                dx = torch.empty((S, M, K), dtype=dx_dtype, device=dev)
-                rc = _timed("gemm_dgrad_" + ("tc" if use_tc else "f32"), 2.0 * S * M * N * K, dev,
-                            lambda: lib.bf_linear_dgrad(_ptr(gyc), _ptr(W), _ptr(dx), S, M, N, K, _dt(cdt),
-                                                        _dt(dx_dtype), st))
-                _lib.check(rc, "bf_linear_dgrad")
-                stats["launches"] += 1
-                g_x = dx.view(x_shape).to(x_dtype)
+                sink = spec.sink
+                buf = None if sink is None else sink.buffer
+                if (buf is not None and use_tc and buf.dtype == dx_dtype == x_dtype and buf.is_contiguous()
+                        and buf.numel() == S * M * K and buf.device == dev):
+                    # the fused residual block already wrote its gradient of x there: add ours in place
+                    rc = _timed("gemm_dgrad_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_dgrad_accumulate(
+                        _ptr(gyc), _ptr(W), _ptr(buf), S, M, N, K, _dt(cdt), _dt(dx_dtype), st))
+                    _lib.check(rc, "bf_linear_dgrad_accumulate")
+                    stats["launches"] += 1
+                    stats["dgrad_accumulated"] += 1
+                    sink.used = True
+                    g_x = None
+                else:
+                    dx = torch.empty((S, M, K), dtype=dx_dtype, device=dev)
+                    rc = _timed("gemm_dgrad_" + ("tc" if use_tc else "f32"), 2.0 * S * M * N * K, dev,
+                                lambda: lib.bf_linear_dgrad(_ptr(gyc), _ptr(W), _ptr(dx), S, M, N, K, _dt(cdt),
+                                                            _dt(dx_dtype), st))
+                    _lib.check(rc, "bf_linear_dgrad")
+                    stats["launches"] += 1
+                    g_x = dx.view(x_shape).to(x_dtype)
             if has_bias and db is None and spec.bias_grad_box:
                 # the consumer of y (fused dropout + residual + LayerNorm backward) already reduced gy over rows
                 cand = spec.bias_grad_box.pop()
@@ -478,7 +492,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
     `bias_grad_box` (a list) receives sum_m dh[s][m][:] for the Linear that made h."""
 
     @staticmethod
-    def forward(ctx, h, r, gamma, beta, S: int, eps: float, drop: DropoutSpec, bias_grad_box):
+    def forward(ctx, h, r, gamma, beta, S: int, eps: float, drop: DropoutSpec, bias_grad_box, sink=None):
         _require_cuda(h, "input")
         lib = _lib.load()
         dev = h.device
@@ -505,14 +519,15 @@ class ResidualLayerNormFn(torch.autograd.Function):
         _lib.check(rc, "bf_resln_fwd")
         stats["launches"] += 1
         ctx.save_for_backward(z, g, mean, rstd)
-        ctx.meta = (S, M, H, stride, gamma.shape, gamma.dtype, None if beta is None else beta.dtype, drop, bias_grad_box)
+        ctx.meta = (S, M, H, stride, gamma.shape, gamma.dtype, None if beta is None else beta.dtype, drop, bias_grad_box,
+                    sink)
         return y.view(h.shape)
 
     @staticmethod
     def backward(ctx, gy):
         lib = _lib.load()
         z, g, mean, rstd = ctx.saved_tensors
-        S, M, H, stride, g_shape, g_dtype, b_dtype, drop, box = ctx.meta
+        S, M, H, stride, g_shape, g_dtype, b_dtype, drop, box, sink = ctx.meta
         dev = z.device
         gyc = gy.contiguous().to(z.dtype)
         dz = torch.empty_like(z)
@@ -532,11 +547,15 @@ class ResidualLayerNormFn(torch.autograd.Function):
         if box is not None:
             box.clear()
             box.append(dbias)
+        if dh is None and sink is not None:
+            dh = dz.clone()  # dropout off: dz would alias the gradient of h, which must not see the accumulations
         dzv = dz.view(gy.shape)
         dhv = dzv if dh is None else dh.view(gy.shape)
+        if sink is not None and ctx.needs_input_grad[1]:
+            sink.buffer, sink.used = dzv, False  # Linear layers fed by the same input add their dgrad into it
         dg = dgamma.view(g_shape).to(g_dtype) if ctx.needs_input_grad[2] else None
         db = dbeta.view(g_shape).to(b_dtype) if (dbeta is not None and ctx.needs_input_grad[3]) else None
-        return dhv, dzv, dg, db, None, None, None, None
+        return dhv, dzv, dg, db, None, None, None, None, None
 
 
 def dropout_mask(n: int, drop: DropoutSpec, device) -> torch.Tensor:

@@ -77,6 +77,57 @@ def get_folded_rows() -> Optional[int]:
     return getattr(_state, "folded_rows", None)
 
 
+# ---- gradient sinks (opt-in, accelerate_host_(grad_sinks=True)) ---------------------------------------------
+class GradSink:
+    """One per tensor x that feeds Bayesian Linear layers AND the residual input of a fused output block in the
+    same forward.  Backward: the fused block's kernel writes its gradient of x (dz) first and parks it here; the
+    Linear layers then ADD their dgrad results into that buffer in place (TMA reduce-add) and hand autograd no
+    gradient of their own, so the engine never runs its separate `grad + grad` passes for x."""
+    __slots__ = ("tensor", "buffer", "used")
+
+    def __init__(self, tensor: torch.Tensor) -> None:
+        self.tensor, self.buffer, self.used = tensor, None, False
+
+    def check(self, grad: torch.Tensor) -> None:
+        """Tensor hook on x: the gradient autograd finally delivers for x must be the buffer the Linear layers
+        accumulated into -- anything else means x had a consumer this scheme does not know (its contribution made
+        the engine build a new sum, and later in-place accumulations were lost)."""
+        buf, used = self.buffer, self.used
+        self.buffer, self.used, self.tensor = None, False, None
+        if used and (grad is None or buf is None or grad.data_ptr() != buf.data_ptr()):
+            raise RuntimeError("bayeformers_b200: gradient sinks are not valid for this model (an input shared by "
+                               "Bayesian Linear layers and a fused residual has further consumers); call "
+                               "accelerate_host_(..., grad_sinks=False)")
+
+
+_sinks_enabled = {"on": False}
+
+
+def enable_grad_sinks(flag: bool = True) -> None:
+    _sinks_enabled["on"] = bool(flag)
+
+
+def grad_sinks_enabled() -> bool:
+    return _sinks_enabled["on"]
+
+
+def reset_sinks() -> None:
+    _state.sinks = {}
+
+
+def sink_for(x: torch.Tensor, create: bool) -> Optional[GradSink]:
+    """The GradSink of tensor `x` in the forward in flight (keyed by identity; the sink keeps x alive, so ids are
+    not reused within one forward)."""
+    table = getattr(_state, "sinks", None)
+    if table is None:
+        table = _state.sinks = {}
+    sink = table.get(id(x))
+    if sink is None and create:
+        sink = table[id(x)] = GradSink(x)
+        x.register_hook(sink.check)
+    return sink
+
+
 def set_kl_grad(flag: bool) -> None:
     _global["kl_grad"] = bool(flag)
 

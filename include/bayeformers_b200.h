@@ -181,6 +181,12 @@ int bf_linear_dgrad(const void* gy, const void* w, void* dx, int64_t S, int64_t 
                     int32_t dtype, int32_t dx_dtype, void* stream);
 int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t M, int64_t N, int64_t K,
                     int32_t dtype, void* stream);
+/* dx[s] += gy[s] . w[s]: the result tiles are added to dx by TMA reduce-add (cp.reduce.async.bulk.tensor .add, in
+ * the element type of dx) instead of stored -- the gradient of an input that also feeds other consumers (the residual
+ * branch, the q / k / v projections of one attention block) is accumulated in place, which replaces autograd's
+ * separate add passes.  bf16 tensor-core path only (dtype == BF_BF16). */
+int bf_linear_dgrad_accumulate(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N, int64_t K,
+                               int32_t dtype, int32_t dx_dtype, void* stream);
 
 /* Extension: forward with the bias + GELU (exact, erf form) epilogue fused, for layers used as
  * y = gelu(F.linear(x, w, b)) (linear.py:104 followed by the host model's activation), and the matching

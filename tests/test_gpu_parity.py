@@ -895,6 +895,30 @@ def test_embedding_and_layernorm_against_composed_oracle(H):
     assert rel_err(bl.bias.mu.grad.cpu().numpy(), mu_b.grad.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("S,M,N,K", [(1, 128, 256, 64), (2, 256, 512, 264), (3, 200, 136, 768), (4, 2560, 768, 768)])
+def test_dgrad_accumulate_adds_in_place(S, M, N, K):
+    """bf_linear_dgrad_accumulate: dx += gy . w through the TMA reduce-add epilogue (single-CTA and CTA-pair kernels,
+    ragged tiles included) against float64."""
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(S * 100 + M + N + K)
+    gy = torch.randn(S, M, N, generator=gen).bfloat16().to(DEV)
+    w = (torch.randn(S, N, K, generator=gen) * 0.05).bfloat16().to(DEV)
+    dx0 = torch.randn(S, M, K, generator=gen).bfloat16().to(DEV)
+    dx = dx0.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.bf_linear_dgrad_accumulate(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st)
+    _lib.check(rc, "bf_linear_dgrad_accumulate")
+    want = dx0.double() + torch.einsum("smn,snk->smk", gy.double(), w.double())
+    assert rel_err(dx.double().cpu().numpy(), want.cpu().numpy()) < BF16_TOL
+    # twice more: still exactly one add per element and launch (no split of the reduction across CTAs)
+    for _ in range(2):
+        _lib.check(lib.bf_linear_dgrad_accumulate(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st), "acc")
+    want3 = dx0.double() + 3 * torch.einsum("smn,snk->smk", gy.double(), w.double())
+    assert rel_err(dx.double().cpu().numpy(), want3.cpu().numpy()) < 2 * BF16_TOL
+    # fp32 mode is refused (the parity path keeps autograd's own accumulation)
+    assert lib.bf_linear_dgrad_accumulate(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_F32, BF_F32, st) != 0
+
+
 # ------------------------------------------------------------------ fused dropout + residual + LayerNorm (output blocks)
 def test_dropout_mask_matches_oracle_contract():
     for n, p, seed, step, site in [(8 * 1000, 0.1, 1234, 0, 1), (4099, 0.5, 0xDEADBEEFCAFEF00D, 9, 77), (5, 0.25, 3, 2, 1)]:
@@ -957,8 +981,9 @@ def test_resln_vs_torch_fp64(S, M, H, shared, dtype, p):
     assert torch.equal(gd.grad, gd2.grad) and torch.equal(bd.grad, bd2.grad) and torch.equal(box[0], box2[0])
 
 
-@pytest.mark.parametrize("mode,bayes_ln", [("fp32", False), ("bf16", False), ("fp32", True)])
-def test_accelerate_host_fuses_hf_output_blocks(mode, bayes_ln):
+@pytest.mark.parametrize("mode,bayes_ln,sinks", [("fp32", False, False), ("bf16", False, False), ("fp32", True, False),
+                                                 ("bf16", False, True), ("bf16", True, True)])
+def test_accelerate_host_fuses_hf_output_blocks(mode, bayes_ln, sinks):
     """accelerate_host_(fuse_residual=True) on HF BERT layers: with dropout off the fused model reproduces the
     unfused one (logits, log-probs and every gradient incl. the bias gradients handed over by the fused
     backward); with dropout on, the block equals its manual composition under the regenerated mask."""
@@ -969,13 +994,16 @@ def test_accelerate_host_fuses_hf_output_blocks(mode, bayes_ln):
     layers = bnn.TORCH2BAYE_ALL if bayes_ln else None
     base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=False, gemm_dtype=mode, kl_grad=True,
                           layers=layers)
-    fused = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, fuse_residual=True)
+    fused = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, fuse_residual=True,
+                                grad_sinks=sinks)
     blocks = [m for m in fused.modules() if type(m).__name__.startswith("Fused")]
     assert len(blocks) == 4 and list(fused.state_dict()) == list(base.state_dict())
     S, B, Tn = 2, 4, 16
     ids = torch.randint(0, cfg.vocab_size, (B, Tn), generator=torch.Generator().manual_seed(3)).to(DEV)
     outs = []
+    acc0 = ops.stats["dgrad_accumulated"]
     for m in (base, fused):
+        bf.runtime.enable_grad_sinks(sinks and m is fused)
         m = m.to(DEV).eval()  # eval(): dropout off, so both models compute the same function
         if mode == "bf16":
             bf.cast_frequentist_(m, torch.bfloat16)
@@ -989,6 +1017,10 @@ def test_accelerate_host_fuses_hf_output_blocks(mode, bayes_ln):
         lp, lq = m.log_prior(), m.log_variational_posterior()
         (logits.square().sum() + 1e-3 * (lq - lp).sum()).backward()
         outs.append((logits.detach(), lp.detach(), lq.detach(), {n: p.grad for n, p in m.named_parameters() if p.grad is not None}))
+    bf.runtime.enable_grad_sinks(False)
+    # with sinks, every layer input that feeds Linear layers and a fused residual took the in-place path:
+    # 2 layers x (q, k, v, intermediate.dense) accumulating dgrads
+    assert ops.stats["dgrad_accumulated"] - acc0 == (8 if sinks else 0)
     tol = FP32_TOL * 10 if mode == "fp32" else BF16_TOL  # fp32: different (still fp32) summation orders through 2 layers
     assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < tol
     assert rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < FP32_TOL
