@@ -7,7 +7,7 @@ import csv
 import sys
 
 OURS = ("bayes_gemm", "bayes_wgrad", "wgrad_reduce", "sample_kl", "layernorm_", "resln_", "bias_grad", "gemm_f32_kernel",
-        "clip_adamw", "grad_sumsq", "gelu_bwd_bias_grad", "philox_normal", "dropout_mask")
+        "clip_adamw", "grad_sumsq", "gelu_bwd_bias_grad", "philox_normal", "dropout_mask_kernel")
 CONTRACTIONS = ("bayes_gemm", "bayes_wgrad_kernel")
 
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
