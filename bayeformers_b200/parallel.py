@@ -111,6 +111,47 @@ class GradSync:
         self._hooks = []
 
 
+# ---- sample sharding (second mode: S >= G, e.g. S = 8 or 16 over 8 GPUs) -------------------
+def shard_samples(S: int, group=None) -> int:
+    """Give this rank its share of the S Monte-Carlo samples: returns S // world and re-keys the eps stream with a
+    rank-distinct seed derived from rank 0's, so the ranks draw independent weight samples (under batch sharding
+    they must draw IDENTICAL ones -- do not mix the two modes in one step).  Every rank then runs the full batch
+    with `mc_samples(S // world)`; gradients are SUMMED (`GradSync(..., average=False)`), the ELBO scalars go through
+    `all_reduce_elbo`, and the per-sample logits through `mean_over_samples` before the loss."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if S % world != 0:
+        raise ValueError(f"mc_samples={S} is not a multiple of the world size {world}")
+    if world > 1:
+        base = broadcast_seed(0, group)
+        rank = dist.get_rank(group)
+        runtime.manual_seed((base + 0x9E3779B97F4A7C15 * (rank + 1)) & 0xFFFFFFFFFFFFFFFF)
+    return S // world
+
+
+class _MeanOverRanks(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, local_sum: torch.Tensor, total: int, group):
+        out = local_sum.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        ctx.total = total
+        return out / total
+
+    @staticmethod
+    def backward(ctx, g):
+        # the loss is replicated on every rank and a function of the same mean: each rank only needs the
+        # derivative with respect to ITS samples, g / S -- no communication in backward
+        return g / ctx.total, None, None
+
+
+def mean_over_samples(raw_local: torch.Tensor, S_total: int, group=None) -> torch.Tensor:
+    """raw_local [S_local, B, ...] -> mean over all S_total samples held by all ranks, differentiable.  The
+    reference's loss is the cross entropy of the MEAN over samples of the logits (examples/bert_glue.py:69,234), a
+    non-linear function of that mean, so the logits are averaged across ranks BEFORE the loss (S*B*C floats)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return raw_local.sum(0) / S_total
+    return _MeanOverRanks.apply(raw_local.sum(0), int(S_total), group)
+
+
 def all_reduce_elbo(log_q: torch.Tensor, log_p: torch.Tensor, group=None):
     """Sample-sharded runs only (each rank owns different MC samples): sum the
     per-rank [log q, log p] pair.  Under batch sharding the scalars are already

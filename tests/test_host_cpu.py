@@ -249,6 +249,40 @@ def test_accelerate_host_fuses_output_blocks():
         layer.output(torch.randn(2, 128), torch.randn(2, 64))
 
 
+def test_grad_sink_registry_and_guard():
+    """runtime.GradSink bookkeeping (no kernels): one sink per input tensor and forward, reset by bnn.Model.forward,
+    and the tensor hook that refuses topologies where in-place accumulation would lose a contribution."""
+    from bayeformers_b200 import runtime
+    runtime.reset_sinks()
+    x = torch.randn(4, 8, requires_grad=True) * 2  # non-leaf, like a layer input
+    assert runtime.sink_for(x, create=False) is None
+    s1 = runtime.sink_for(x, create=True)
+    assert runtime.sink_for(x, create=False) is s1 and runtime.sink_for(x.clone(), create=False) is None
+    # valid case: the gradient autograd delivers for x IS the buffer the Linear layers accumulated into
+    buf = torch.zeros(4, 8)
+    s1.buffer, s1.used = buf, True
+    s1.check(buf)  # no error; one-shot state is cleared
+    assert s1.buffer is None and s1.used is False and s1.tensor is None
+    # invalid case: some other consumer made the engine build a new sum after the accumulation
+    s1.buffer, s1.used = buf, True
+    with pytest.raises(RuntimeError, match="gradient sinks are not valid"):
+        s1.check(buf + 1)
+    # unused sinks never complain (inputs of layers that have no fused residual consumer)
+    s2 = runtime.sink_for(torch.randn(2, 2, requires_grad=True) + 0, create=True)
+    s2.check(torch.zeros(2, 2))
+    runtime.reset_sinks()
+    assert runtime.sink_for(x, create=False) is None
+    # the hook is wired: backward through x calls check (no buffer set -> silent)
+    runtime.enable_grad_sinks(False)
+    y = torch.randn(3, 3, requires_grad=True) * 1.0
+    s3 = runtime.sink_for(y, create=True)
+    y.sum().backward()
+    assert s3.tensor is None  # check() ran
+    with pytest.raises(ValueError, match="fuse_residual"):
+        bf.accelerate_host_(torch.nn.Sequential(torch.nn.Linear(2, 2)), fuse_residual=False, grad_sinks=True)
+    assert runtime.grad_sinks_enabled() is False
+
+
 def test_harness_fold_pick_and_predictive_stats():
     from bayeformers_b200 import harness
     x = torch.arange(6).view(2, 3)

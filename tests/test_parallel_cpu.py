@@ -69,3 +69,59 @@ def test_gradsync_single_process_is_noop():
     g = net.weight.grad.clone()
     sync.finish()
     assert torch.equal(g, net.weight.grad) and sync.world == 1
+
+
+def _worker_samples(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bayeformers_b200 as bf
+    from bayeformers_b200 import parallel, runtime
+
+    bf.manual_seed(77 + rank)
+    S = 4
+    s_local = parallel.shard_samples(S)
+    # stand-in for the per-sample logits of this rank's samples: a linear map with a shared parameter
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(3, 5))
+    x = torch.arange(2 * s_local * 5, dtype=torch.float32).view(s_local, 2, 5) * (rank + 1) / 10
+    raw = x @ w.t()                                   # [S_local, B=2, C=3]
+    mean = parallel.mean_over_samples(raw, S)         # identical on both ranks
+    loss = torch.nn.functional.cross_entropy(mean, torch.tensor([0, 2]))
+    loss.backward()
+    sync_grad = w.grad.clone()
+    dist.all_reduce(sync_grad, op=dist.ReduceOp.SUM)  # what GradSync(average=False) does
+    ret[rank] = dict(s_local=s_local, seed=runtime.seed(), mean=mean.detach().clone(), loss=float(loss),
+                     grad=sync_grad, raw=raw.detach().clone(), x=x)
+    dist.destroy_process_group()
+
+
+def test_sample_sharding_world2_gloo():
+    """shard_samples / mean_over_samples: two ranks holding 2 of 4 samples each reproduce the single-process
+    loss and gradient of CE(mean over the 4 samples of the logits) after a SUM all-reduce of the gradients."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_samples, args=(world, port, ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+        assert r0["s_local"] == r1["s_local"] == 2
+        assert r0["seed"] != r1["seed"]  # independent eps streams per rank
+        assert torch.equal(r0["mean"], r1["mean"]) and r0["loss"] == r1["loss"]
+        assert torch.equal(r0["grad"], r1["grad"])
+        # single-process reference over all 4 samples
+        torch.manual_seed(0)
+        w = torch.nn.Parameter(torch.randn(3, 5))
+        raw = torch.cat([r0["x"], r1["x"]]) @ w.t()
+        loss = torch.nn.functional.cross_entropy(raw.mean(0), torch.tensor([0, 2]))
+        loss.backward()
+        assert abs(float(loss) - r0["loss"]) < 1e-6
+        assert torch.allclose(w.grad, r0["grad"], rtol=1e-5, atol=1e-7)
+
+
+def test_sample_sharding_single_process():
+    from bayeformers_b200 import parallel
+
+    assert parallel.shard_samples(8) == 8
+    raw = torch.randn(4, 2, 3)
+    assert torch.allclose(parallel.mean_over_samples(raw, 4), raw.mean(0))
