@@ -220,6 +220,13 @@ __device__ __forceinline__ float bf_mixture_logp(float w, const BfMixture& m) {
     const float w2 = w * w;
     const float n1 = -(w2 * m.inv_two_var1) - m.log_s1 - BF_LOG_SQRT_2PI;
     const float n2 = -(w2 * m.inv_two_var2) - m.log_s2 - BF_LOG_SQRT_2PI;
+    if (n1 > -80.0f) {
+        // common case (|w| < ~12 sigma1): component 1 is a normal fp32 number, MUFU ex2 / lg2 with an fma-corrected
+        // argument are accurate to ~1e-7 here.  Component 2 may flush to zero where expf would still return a
+        // denormal; it is then < 1e-30 of component 1 and changes nothing in fp32.
+        return bf_log_sum_term(m.pi * bf_exp(n1) + m.one_minus_pi * bf_exp(n2));
+    }
+    // far tail: libdevice, so the reference's denormal / -inf behaviour (quirk Q10) is reproduced exactly
     return logf(m.pi * expf(n1) + m.one_minus_pi * expf(n2));
 }
 
