@@ -642,6 +642,7 @@ inline int bwd_blocks(int64_t S, int64_t M) {
 // upper bound over both backward kernels (the workspace is sized with it): fewer warps per block -> more blocks
 inline int bwd_blocks_h(int64_t S, int64_t M, int64_t H) { return bwd_blocks_w(S, M, H / 256 <= 2 ? 12 : 8); }
 static_assert(StagedCfg<float, 4>::kSmemBytes <= 227 * 1024, "staged ring exceeds shared memory");
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t counters_bytes(int64_t S) { return (((S + 1) * 4 + 255) / 256) * 256; }
 
 DropSpec make_drop(float p, uint64_t seed, uint32_t step, uint32_t site) {
@@ -684,8 +685,7 @@ int launch_bwd_c(const void* gy, const void* z, const float* gamma, const float*
                  const DropSpec& d, cudaStream_t st) {
     constexpr int H = 256 * C;
     using SC = StagedCfg<T, C>;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(z)) & 15u) == 0;
-    const bool staged = aligned && use_staged_bwd();
+    const bool staged = use_staged_bwd();  // BF_RESLN_BWD=regs keeps the register-prefetch kernel selectable (A/B timing)
     const int nblk = staged ? bwd_blocks_w(S, M, SC::kWarps) : bwd_blocks<C>(S, M);
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + counters_bytes(S));
@@ -769,6 +769,8 @@ extern "C" int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const f
     BF_CHECK_ARG(affine_stride == 0 || affine_stride >= H, "bad affine stride");
     BF_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "p_drop must be in [0, 1)");
     BF_CHECK_ARG(site_id < 0x80000000u, "site_id must be < 2^31");
+    BF_CHECK_ARG(aligned16(h) && aligned16(r) && aligned16(z) && aligned16(y) && aligned16(gamma) && (!beta || aligned16(beta)),
+                 "h, r, z, y, gamma, beta must be 16-byte aligned (vector loads / stores)");
     if (M == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const DropSpec d = make_drop(p_drop, seed, step, site_id);
@@ -799,6 +801,9 @@ extern "C" int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const 
     BF_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "p_drop must be in [0, 1)");
     BF_CHECK_ARG(p_drop <= 0.0f || dh, "dh is required when p_drop > 0");
     BF_CHECK_ARG(site_id < 0x80000000u, "site_id must be < 2^31");
+    BF_CHECK_ARG(aligned16(gy) && aligned16(z) && aligned16(dz) && (!dh || aligned16(dh)) && aligned16(gamma) &&
+                     aligned16(dgamma) && (!dbeta || aligned16(dbeta)) && (!dbias || aligned16(dbias)) && aligned16(workspace),
+                 "gy, z, dz, dh, gamma, dgamma, dbeta, dbias, workspace must be 16-byte aligned (vector / bulk copies)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const DropSpec d = make_drop(p_drop, seed, step, site_id);
     if (dtype == BF_BF16) {

@@ -80,6 +80,13 @@ def _dt(t: torch.dtype) -> int:
     raise TypeError(f"unsupported dtype {t}")
 
 
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Dense tensor whose storage offset breaks 16-byte alignment (a slice of a larger buffer) -> private copy:
+    the row kernels use 16-byte vector and bulk copies."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -433,9 +440,9 @@ class LayerNormFn(torch.autograd.Function):
         if rows % S != 0:
             raise ValueError(f"{rows} rows are not a multiple of mc_samples={S}")
         M = rows // S
-        xc = x.detach().contiguous()
-        g = gamma.detach().to(torch.float32).contiguous()
-        b = None if beta is None else beta.detach().to(torch.float32).contiguous()
+        xc = _aligned(x.detach())
+        g = _aligned(gamma.detach().to(torch.float32))
+        b = None if beta is None else _aligned(beta.detach().to(torch.float32))
         stride = H if g.dim() == 2 and g.shape[0] == S and S > 1 else 0
         if g.numel() != (S * H if stride else H):
             raise ValueError(f"affine of shape {tuple(gamma.shape)} does not match S={S}, H={H}")
@@ -458,7 +465,7 @@ class LayerNormFn(torch.autograd.Function):
         xc, g, mean, rstd = ctx.saved_tensors
         S, M, H, stride, g_shape, g_dtype, b_dtype = ctx.meta
         dev = xc.device
-        gyc = gy.contiguous().to(xc.dtype)
+        gyc = _aligned(gy.to(xc.dtype))
         dx = torch.empty_like(xc)
         Sa = S if stride else 1  # a shared affine is one "sample" spanning all rows
         dgamma = torch.empty((Sa, H), dtype=torch.float32, device=dev)
@@ -503,9 +510,9 @@ class ResidualLayerNormFn(torch.autograd.Function):
         if rows % S != 0:
             raise ValueError(f"{rows} rows are not a multiple of mc_samples={S}")
         M = rows // S
-        hc, rc_ = h.detach().contiguous(), r.detach().contiguous()
-        g = gamma.detach().to(torch.float32).contiguous()
-        b = None if beta is None else beta.detach().to(torch.float32).contiguous()
+        hc, rc_ = _aligned(h.detach()), _aligned(r.detach())
+        g = _aligned(gamma.detach().to(torch.float32))
+        b = None if beta is None else _aligned(beta.detach().to(torch.float32))
         stride = H if g.dim() == 2 and g.shape[0] == S and S > 1 else 0
         if g.numel() != (S * H if stride else H):
             raise ValueError(f"affine of shape {tuple(gamma.shape)} does not match S={S}, H={H}")
@@ -529,7 +536,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
         z, g, mean, rstd = ctx.saved_tensors
         S, M, H, stride, g_shape, g_dtype, b_dtype, drop, box, sink = ctx.meta
         dev = z.device
-        gyc = gy.contiguous().to(z.dtype)
+        gyc = _aligned(gy.to(z.dtype))
         dz = torch.empty_like(z)
         dh = torch.empty_like(z) if drop.p > 0 else None
         Sa = S if stride else 1

@@ -415,8 +415,8 @@ def run_ours(args):
                                "lighter kernels and can clock higher, so frac may slightly exceed 1)",
                 # dram__bytes_read+write of the profiled FFN-shape fwd launch (S=4, M=4096, N=3072, K=768; algorithmic
                 # operand+result bytes 145 MB, most of the bf16 result still in L2 at kernel end):
-                # profiles/r01b_ncu_full_kernels_cta_pairs.md row 5
-                "traffic": 92.0e6, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
+                # profiles/r01e_ncu_full_kernels_final.md row 3 (44.1 + 48.7 MB)
+                "traffic": 92.8e6, "launches_per_step": g_calls / kern_steps, "avg_launch_ms": g_ms / max(g_calls, 1),
                 "share_of_step": g_ms / kern_steps / ms,
                 "timing": "CUDA events around every launch on the launching stream" +
                           (", taken in eager executions of the same step after the timed graph replays" if use_graph else

@@ -1082,3 +1082,29 @@ def test_full_size_properties_config2():
     # sample statistics of the standardised draw
     z = ((w[0].double() - mu.double()) / sig)
     assert abs(float(z.mean())) < 5 / np.sqrt(n) and abs(float(z.var()) - 1) < 5 * np.sqrt(2 / n)
+
+
+def test_row_kernels_take_misaligned_views():
+    """A dense view whose storage offset breaks 16-byte alignment (slice of a flat buffer) is copied by the binding
+    instead of reaching the vector / bulk-copy kernels; the C ABI itself refuses such pointers."""
+    H, rows = 256, 64
+    flat = torch.randn(rows * H + 8, device=DEV).bfloat16()
+    h = flat[1:1 + rows * H].view(rows, H)           # 2-byte offset
+    assert h.data_ptr() % 16 != 0 and h.is_contiguous()
+    r = torch.randn(rows, H, device=DEV).bfloat16().requires_grad_()
+    g, b = torch.ones(H, device=DEV, requires_grad=True), torch.zeros(H, device=DEV, requires_grad=True)
+    y = ops.ResidualLayerNormFn.apply(h, r, g, b, 1, 1e-5, ops.DropoutSpec(), None)
+    want = torch.nn.functional.layer_norm((h.float() + r.float()), (H,), g, b, 1e-5)
+    assert rel_err(y.float().detach().cpu().numpy(), want.detach().cpu().numpy()) < BF16_TOL
+    gy = torch.randn(rows * H + 8, device=DEV).bfloat16()[1:1 + rows * H].view(rows, H)
+    y.backward(gy)
+    assert r.grad is not None and torch.isfinite(r.grad.float()).all()
+    y2 = ops.LayerNormFn.apply(h, g, b, 1, 1e-5)
+    assert rel_err(y2.float().detach().cpu().numpy(),
+                   torch.nn.functional.layer_norm(h.float(), (H,), g, b, 1e-5).detach().cpu().numpy()) < BF16_TOL
+    lib = _lib.load()
+    z = torch.empty(rows, H, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    rc = lib.bf_resln_fwd(h.data_ptr(), r.data_ptr(), BF_BF16, g.data_ptr(), b.data_ptr(), 0, 1, rows, H, 1e-5, 0.0, 1, 0, 1,
+                          z.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"16-byte aligned" in lib.bf_last_error()
