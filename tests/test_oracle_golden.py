@@ -161,6 +161,12 @@ def test_dropout_mask_contract():
     assert np.array_equal(P.dropout_keep_mask(1001, 0.1, 11, 2, 5), m[:1001])  # prefix property
     assert not np.array_equal(P.dropout_keep_mask(4096, 0.1, 11, 3, 5), m[:4096])  # next step: new mask
     assert P.dropout_keep_mask(100, 0.0, 1, 1, 1).all()
+    # known answers (the CUDA kernels reproduce the oracle bit for bit on the B200: tests/test_gpu_parity.py); pinned
+    # here so the mask contract cannot drift without a test noticing
+    kat = {(0.1, 0xDEADBEEFCAFEF00D, 9, 77): "1111111001111111011111111111011111111111011110111111101111101011",
+           (0.5, 1234, 0, 1): "1111010010110101111111001100111100100001110011001000011110101011"}
+    for (p_, seed, step, site), bits in kat.items():
+        assert "".join(map(str, P.dropout_keep_mask(64, p_, seed, step, site))) == bits
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/bayeformers"), reason="live reference only in the build container")
