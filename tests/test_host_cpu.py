@@ -321,3 +321,32 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/bayeformers_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
     assert _lib.load().bf_abi_version() == 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/bayeformers"), reason="live reference only in the build container")
+@pytest.mark.parametrize("kw", [dict(delta=0.05, freeze=True), dict(delta=0.1, freeze=False), dict()])
+def test_reference_checkpoint_loads_strictly_and_back(kw):
+    """Drop-in checkpoint compatibility: a state_dict saved by the unmodified reference
+    (examples/bert_glue.py:303-309 saves `b_model.state_dict()`) loads into this package's model with strict=True and
+    vice versa -- same keys, same shapes, same values after the round trip."""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from bayeformers import to_bayesian as ref_to_bayesian
+    finally:
+        sys.path.remove("/root/reference")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(10, 12), torch.nn.Tanh(), torch.nn.Linear(12, 3, bias=False))
+    torch.manual_seed(5)
+    ref = ref_to_bayesian(net, **kw)
+    torch.manual_seed(6)  # different init draws on purpose: loading must overwrite them
+    ours = bf.to_bayesian(net, **kw)
+    ref_sd = ref.state_dict()
+    assert list(ref_sd) == list(ours.state_dict())
+    ours.load_state_dict(ref_sd, strict=True)
+    for k, v in ours.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    back = ref_to_bayesian(net, **kw)
+    back.load_state_dict(ours.state_dict(), strict=True)
+    for k, v in back.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
