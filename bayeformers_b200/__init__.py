@@ -22,12 +22,13 @@ from .nn.parameters.gaussian import DEFAULT_SCALED_GAUSSIAN_MIXTURE
 from .nn.parameters.initializations import DEFAULT_UNIFORM, Initialization
 from .harness import predictive_stats, sample_bayesian
 from .presample import enable_presample
-from .runtime import (advance_step, disable_device_step, enable_device_step, hf_capture_compat, manual_seed,
-                      mc_samples, set_gemm_dtype, set_kl_grad)
+from .runtime import (advance_step, disable_device_step, enable_device_step, hf_capture_compat, load_rng_state,
+                      manual_seed, mc_samples, rng_state, set_gemm_dtype, set_kl_grad)
 
 __all__ = ["to_bayesian", "cast_frequentist_", "accelerate_host_", "enable_presample", "sample_bayesian",
            "predictive_stats", "nn", "Model", "manual_seed", "mc_samples", "set_gemm_dtype",
-           "set_kl_grad", "enable_device_step", "disable_device_step", "advance_step", "hf_capture_compat"]
+           "set_kl_grad", "enable_device_step", "disable_device_step", "advance_step", "hf_capture_compat", "rng_state",
+           "load_rng_state"]
 
 
 def cast_frequentist_(model: tnn.Module, dtype: torch.dtype) -> tnn.Module:

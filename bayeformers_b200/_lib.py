@@ -13,8 +13,10 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_vo
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libbayeformers_b200.so")
 
+ABI_VERSION = 2
 BF_F32, BF_BF16 = 0, 1
 BF_PRIOR_MIXTURE, BF_PRIOR_GAUSSIAN, BF_PRIOR_NONE = 0, 1, 2
+BF_OPT_GEMM_2CTA, BF_OPT_WGRAD_2CTA, BF_OPT_RESLN_BWD_STAGED, BF_OPT_SK_PREFETCH = 0, 1, 2, 3
 
 class BfTensorDesc(ctypes.Structure):
     """`bf_tensor_desc` of include/bayeformers_b200.h (multi-tensor sample+KL)."""
@@ -27,7 +29,7 @@ class BfTensorDesc(ctypes.Structure):
 class BfOptDesc(ctypes.Structure):
     """`bf_opt_desc` of include/bayeformers_b200.h (fused clip + AdamW)."""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
-                ("n", c_int64), ("dtype", c_int32), ("vec", c_int32)]
+                ("n", c_int64), ("dtype", c_int32), ("vec", c_int32), ("master", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/bayeformers_b200.h one to one
@@ -36,6 +38,8 @@ SIGNATURES = {
     "bf_last_error": (c_char_p, []),
     "bf_device_is_sm100": (c_int32, []),
     "bf_set_step_counter": (c_int32, [c_void_p]),
+    "bf_set_option": (c_int32, [c_int32, c_int32]),
+    "bf_get_option": (c_int32, [c_int32]),
     "bf_philox_normal": (c_int32, [c_void_p, c_int64, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p]),
     "bf_sample_kl_workspace_bytes": (c_int64, [c_int64, c_int32]),
     "bf_sample_kl_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
@@ -79,6 +83,13 @@ SIGNATURES = {
     "bf_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_bias_grad": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "bf_embedding_supported": (c_int32, [c_int64]),
+    "bf_embedding_fwd": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_uint64, c_uint32,
+                                   c_uint32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "bf_embedding_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "bf_embedding_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                   c_int64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
     "bf_resln_supported": (c_int32, [c_int64]),
     "bf_resln_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -112,8 +123,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.bf_abi_version() != 1:
-        raise NativeLibraryError(f"ABI version mismatch: library {lib.bf_abi_version()} vs binding 1")
+    if lib.bf_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.bf_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -44,6 +44,8 @@ void bf_set_error(const std::string& msg);
 int bf_num_sms();
 // device-resident step counter (CUDA-graph replays must not redraw the same eps): see bf_set_step_counter
 const uint32_t* bf_step_counter();
+// tuning switch `id` (BF_OPT_*), see bf_set_option
+int bf_option(int id);
 
 // ---------------------------------------------------------------------------
 // constants

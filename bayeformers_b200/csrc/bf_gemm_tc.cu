@@ -295,12 +295,9 @@ int bf_linear_dgrad_bf16_2cta(const void*, const void*, void*, int64_t, int64_t,
 
 // CTA-pair (cta_group::2, 256 x 256 tiles) kernels of bf_gemm_tc2.cu when there are enough 256 x 256 tiles to give
 // every SM pair one (measured: 3-10 % faster than the single-CTA kernel from there on, slower below);
-// BF_GEMM_2CTA=0 / 2 in the environment forces the single-CTA / CTA-pair kernels (A/B measurements)
+// bf_set_option(BF_OPT_GEMM_2CTA, 0 / 2) forces the single-CTA / CTA-pair kernels (A/B measurements)
 static bool use_cta_pairs(int64_t S, int64_t rows, int64_t cols) {
-    static const int mode = [] {
-        const char* e = getenv("BF_GEMM_2CTA");
-        return e ? atoi(e) : 1;
-    }();
+    const int mode = bf_option(BF_OPT_GEMM_2CTA);
     if (mode == 0 || rows < 256) return false;
     if (mode == 2) return true;
     const int64_t pair_tiles = S * ((rows + 255) / 256) * ((cols + 255) / 256);

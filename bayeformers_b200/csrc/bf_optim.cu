@@ -106,6 +106,7 @@ __device__ __forceinline__ void adamw_chunk(const bf_opt_desc& d, int64_t lo, in
                                             float step_size, float inv_sqrt_bc2, const AdamScalars& a) {
     T* const p = reinterpret_cast<T*>(d.param);
     const T* const g = reinterpret_cast<const T*>(d.grad);
+    float* const master = d.master;  // fp32 master copy of a bf16 parameter (nullable): the update runs on it
     auto upd = [&](float pv, float gv, float& m, float& v) {
         gv *= clip;
         pv *= decay;                               // p.mul_(1 - lr*wd)
@@ -116,22 +117,24 @@ __device__ __forceinline__ void adamw_chunk(const bf_opt_desc& d, int64_t lo, in
     };
     if (d.vec) {
         for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi; i += 4 * kOptThreads) {
-            float4 pv = opt_ld4<T>(p + i);
+            float4 pv = master ? *reinterpret_cast<const float4*>(master + i) : opt_ld4<T>(p + i);
             const float4 gv = opt_ld4<T>(g + i);
             float4 m = *reinterpret_cast<const float4*>(d.exp_avg + i);
             float4 v = *reinterpret_cast<const float4*>(d.exp_avg_sq + i);
             pv.x = upd(pv.x, gv.x, m.x, v.x), pv.y = upd(pv.y, gv.y, m.y, v.y);
             pv.z = upd(pv.z, gv.z, m.z, v.z), pv.w = upd(pv.w, gv.w, m.w, v.w);
             opt_st4<T>(p + i, pv);
+            if (master) *reinterpret_cast<float4*>(master + i) = pv;
             *reinterpret_cast<float4*>(d.exp_avg + i) = m;
             *reinterpret_cast<float4*>(d.exp_avg_sq + i) = v;
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += kOptThreads) {
             float m = d.exp_avg[i], v = d.exp_avg_sq[i];
-            const float pn = upd(bf_ld_as_float(p + i), bf_ld_as_float(g + i), m, v);
+            const float pn = upd(master ? master[i] : bf_ld_as_float(p + i), bf_ld_as_float(g + i), m, v);
             if (sizeof(T) == 2) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(pn);
             else reinterpret_cast<float*>(p)[i] = pn;
+            if (master) master[i] = pn;
             d.exp_avg[i] = m, d.exp_avg_sq[i] = v;
         }
     }

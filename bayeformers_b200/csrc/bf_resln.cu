@@ -672,11 +672,8 @@ int launch_fwd_c(const void* h, const void* r, const float* gamma, const float* 
 }
 
 inline bool use_staged_bwd() {
-    static const int v = [] {
-        const char* e = getenv("BF_RESLN_BWD");  // "regs": force the register-prefetch kernel (A/B timing, debugging)
-        return (e && e[0] == 'r') ? 0 : 1;
-    }();
-    return v != 0;
+    // bf_set_option(BF_OPT_RESLN_BWD_STAGED, 0): force the register-prefetch kernel (A/B timing, debugging)
+    return bf_option(BF_OPT_RESLN_BWD_STAGED) != 0;
 }
 
 template <typename T, int C>
@@ -685,7 +682,7 @@ int launch_bwd_c(const void* gy, const void* z, const float* gamma, const float*
                  const DropSpec& d, cudaStream_t st) {
     constexpr int H = 256 * C;
     using SC = StagedCfg<T, C>;
-    const bool staged = use_staged_bwd();  // BF_RESLN_BWD=regs keeps the register-prefetch kernel selectable (A/B timing)
+    const bool staged = use_staged_bwd();  // BF_OPT_RESLN_BWD_STAGED = 0 keeps the register-prefetch kernel selectable (A/B timing)
     const int nblk = staged ? bwd_blocks_w(S, M, SC::kWarps) : bwd_blocks<C>(S, M);
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + counters_bytes(S));

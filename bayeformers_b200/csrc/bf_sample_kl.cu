@@ -591,8 +591,11 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
     SampleKlParams p{};
     p.mu = d.mu, p.rho = d.rho, p.prior_mu = d.prior_mu, p.prior_rho = d.prior_rho;
     p.mix.pi = d.pi;
-    WT* const w_out = mp.w_base ? reinterpret_cast<WT*>(mp.w_base + reinterpret_cast<intptr_t>(d.w_out))
-                                : reinterpret_cast<WT*>(d.w_out);
+    // w_out == (void*)-1: log-probs only (Embedding tables: rows are sampled on lookup, bf_embedding_fwd)
+    const bool no_out = reinterpret_cast<intptr_t>(d.w_out) == (intptr_t)-1;
+    WT* const w_out = no_out ? nullptr
+                      : mp.w_base ? reinterpret_cast<WT*>(mp.w_base + reinterpret_cast<intptr_t>(d.w_out))
+                                  : reinterpret_cast<WT*>(d.w_out);
     const int64_t n = d.n;
     const int64_t nquad = (n + 3) >> 2;
     int64_t q_end = q_begin + kChunkQuads;
@@ -994,13 +997,7 @@ extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t
     mp.k0 = (uint32_t)(seed & 0xffffffffu), mp.k1 = (uint32_t)(seed >> 32), mp.step = step;
     mp.step_ptr = bf_step_counter();
     mp.w_base = reinterpret_cast<char*>(w_base);
-    {
-        static const int mode = [] {
-            const char* e = getenv("BF_SK_PREFETCH");  // A/B switch: 0 none, 1 L1 (default), 2 L2
-            return e ? atoi(e) : 1;
-        }();
-        mp.prefetch = mode;
-    }
+    mp.prefetch = bf_option(BF_OPT_SK_PREFETCH);  // A/B switch: 0 none, 1 L1 (default), 2 L2
     const int64_t cap = (int64_t)bf_num_sms() * kFwdBlocksPerSm;
     const int grid = (int)(n_chunks < cap ? n_chunks : cap);
     for (int s0 = 0; s0 < S;) {

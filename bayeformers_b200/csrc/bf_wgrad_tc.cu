@@ -334,16 +334,14 @@ static int choose_splits(int64_t S, int64_t tiles, int k_steps, int64_t workers,
 }
 
 // tile shape + slicing of one call: single CTAs on 128 x 256 tiles, or CTA pairs on 256 x 256 tiles (same time per
-// item, a third less operand traffic) when that does not cost waves.  BF_WGRAD_2CTA=0 / 2 forces single / pair.
+// item, a third less operand traffic) when that does not cost waves.  bf_set_option(BF_OPT_WGRAD_2CTA, 0 / 2) forces
+// single / pair.
 struct Plan {
     bool pair;
     int i_tiles, j_tiles, k_steps, splits;
 };
 static Plan make_plan(int64_t S, int64_t M, int64_t N, int64_t K) {
-    static const int mode = [] {
-        const char* e = getenv("BF_WGRAD_2CTA");
-        return e ? atoi(e) : 1;
-    }();
+    const int mode = bf_option(BF_OPT_WGRAD_2CTA);
     Plan a{}, b{};
     double ca = 0, cb = 0;
     const int ks = tc::cdiv(M, tc::BLOCK_K);

@@ -45,6 +45,9 @@ class BayesianLayer(nn.Module):
         # grad-carrying versions of the two scalars when kl_grad is on
         self.live_log_prior = None
         self.live_log_variational_posterior = None
+        # per-sample [S] values of the last folded forward (None when S == 1); plain attributes, never in state_dict
+        self.log_prior_samples = None
+        self.log_variational_posterior_samples = None
         self._presampled = None  # one forward's draw made by presample.Presampler (consumed by forward)
 
     def _kl_grad(self) -> bool:
@@ -53,12 +56,33 @@ class BayesianLayer(nn.Module):
     def _gemm_dtype(self) -> torch.dtype:
         return runtime.get_gemm_dtype() if self.gemm_dtype is None else self.gemm_dtype
 
-    def _publish(self, logq: torch.Tensor, logp: torch.Tensor, S: int, kl_grad: bool) -> None:
-        """Store the last forward's scalars: 0-dim for S == 1 (reference
-        behaviour), [S] under mc_samples(S)."""
-        lq = logq[0] if S == 1 else logq
-        lp = logp[0] if S == 1 else logp
-        self.log_prior.data = lp.detach()
-        self.log_variational_posterior.data = lq.detach()
+    def _publish(self, logq: torch.Tensor, logp: torch.Tensor, S: int, kl_grad: bool, means=None) -> None:
+        """Store the last forward's scalars.  The two registered Parameters stay 0-dim whatever S is (so a
+        state_dict saved after a folded forward has the reference's shapes, linear.py:80-81): the value itself for
+        S == 1 (reference behaviour), the mean over the S samples under mc_samples(S) -- what downstream code takes
+        of them anyway (examples/bert_glue.py:70-71).  The per-sample [S] values live in `*_samples` (and, grad
+        carrying, in `live_*` when kl_grad is on); `bnn.Model.log_prior()` sums those.
+        `means`: optional precomputed (mean log q, mean log p) 0-dim tensors (multi-tensor sampling computes them for
+        all layers at once)."""
+        if S == 1:
+            lq, lp = logq[0], logp[0]
+            self.log_prior.data = lp.detach()
+            self.log_variational_posterior.data = lq.detach()
+            self.log_prior_samples = self.log_variational_posterior_samples = None
+        else:
+            lq, lp = logq, logp
+            mq, mp = means if means is not None else (logq.detach().mean(), logp.detach().mean())
+            self.log_prior.data = mp
+            self.log_variational_posterior.data = mq
+            self.log_prior_samples = lp.detach()
+            self.log_variational_posterior_samples = lq.detach()
         self.live_log_prior = lp if kl_grad else None
         self.live_log_variational_posterior = lq if kl_grad else None
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # checkpoints written by round-1 builds may hold [S]-shaped scalars: fold them to the reference's 0-dim form
+        for name in ("log_prior", "log_variational_posterior"):
+            v = state_dict.get(prefix + name)
+            if torch.is_tensor(v) and v.dim() > 0:
+                state_dict[prefix + name] = v.float().mean()
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)

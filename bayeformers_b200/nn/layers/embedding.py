@@ -1,8 +1,17 @@
 """Bayesian Embedding (absent from the reference snapshot).
 
 Specified by analogy with bnn.Linear: the whole table is a `Gaussian`, every
-forward samples the whole table and reduces log q / log p over it (one fused
-kernel pass), then looks rows up.  MOPED conversion as for Linear.
+forward draws a sample of the whole table, reduces log q / log p over ALL of it
+and looks rows up (the reference's `Gaussian.sample`, gaussian.py:90-101,
+composed with `F.embedding`).  MOPED conversion as for Linear.
+
+The S sampled tables are never materialised: eps is a pure function of (seed,
+step, tensor, sample, element), so `bf_embedding_fwd` samples exactly the rows
+the ids name while a weight-less sample+KL pass reduces the two log-probs over
+the whole table with the same stream; the backward is row-sparse and
+deterministic (`bf_embedding_bwd`).  Output dtype = the layer's GEMM dtype
+(fp32, or bf16 in tensor-core mode).  `max_norm` / `scale_grad_by_freq` fall back
+to torch's semantics on a materialised table.
 """
 from __future__ import annotations
 
@@ -40,21 +49,37 @@ class Embedding(BayesianLayer):
         S = runtime.get_mc_samples()
         kl_grad = self._kl_grad()
         prior = prior_spec_of(self.weight_prior)
-        out_dtype = torch.float32
+        if S > 1:
+            rows = runtime.get_folded_rows()
+            if input.shape[0] == 1 and rows is not None and rows % S == 0:
+                # broadcast ids (e.g. HF position_ids [1, T]): every folded row looks its ids up in ITS sample's table
+                input = input.expand(rows, *input.shape[1:])
+            if input.shape[0] % S != 0:
+                raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
+        pre, self._presampled = self._presampled, None  # a draw serves exactly one forward
+        if pre is not None and pre[0] != S:
+            pre = None
+        fused = (self.max_norm is None and not self.scale_grad_by_freq and ops.embedding_supported(self.embedding_dim)
+                 and input.dim() >= 1)
+        if fused:
+            # rows are sampled on lookup; log q / log p still cover the whole table (module docstring)
+            stream = pre[5] if pre is not None else self.weight.next_stream(S)
+            spec = ops.EmbeddingSpec(S=S, kl_grad=kl_grad, prior=prior, stream=stream, out_dtype=self._gemm_dtype(),
+                                     padding_idx=self.padding_idx,
+                                     presampled=None if pre is None else (pre[3], pre[4]))
+            self._last_streams = (stream, None)
+            out, logq, logp = ops.EmbeddingFn.apply(input, self.weight.mu, self.weight.rho, prior.mu, prior.rho, spec)
+            self._publish(logq, logp, S, kl_grad, means=pre[7] if pre is not None else None)
+            return out
+        # max_norm / scale_grad_by_freq: torch semantics on a materialised table (not the hot path)
         w, logq, logp = ops.SampleKL.apply(self.weight.mu, self.weight.rho, prior.mu, prior.rho, prior,
-                                           self.weight.next_stream(S), S, out_dtype, kl_grad)
+                                           self.weight.next_stream(S), S, torch.float32, kl_grad)
         self._publish(logq, logp, S, kl_grad)
         kw = dict(padding_idx=self.padding_idx, max_norm=self.max_norm, norm_type=self.norm_type,
                   scale_grad_by_freq=self.scale_grad_by_freq)
         if S == 1:
             return F.embedding(input, w[0], **kw)
-        rows = runtime.get_folded_rows()
-        if input.shape[0] == 1 and rows is not None and rows % S == 0:
-            # broadcast ids (e.g. HF position_ids [1, T]): every folded row looks its ids up in ITS sample's table
-            input = input.expand(rows, *input.shape[1:])
-        if input.shape[0] % S != 0:
-            raise ValueError(f"leading dimension {input.shape[0]} is not a multiple of mc_samples={S}")
-        chunks = input.view(S, input.shape[0] // S, *input.shape[1:])
+        chunks = input.reshape(S, input.shape[0] // S, *input.shape[1:])
         return torch.cat([F.embedding(chunks[s], w[s], **kw) for s in range(S)], dim=0)
 
     @classmethod

@@ -47,20 +47,28 @@ class LayerNorm(BayesianLayer):
 
     def sample_affine(self):
         """Draw gamma_s / beta_s for the current mc_samples and publish the layer's log-probs
-        (weight then bias, as Linear does).  Returns (w [S, H] fp32, b [S, H] fp32 or None, S)."""
+        (weight then bias, as Linear does).  Returns (w [S, H] fp32, b [S, H] fp32 or None, S).  One autograd node
+        (`ops.SamplePair`); the draw comes from the multi-tensor sampler when `enable_presample` is on."""
         S = runtime.get_mc_samples()
         kl_grad = self._kl_grad()
+        has_bias = isinstance(self.bias, Gaussian)
         wp = prior_spec_of(self.weight_prior)
-        w, logq, logp = ops.SampleKL.apply(self.weight.mu, self.weight.rho, wp.mu, wp.rho, wp,
-                                           self.weight.next_stream(S), S, torch.float32, kl_grad)
-        b = None
-        if isinstance(self.bias, Gaussian):
-            bp = prior_spec_of(self.bias_prior)
-            b, lq_b, lp_b = ops.SampleKL.apply(self.bias.mu, self.bias.rho, bp.mu, bp.rho, bp,
-                                               self.bias.next_stream(S), S, torch.float32, kl_grad)
-            logq, logp = logq + lq_b, logp + lp_b
-        self._publish(logq, logp, S, kl_grad)
-        return w, b, S
+        bp = prior_spec_of(self.bias_prior) if has_bias else ops.PriorSpec()
+        pre, self._presampled = self._presampled, None  # a draw serves exactly one forward
+        if pre is not None and pre[0] != S:
+            pre = None
+        if pre is not None:
+            spec = ops.PairSpec(S=S, kl_grad=kl_grad, w_prior=wp, b_prior=bp, w_stream=pre[5], b_stream=pre[6],
+                                presampled=pre[1:5])
+        else:
+            spec = ops.PairSpec(S=S, kl_grad=kl_grad, w_prior=wp, b_prior=bp, w_stream=self.weight.next_stream(S),
+                                b_stream=self.bias.next_stream(S) if has_bias else ops.StreamSpec())
+        self._last_streams = (spec.w_stream, spec.b_stream)
+        w, b, logq, logp = ops.SamplePair.apply(
+            self.weight.mu, self.weight.rho, self.bias.mu if has_bias else None, self.bias.rho if has_bias else None,
+            wp.mu, wp.rho, bp.mu, bp.rho, spec)
+        self._publish(logq, logp, S, kl_grad, means=pre[7] if pre is not None else None)
+        return w, (b if has_bias else None), S
 
     def forward(self, input: Tensor) -> Tensor:
         w, b, S = self.sample_affine()

@@ -73,7 +73,7 @@ class Linear(BayesianLayer):
             input, self.weight.mu, self.weight.rho,
             self.bias.mu if has_bias else None, self.bias.rho if has_bias else None,
             w_prior.mu, w_prior.rho, b_prior.mu, b_prior.rho, spec)
-        self._publish(logq, logp, S, kl_grad)
+        self._publish(logq, logp, S, kl_grad, means=pre[7] if pre is not None and len(pre) > 7 else None)
         return y
 
     @classmethod

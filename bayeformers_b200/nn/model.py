@@ -59,6 +59,8 @@ class Model(Module):
             # grad-carrying value when the layer ran with kl_grad=True, else the
             # reference's detached Parameter
             live = getattr(child, "live_" + name, None)
+            if live is None:  # per-sample [S] values of a folded forward, else the 0-dim Parameter
+                live = getattr(child, name + "_samples", None)
             value = value + (live if live is not None else getattr(child, name))
         return value
 

@@ -57,6 +57,19 @@ class Gaussian(Parameter):
     def reset_parameters(self) -> None:
         self.mu, self.rho = self.initialization(self.mu, self.rho)
 
+    def __deepcopy__(self, memo):
+        # a copy is a NEW variational tensor: it must not share the eps stream of the original (cloned layers of
+        # nn.TransformerEncoder, EMA copies, ... would otherwise draw identical eps every step)
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        from copy import deepcopy
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = deepcopy(v, memo)
+        new.normal = Normal(new.zero, new.one) if isinstance(self.normal, Normal) else self.normal
+        new.tensor_id = runtime.next_tensor_id()
+        return new
+
     @property
     def sigma(self) -> Tensor:
         return F.softplus(self.rho)

@@ -72,6 +72,47 @@ def _stream(dev: torch.device):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class on_device:
+    """Make `dev` the current CUDA device for the duration of a group of C-ABI calls (the library launches on the
+    current device: streams, SM counts and the step counter are per device).  A no-op -- one integer compare --
+    in the usual one-process-per-GPU set-up where it already is."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev: torch.device) -> None:
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _guarded(fn):
+    """Decorator for autograd.Function forward / backward bodies: run under `on_device` of the first CUDA tensor."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args, **kwargs):
+        dev = next((a.device for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        if dev is None:
+            saved = getattr(ctx, "saved_tensors", ())
+            dev = next((t.device for t in saved if torch.is_tensor(t) and t.is_cuda), None)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args, **kwargs)
+        with on_device(dev):
+            return fn(ctx, *args, **kwargs)
+
+    return wrapper
+
+
 def _dt(t: torch.dtype) -> int:
     if t == torch.float32:
         return BF_F32
@@ -196,6 +237,7 @@ class SampleKL(torch.autograd.Function):
     (gaussian.py:90-116,160-171) with one fused pass; backward regenerates eps."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, mu, rho, prior_mu, prior_rho, prior: PriorSpec, stream: StreamSpec, S: int, w_dtype, kl_grad):
         _require_cuda(mu, "variational parameter")
         prior = PriorSpec(prior.kind, prior.pi, prior.sigma1, prior.sigma2, prior_mu, prior_rho)
@@ -210,6 +252,7 @@ class SampleKL(torch.autograd.Function):
         return w, logq, logp
 
     @staticmethod
+    @_guarded
     def backward(ctx, gw, glq, glp):
         mu, rho, prior_mu, prior_rho = ctx.saved_tensors
         prior, stream, S, kl_grad = ctx.meta
@@ -226,6 +269,170 @@ class SampleKL(torch.autograd.Function):
         g_mu, g_rho = sample_kl_backward(gw, mu.detach(), rho.detach(), prior, stream, S, glq, glp,
                                          ctx.needs_input_grad[0])
         return g_mu, g_rho, None, None, None, None, None, None, None
+
+
+@dataclass
+class PairSpec:
+    """One (weight, bias) pair of small variational tensors sampled together (bnn.LayerNorm's gamma / beta)."""
+    S: int
+    kl_grad: bool
+    w_prior: PriorSpec
+    b_prior: PriorSpec
+    w_stream: StreamSpec
+    b_stream: StreamSpec = field(default_factory=StreamSpec)
+    presampled: Optional[Tuple] = None  # (w[S,n] fp32, b[S,n] fp32 or None, logq[S], logp[S]) from the Presampler
+
+
+class SamplePair(torch.autograd.Function):
+    """(w_mu, w_rho, b_mu, b_rho) -> (w[S,...], b[S,...] or None, log q[S], log p[S]): weight then bias accumulated
+    into one pair of scalars, as Linear does (linear.py:97-102).  Fresh draw or the multi-tensor sampler's; backward
+    regenerates eps for both tensors from their recorded streams."""
+
+    @staticmethod
+    @_guarded
+    def forward(ctx, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, spec: PairSpec):
+        _require_cuda(w_mu, "variational parameter")
+        S, dev = spec.S, w_mu.device
+        has_bias = b_mu is not None
+        if spec.presampled is not None:
+            w, b, logq, logp = spec.presampled
+        else:
+            logq = torch.empty(S, dtype=torch.float32, device=dev)
+            logp = torch.empty(S, dtype=torch.float32, device=dev)
+            wp = PriorSpec(spec.w_prior.kind, spec.w_prior.pi, spec.w_prior.sigma1, spec.w_prior.sigma2, wp_mu, wp_rho)
+            w = sample_kl_forward(w_mu.detach(), w_rho.detach(), wp, spec.w_stream, S, torch.float32, logq, logp, False)
+            b = None
+            if has_bias:
+                bp = PriorSpec(spec.b_prior.kind, spec.b_prior.pi, spec.b_prior.sigma1, spec.b_prior.sigma2, bp_mu,
+                               bp_rho)
+                b = sample_kl_forward(b_mu.detach(), b_rho.detach(), bp, spec.b_stream, S, torch.float32, logq, logp,
+                                      True)
+        ctx.save_for_backward(w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho)
+        ctx.spec = spec
+        if not spec.kl_grad:
+            ctx.mark_non_differentiable(logq, logp)
+        if not has_bias:
+            b = torch.empty(0, device=dev)  # placeholder output (autograd outputs must be tensors)
+            ctx.mark_non_differentiable(b)
+        return w, b, logq, logp
+
+    @staticmethod
+    @_guarded
+    def backward(ctx, gw, gb, glq, glp):
+        w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho = ctx.saved_tensors
+        spec = ctx.spec
+        S, dev = spec.S, w_rho.device
+        if spec.kl_grad:
+            glq, glp = _kl_upstream(glq, S, dev), _kl_upstream(glp, S, dev)
+        else:
+            glq = glp = None
+
+        def one(g, mu, rho, prior, pmu, prho, stream, need_mu):
+            pr = PriorSpec(prior.kind, prior.pi, prior.sigma1, prior.sigma2, pmu, prho)
+            if g is not None:
+                g = g.reshape(S, -1)
+                if g.dtype not in (torch.float32, torch.bfloat16):
+                    g = g.float()
+            return sample_kl_backward(g, mu.detach(), rho.detach(), pr, stream, S, glq, glp, need_mu)
+
+        g_wmu, g_wrho = one(gw, w_mu, w_rho, spec.w_prior, wp_mu, wp_rho, spec.w_stream, ctx.needs_input_grad[0])
+        g_bmu = g_brho = None
+        if b_mu is not None:
+            g_bmu, g_brho = one(gb, b_mu, b_rho, spec.b_prior, bp_mu, bp_rho, spec.b_stream, ctx.needs_input_grad[2])
+        return g_wmu, g_wrho, g_bmu, g_brho, None, None, None, None, None
+
+
+@dataclass
+class EmbeddingSpec:
+    S: int
+    kl_grad: bool
+    prior: PriorSpec
+    stream: StreamSpec
+    out_dtype: torch.dtype
+    padding_idx: Optional[int] = None
+    presampled: Optional[Tuple] = None  # (logq[S], logp[S]) of the whole table from the Presampler
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """ids [S*B, ...] -> (rows [S*B, ..., H], log q[S], log p[S]) of a Bayesian embedding table.
+    The log-probs are reduced over the WHOLE table (one sample+KL pass that writes no weights), while only the
+    looked-up rows are sampled (`bf_embedding_fwd`); backward is row-sparse and deterministic (`bf_embedding_bwd`),
+    plus the dense KL terms when kl_grad is on."""
+
+    @staticmethod
+    @_guarded
+    def forward(ctx, ids, mu, rho, prior_mu, prior_rho, spec: EmbeddingSpec):
+        _require_cuda(mu, "embedding table")
+        lib = _lib.load()
+        dev = mu.device
+        S = spec.S
+        V, H = mu.shape
+        if ids.device != dev:
+            raise RuntimeError(f"bayeformers_b200: ids are on {ids.device}, the table on {dev}")
+        idc = ids.detach().to(torch.int64).contiguous()
+        n_tok = idc.numel()
+        if idc.dim() < 1 or idc.shape[0] % S != 0:
+            raise ValueError(f"ids of shape {tuple(ids.shape)} cannot be split into mc_samples={S} groups of rows")
+        tps = max(n_tok // S, 1)
+        prior = PriorSpec(spec.prior.kind, spec.prior.pi, spec.prior.sigma1, spec.prior.sigma2, prior_mu, prior_rho)
+        if spec.presampled is not None:
+            logq, logp = spec.presampled
+        else:
+            logq = torch.empty(S, dtype=torch.float32, device=dev)
+            logp = torch.empty(S, dtype=torch.float32, device=dev)
+            sample_kl_forward(mu.detach(), rho.detach(), prior, spec.stream, S, torch.float32, logq, logp, False,
+                              want_w=False)
+        eps = _eps_arg(spec.stream, S, V * H, dev)
+        out = torch.empty(tuple(idc.shape) + (H,), dtype=spec.out_dtype, device=dev)
+        nbytes = float(n_tok * H * (8 + out.element_size()))
+        rc = _timed("embedding_fwd", nbytes, dev, lambda: lib.bf_embedding_fwd(
+            _ptr(idc), n_tok, tps, _ptr(mu), _ptr(rho), V, H, spec.stream.seed, spec.stream.step, spec.stream.tensor_id,
+            _ptr(eps), _ptr(out), _dt(spec.out_dtype), _stream(dev)))
+        _lib.check(rc, "bf_embedding_fwd")
+        stats["launches"] += 1
+        ctx.save_for_backward(idc, mu, rho, prior_mu, prior_rho)
+        ctx.meta = (spec, tps)
+        ctx.mark_non_differentiable(*( [] if spec.kl_grad else [logq, logp]))
+        return out, logq, logp
+
+    @staticmethod
+    @_guarded
+    def backward(ctx, gout, glq, glp):
+        lib = _lib.load()
+        idc, mu, rho, prior_mu, prior_rho = ctx.saved_tensors
+        spec, tps = ctx.meta
+        S, dev = spec.S, mu.device
+        V, H = mu.shape
+        need_mu = ctx.needs_input_grad[1]
+        prior = PriorSpec(spec.prior.kind, spec.prior.pi, spec.prior.sigma1, spec.prior.sigma2, prior_mu, prior_rho)
+        if spec.kl_grad:
+            # dense part: the KL terms touch every element of the table
+            g_mu, g_rho = sample_kl_backward(None, mu.detach(), rho.detach(), prior, spec.stream, S,
+                                             _kl_upstream(glq, S, dev), _kl_upstream(glp, S, dev), need_mu)
+        else:
+            g_rho = torch.zeros_like(rho, dtype=torch.float32)
+            g_mu = torch.zeros_like(rho, dtype=torch.float32) if need_mu else None
+        n_tok = idc.numel()
+        if gout is not None and n_tok > 0:
+            g = gout.reshape(n_tok, H)
+            if g.dtype not in (torch.float32, torch.bfloat16):
+                g = g.float()
+            g = _aligned(g)
+            sorted_ids, perm = torch.sort(idc.reshape(-1), stable=True)  # index bookkeeping; arithmetic is ours
+            eps = _eps_arg(spec.stream, S, V * H, dev)
+            ws = _workspace("embedding_bwd", dev, lib.bf_embedding_bwd_workspace_bytes(n_tok, H))
+            pad = -1 if spec.padding_idx is None else int(spec.padding_idx) % V
+            nbytes = float(n_tok * H * (g.element_size() + 8))
+            rc = _timed("embedding_bwd", nbytes, dev, lambda: lib.bf_embedding_bwd(
+                _ptr(g), _dt(g.dtype), _ptr(sorted_ids), _ptr(perm), n_tok, tps, _ptr(rho), V, H, pad, spec.stream.seed,
+                spec.stream.step, spec.stream.tensor_id, _ptr(eps), _ptr(g_mu), _ptr(g_rho), _ptr(ws), _stream(dev)))
+            _lib.check(rc, "bf_embedding_bwd")
+            stats["launches"] += 2
+        return None, g_mu, g_rho, None, None, None
+
+
+def embedding_supported(H: int) -> bool:
+    return bool(_lib.load().bf_embedding_supported(int(H)))
 
 
 @dataclass
@@ -258,6 +465,7 @@ class BayesLinear(torch.autograd.Function):
     Replaces Linear.forward (linear.py:83-104) and its autograd graph."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, x, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, spec: LinearSpec):
         _require_cuda(x, "input")
         _require_cuda(w_mu, "weight")
@@ -321,6 +529,7 @@ class BayesLinear(torch.autograd.Function):
         return y.view(*x.shape[:-1], N), logq, logp
 
     @staticmethod
+    @_guarded
     def backward(ctx, gy, glq, glp):
         lib = _lib.load()
         xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z = ctx.saved_tensors
@@ -431,6 +640,7 @@ class LayerNormFn(torch.autograd.Function):
     (shared affine).  Replaces F.layer_norm and its autograd."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, x, gamma, beta, S: int, eps: float):
         _require_cuda(x, "input")
         lib = _lib.load()
@@ -460,6 +670,7 @@ class LayerNormFn(torch.autograd.Function):
         return y.view(x.shape)
 
     @staticmethod
+    @_guarded
     def backward(ctx, gy):
         lib = _lib.load()
         xc, g, mean, rstd = ctx.saved_tensors
@@ -499,6 +710,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
     `bias_grad_box` (a list) receives sum_m dh[s][m][:] for the Linear that made h."""
 
     @staticmethod
+    @_guarded
     def forward(ctx, h, r, gamma, beta, S: int, eps: float, drop: DropoutSpec, bias_grad_box, sink=None):
         _require_cuda(h, "input")
         lib = _lib.load()
@@ -531,6 +743,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
         return y.view(h.shape)
 
     @staticmethod
+    @_guarded
     def backward(ctx, gy):
         lib = _lib.load()
         z, g, mean, rstd = ctx.saved_tensors
@@ -570,7 +783,9 @@ def dropout_mask(n: int, drop: DropoutSpec, device) -> torch.Tensor:
     lib = _lib.load()
     dev = torch.device(device)
     out = torch.empty(n, dtype=torch.uint8, device=dev)
-    rc = lib.bf_dropout_mask(_ptr(out), n, float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _stream(dev))
+    with on_device(dev):
+        rc = lib.bf_dropout_mask(_ptr(out), n, float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id,
+                                 _stream(dev))
     _lib.check(rc, "bf_dropout_mask")
     return out
 
@@ -592,6 +807,7 @@ def philox_normal(n: int, seed: int, step: int, tensor_id: int, sample_id: int, 
     lib = _lib.load()
     dev = torch.device(device)
     out = torch.empty(n, dtype=torch.float32, device=dev)
-    rc = lib.bf_philox_normal(_ptr(out), n, seed, step, tensor_id, sample_id, _stream(dev))
+    with on_device(dev):
+        rc = lib.bf_philox_normal(_ptr(out), n, seed, step, tensor_id, sample_id, _stream(dev))
     _lib.check(rc, "bf_philox_normal")
     return out

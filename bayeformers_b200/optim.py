@@ -7,7 +7,10 @@ does in two launches what the reference's loop does with
 `clip_grad_norm_(params, 1.0); AdamW.step()` (examples/bert_glue.py:240-241):
 one pass for the global gradient norm, one pass that clips and updates (the
 separate "scale the gradients" pass disappears).  Arithmetic is
-torch.optim.AdamW's; moments are kept in fp32 for bf16 parameters.  The
+torch.optim.AdamW's; bf16 parameters (what `cast_frequentist_` makes of the host
+model's embeddings / LayerNorms) get fp32 moments AND an fp32 master copy that the
+update runs on -- at lr 2e-5 a step is smaller than half a bf16 ulp of a 0.02-sized
+weight and would otherwise round away.  The
 per-tensor step counts live on the device (advanced by the kernel), so `step()`
 can be captured in a CUDA graph.
 CUDA-only, like the rest of the hot path.
@@ -38,7 +41,11 @@ class ClipAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.max_grad_norm = -1.0 if max_grad_norm is None else float(max_grad_norm)
         dev = self.params[0].device
+        if any(p.device != dev for p in self.params):
+            raise ValueError("ClipAdamW: all parameters must live on one device (one process per GPU)")
         self.device = dev
+        # fp32 masters of the bf16 parameters (None for fp32 parameters, which are their own masters)
+        self.master = [p.detach().float().clone() if p.dtype == torch.bfloat16 else None for p in self.params]
         self.exp_avg = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in self.params]
         self.exp_avg_sq = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in self.params]
         self.step_count = torch.zeros(len(self.params), dtype=torch.float32, device=dev)  # per tensor, like torch
@@ -77,6 +84,7 @@ class ClipAdamW:
             d = descs[i]
             d.param, d.exp_avg, d.exp_avg_sq = p.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr()
             d.n, d.dtype = p.numel(), (BF_BF16 if p.dtype == torch.bfloat16 else BF_F32)
+            d.master = None if self.master[i] is None else self.master[i].data_ptr()
             if g is None:
                 d.grad = None
             else:
@@ -103,12 +111,40 @@ class ClipAdamW:
     def step(self) -> torch.Tensor:
         """One update; returns the (device) global gradient norm before clipping."""
         lib = _lib.load()
-        self._upload_descs()
-        nbytes = float(sum(p.numel() * (2 * p.element_size() + 16 + p.element_size()) for p in self.params))
-        rc = ops._timed("clip_adamw", nbytes, self.device, lambda: lib.bf_clip_adamw_step(
-            self.d_descs.data_ptr(), self.d_chunks.data_ptr(), self.n_chunks, self.lr, self.betas[0], self.betas[1],
-            self.eps, self.weight_decay, self.max_grad_norm, self.step_count.data_ptr(), self.grad_norm.data_ptr(),
-            self.d_ws.data_ptr(), ops._stream(self.device)))
+        with ops.on_device(self.device):
+            self._upload_descs()
+            nbytes = float(sum(p.numel() * (2 * p.element_size() + 16 + p.element_size()) for p in self.params))
+            rc = ops._timed("clip_adamw", nbytes, self.device, lambda: lib.bf_clip_adamw_step(
+                self.d_descs.data_ptr(), self.d_chunks.data_ptr(), self.n_chunks, self.lr, self.betas[0], self.betas[1],
+                self.eps, self.weight_decay, self.max_grad_norm, self.step_count.data_ptr(), self.grad_norm.data_ptr(),
+                self.d_ws.data_ptr(), ops._stream(self.device)))
         _lib.check(rc, "bf_clip_adamw_step")
         ops.stats["launches"] += 2
         return self.grad_norm
+
+    # ---- checkpointing (the reference saves no optimizer state, bert_glue.py:303-309; a resumable run needs it)
+    def state_dict(self) -> dict:
+        return {"exp_avg": [t.detach().cpu() for t in self.exp_avg],
+                "exp_avg_sq": [t.detach().cpu() for t in self.exp_avg_sq],
+                "master": [None if t is None else t.detach().cpu() for t in self.master],
+                "step_count": self.step_count.detach().cpu(),
+                "hyper": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                          "max_grad_norm": self.max_grad_norm}}
+
+    @torch.no_grad()
+    def load_state_dict(self, state: dict) -> None:
+        if len(state["exp_avg"]) != len(self.params):
+            raise ValueError("optimizer state does not match the parameter list")
+        for dst, src in zip(self.exp_avg, state["exp_avg"]):
+            dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, state["exp_avg_sq"]):
+            dst.copy_(src)
+        for p, dst, src in zip(self.params, self.master, state["master"]):
+            if dst is not None:
+                dst.copy_(p.detach().float() if src is None else src)
+        self.step_count.copy_(state["step_count"])
+        h = state.get("hyper", {})
+        self.lr, self.eps = float(h.get("lr", self.lr)), float(h.get("eps", self.eps))
+        self.betas = tuple(h.get("betas", self.betas))
+        self.weight_decay = float(h.get("weight_decay", self.weight_decay))
+        self.max_grad_norm = float(h.get("max_grad_norm", self.max_grad_norm))

@@ -156,36 +156,103 @@ def get_gemm_dtype() -> torch.dtype:
 
 
 # ---- device-resident step counter (CUDA-graph capture of a whole training step) ----------
-_device_step = {"tensor": None}
+_device_step = {}  # device index -> int32[1] tensor registered with the library for that device
 
 
 def enable_device_step(device) -> torch.Tensor:
-    """Allocate the device step counter and register it with the kernels.  From
+    """Allocate the step counter of `device` and register it with the kernels.  From
     then on eps is a function of (seed, tensor_id, host_step + device_step,
     sample): call `advance_step()` once per training step -- it is a plain
     device add, so it can live inside a captured CUDA graph."""
-    from . import _lib
+    from . import _lib, ops
 
     dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     t = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(_lib.load().bf_set_step_counter(t.data_ptr()), "bf_set_step_counter")
-    _device_step["tensor"] = t
+    with ops.on_device(dev):
+        _lib.check(_lib.load().bf_set_step_counter(t.data_ptr()), "bf_set_step_counter")
+    _device_step[dev.index] = t
     return t
 
 
-def disable_device_step() -> None:
-    from . import _lib
+def disable_device_step(device=None) -> None:
+    from . import _lib, ops
 
-    if _device_step["tensor"] is not None:
-        _lib.check(_lib.load().bf_set_step_counter(None), "bf_set_step_counter")
-        _device_step["tensor"] = None
+    for idx in list(_device_step) if device is None else [torch.device(device).index]:
+        if idx in _device_step:
+            with ops.on_device(torch.device("cuda", idx)):
+                _lib.check(_lib.load().bf_set_step_counter(None), "bf_set_step_counter")
+            del _device_step[idx]
 
 
-def advance_step(n: int = 1) -> None:
-    t = _device_step["tensor"]
-    if t is None:
+def advance_step(n: int = 1, device=None) -> None:
+    if not _device_step:
         raise RuntimeError("enable_device_step(device) first")
-    t.add_(n)
+    if device is None:
+        for t in _device_step.values():
+            t.add_(n)
+    else:
+        _device_step[torch.device(device).index].add_(n)
+
+
+# ---- reproducible resume (SURVEY.md section 5, checkpoint row) -----------------------------------------------
+def rng_state(model: torch.nn.Module) -> dict:
+    """Everything that determines the NEXT eps draw and dropout mask of `model`: the Philox seed, the stream id and
+    the per-tensor step of every variational tensor, the multi-tensor sampler's run counter, the call counters of the
+    fused dropout sites and the device step counters.  Plain Python / CPU values: store it NEXT TO the state_dict
+
+        torch.save({"model": bm.state_dict(), "rng": bf.rng_state(bm), "optimizer": opt.state_dict()}, path)
+
+    (the reference's checkpoints hold `"model": b_model.state_dict()` plus scalars, examples/bert_glue.py:303-309).
+    It is deliberately not part of `state_dict()`: an extra key there would break strict loading of our checkpoints
+    into the reference and of reference checkpoints into this package.  Reads the device counters (one sync)."""
+    from .nn.parameters.gaussian import Gaussian
+
+    out = {"version": 1, "seed": seed(), "gaussians": {}, "dropout_sites": {}, "presample_runs": None,
+           "device_steps": {int(i): int(t.item()) for i, t in _device_step.items()}}
+    for name, mod in model.named_modules():
+        if isinstance(mod, Gaussian):
+            out["gaussians"][name] = {"tensor_id": int(mod.tensor_id), "step": int(mod.step)}
+        if hasattr(mod, "_bf_site"):
+            out["dropout_sites"][name] = {"site": int(mod._bf_site), "calls": int(getattr(mod, "_bf_calls", 0))}
+    ps = getattr(model, "_presampler", None)
+    if ps is not None:
+        out["presample_runs"] = int(ps._runs)
+    return out
+
+
+def load_rng_state(model: torch.nn.Module, state: dict) -> None:
+    """Inverse of `rng_state`: after this the model's next forward draws exactly what the checkpointed process
+    would have drawn next (same seed, stream ids, steps and dropout counters)."""
+    from .nn.parameters.gaussian import Gaussian
+
+    if state.get("version") != 1:
+        raise ValueError(f"unknown rng_state version {state.get('version')!r}")
+    manual_seed(int(state["seed"]))
+    mods = dict(model.named_modules())
+    for name, g in state["gaussians"].items():
+        mod = mods.get(name)
+        if not isinstance(mod, Gaussian):
+            raise KeyError(f"rng_state names a variational tensor {name!r} this model does not have")
+        mod.tensor_id, mod.step = int(g["tensor_id"]), int(g["step"])
+    for name, d in state["dropout_sites"].items():
+        mod = mods.get(name)
+        if mod is None or not hasattr(mod, "_bf_site"):
+            raise KeyError(f"rng_state names a fused dropout site {name!r} this model does not have "
+                           "(call accelerate_host_ with the same options before loading)")
+        mod._bf_site, mod._bf_calls = int(d["site"]), int(d["calls"])
+    ps = getattr(model, "_presampler", None)
+    if state.get("presample_runs") is not None:
+        if ps is None:
+            raise KeyError("rng_state was taken with multi-tensor sampling on: call enable_presample(model) first")
+        ps._runs = int(state["presample_runs"])
+        ps._sig = None  # stream ids may have changed: rebuild the descriptor table
+    for idx, value in state.get("device_steps", {}).items():
+        t = _device_step.get(int(idx))
+        if t is None:
+            raise KeyError(f"rng_state holds a device step for cuda:{idx}: call enable_device_step first")
+        t.fill_(int(value))
 
 
 @contextlib.contextmanager

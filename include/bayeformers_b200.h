@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define BF_ABI_VERSION 1
+#define BF_ABI_VERSION 2
 
 /* element types of activation / sampled-weight buffers */
 #define BF_F32 0
@@ -56,11 +56,22 @@ int bf_abi_version(void);
 const char* bf_last_error(void);
 /* 1 when the running device is sm_100 (tcgen05 path usable), else 0; <0 on error */
 int bf_device_is_sm100(void);
-/* Optional device-resident step counter (one process per GPU): when set, every kernel
+/* Optional device-resident step counter, registered for the CURRENT device (cudaGetDevice at
+ * the time of the call; one slot per device): when set, every kernel launched on that device
  * that draws eps uses  step + *device_counter  as the Philox step.  This is what makes a
  * whole training step capturable in a CUDA graph: the `step` arguments get baked into the
  * graph, the counter is bumped on the device between replays.  NULL switches it off. */
 int bf_set_step_counter(const uint32_t* device_counter);
+
+/* Tuning switches for A/B measurements.  The library never reads the environment; a caller that
+ * wants a non-default kernel choice says so here.  Defaults are the production choices. */
+#define BF_OPT_GEMM_2CTA 0         /* fwd/dgrad: 0 single-CTA kernels, 1 auto (default), 2 force CTA pairs */
+#define BF_OPT_WGRAD_2CTA 1        /* fused wgrad: same values */
+#define BF_OPT_RESLN_BWD_STAGED 2  /* 1 (default): shared-memory-staged resln backward, 0: register prefetch */
+#define BF_OPT_SK_PREFETCH 3       /* multi-tensor sample+KL prefetch: 0 none, 1 L1 (default), 2 L2 */
+#define BF_OPT_COUNT 4
+int bf_set_option(int32_t option, int32_t value);
+int bf_get_option(int32_t option);
 
 /* ------------------------------------------------------------------------- *
  * eps stream, exposed for the statistical tests.
@@ -123,7 +134,7 @@ typedef struct bf_tensor_desc {
     const float* rho;
     const float* prior_mu;  /* BF_PRIOR_GAUSSIAN only */
     const float* prior_rho; /* NULL: constant prior sigma in `sigma1` */
-    void* w_out;            /* [S][w_stride] of w_dtype, or NULL */
+    void* w_out;            /* [S][w_stride] of w_dtype; NULL (without w_base) or (void*)-1: log-probs only */
     int64_t n;
     int64_t w_stride;
     uint32_t tensor_id;
@@ -255,6 +266,40 @@ int bf_layernorm_bwd(const void* gy, const void* x, int32_t dtype, const float* 
                      float* dbeta, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * S-sample Embedding (the Bayesian Embedding the north_star names, absent from
+ * the reference snapshot; specified as the reference's Gaussian.sample (gaussian.py:90-101) of the
+ * whole table composed with F.embedding).  Only the looked-up rows are sampled -- eps is a pure
+ * function of (seed, step, tensor_id, sample, element), so the S sampled tables are never
+ * materialised; the log-prob sums over the WHOLE table come from bf_sample_kl_fwd / _multi with
+ * w_out == NULL, using the same (seed, step, tensor_id).
+ *
+ *   fwd : out[t][:] = mu[id_t][:] + softplus(rho[id_t][:]) * eps_s(id_t*H + :),  s = t / tok_per_sample
+ *   bwd : grad_mu[r]  += sum_{t: id_t = r} g[t]
+ *         grad_rho[r] += sigmoid(rho[r]) * sum_{t: id_t = r} g[t] * eps_{s(t)}(r*H + :)
+ *
+ * ids          [n_tok] int64 (row ids; out-of-range ids give zero rows and no gradient)
+ * mu, rho      [V, H] fp32, H % 4 == 0 (bf_embedding_supported)
+ * eps_in       NULL, or [S][V*H] fp32 injected eps (parity tests)
+ * out, g       [n_tok, H] of out_dtype / g_dtype (BF_F32 / BF_BF16)
+ * sorted_ids, perm  the ids in ascending order and, for each sorted position, the original token
+ *              index (a stable sort by the caller -- index bookkeeping, no arithmetic)
+ * grad_mu, grad_rho  [V, H] fp32, ACCUMULATED into: the caller initialises them (zeros, or the
+ *              KL terms from bf_sample_kl_bwd with grad_w == NULL); grad_mu may be NULL (frozen mu);
+ *              rows equal to padding_idx receive nothing.  Deterministic: every row is reduced in
+ *              sorted-token order by one thread block, no float atomics.
+ * workspace    bf_embedding_bwd_workspace_bytes(n_tok, H) bytes, contents irrelevant
+ * ------------------------------------------------------------------------- */
+int bf_embedding_supported(int64_t H);
+int bf_embedding_fwd(const int64_t* ids, int64_t n_tok, int64_t tok_per_sample, const float* mu, const float* rho,
+                     int64_t V, int64_t H, uint64_t seed, uint32_t step, uint32_t tensor_id, const float* eps_in,
+                     void* out, int32_t out_dtype, void* stream);
+int64_t bf_embedding_bwd_workspace_bytes(int64_t n_tok, int64_t H);
+int bf_embedding_bwd(const void* g, int32_t g_dtype, const int64_t* sorted_ids, const int64_t* perm, int64_t n_tok,
+                     int64_t tok_per_sample, const float* rho, int64_t V, int64_t H, int64_t padding_idx,
+                     uint64_t seed, uint32_t step, uint32_t tensor_id, const float* eps_in, float* grad_mu,
+                     float* grad_rho, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Fused  y = LayerNorm(dropout(h) + r)  around a Bayesian Linear (the "output"
  * blocks of a transformer host model: dense -> dropout -> LayerNorm(h + input),
  * e.g. transformers' BertSelfOutput / BertOutput).  The LayerNorm is the S-sample
@@ -311,7 +356,9 @@ typedef struct bf_opt_desc {
     float* exp_avg_sq; /* [n] fp32 */
     int64_t n;
     int32_t dtype; /* BF_F32 / BF_BF16 (param and grad) */
-    int32_t vec;   /* 1: n % 4 == 0 and all four pointers 16 B aligned (8 B for bf16 param / grad) */
+    int32_t vec;   /* 1: n % 4 == 0 and all pointers 16 B aligned (8 B for bf16 param / grad) */
+    float* master; /* NULL, or [n] fp32 master copy of a BF_BF16 parameter: the update reads and writes the master
+                      and stores its bf16 rounding in `param` (an update smaller than half a bf16 ulp is not lost) */
 } bf_opt_desc;
 
 int32_t bf_optim_chunk_elems(void);

@@ -320,7 +320,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/bayeformers_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert _lib.load().bf_abi_version() == 1
+    assert _lib.load().bf_abi_version() == _lib.ABI_VERSION == 2
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/bayeformers"), reason="live reference only in the build container")
