@@ -251,9 +251,77 @@ class OracleLinear(nn.Module):
         return y
 
 
-def oracle_convert(model: nn.Module, delta: Optional[float], freeze: bool, eps: Optional[EpsSource] = None):
+class _OracleVariational(nn.Module):
+    """Shared by the two modules the reference snapshot lacks: they are SPECIFIED as the
+    reference's Gaussian.sample / .log_prob (gaussian.py:90-116) composed with the torch functional op, with the
+    log-prob bookkeeping of Linear.forward (linear.py:97-102: weight then bias, detached)."""
+
+    def _draw(self, names):
+        ws, lp, lq = [], 0.0, 0.0
+        for n in names:
+            mu, rho, prior = getattr(self, n + "_mu"), getattr(self, n + "_rho"), getattr(self, n + "_prior")
+            if mu is None:
+                ws.append(None)
+                continue
+            w = gaussian_sample(mu, rho, self.eps.draw(mu.shape))
+            with torch.no_grad():
+                lp = lp + prior_log_prob(w, prior)
+                lq = lq + gaussian_log_prob(w, mu, rho)
+            ws.append(w)
+        self.log_prior, self.log_variational_posterior = lp, lq
+        return ws
+
+
+class OracleEmbedding(_OracleVariational):
+    """Sample the WHOLE table, log-probs over the whole table, then F.embedding."""
+
+    def __init__(self, w_mu, w_rho, w_prior, eps: EpsSource, padding_idx=None, mu_trainable=True):
+        super().__init__()
+        self.w_mu = nn.Parameter(w_mu, requires_grad=mu_trainable)
+        self.w_rho = nn.Parameter(w_rho)
+        self.w_prior, self.eps, self.padding_idx = w_prior, eps, padding_idx
+        self.log_prior = self.log_variational_posterior = torch.tensor(0.0)
+
+    def forward(self, ids):
+        (W,) = self._draw(["w"])
+        return F.embedding(ids, W, padding_idx=self.padding_idx)
+
+
+class OracleLayerNorm(_OracleVariational):
+    """Sample gamma and beta, then F.layer_norm."""
+
+    def __init__(self, shape, ln_eps, w_mu, w_rho, b_mu, b_rho, w_prior, b_prior, eps: EpsSource, mu_trainable=True):
+        super().__init__()
+        self.shape, self.ln_eps = tuple(shape), ln_eps
+        self.w_mu = nn.Parameter(w_mu, requires_grad=mu_trainable)
+        self.w_rho = nn.Parameter(w_rho)
+        self.b_mu = nn.Parameter(b_mu, requires_grad=mu_trainable) if b_mu is not None else None
+        self.b_rho = nn.Parameter(b_rho) if b_rho is not None else None
+        self.w_prior, self.b_prior, self.eps = w_prior, b_prior, eps
+        self.log_prior = self.log_variational_posterior = torch.tensor(0.0)
+
+    def forward(self, x):
+        W, b = self._draw(["w", "b"])
+        return F.layer_norm(x, self.shape, W, b, self.ln_eps)
+
+
+def _moped_pair(src: torch.Tensor, delta: Optional[float]):
+    """(mu, rho, prior) of one tensor under from_frequentist: uniform draw first (the ctor always makes it), MOPED
+    overwrite + one more uniform draw for the prior's own construction when delta is given (linear.py:137-150)."""
+    mu, rho = uniform_init(torch.zeros_like(src), torch.zeros_like(src))
+    prior = default_mixture_prior()
+    if delta is not None:
+        mu, rho = src, moped_rho(src, delta)
+        uniform_init(torch.zeros_like(src), torch.zeros_like(src))
+        prior = gaussian_prior(src.clone(), torch.ones_like(src))
+    return mu, rho, prior
+
+
+def oracle_convert(model: nn.Module, delta: Optional[float], freeze: bool, eps: Optional[EpsSource] = None,
+                   all_layers: bool = False):
     """deep-copy + swap every exact-class nn.Linear child for `OracleLinear`
-    with MOPED (delta given) or default-uniform init.
+    with MOPED (delta given) or default-uniform init.  `all_layers` also swaps nn.Embedding / nn.LayerNorm (rows
+    A9 / A10, composed from the reference's Gaussian arithmetic).
     Ref: bayeformers/__init__.py:50-61; bayeformers/nn/layers/linear.py:106-164."""
     eps = eps or EpsSource()
     new = copy.deepcopy(model)
@@ -286,6 +354,18 @@ def oracle_convert(model: nn.Module, delta: Optional[float], freeze: bool, eps: 
                         b_prior = gaussian_prior(b.clone(), torch.ones_like(b))
                     trainable = not freeze
                 setattr(mod, name, OracleLinear(w_mu, w_rho, b_mu, b_rho, w_prior, b_prior, eps, trainable))
+            elif all_layers and child.__class__ is nn.Embedding:
+                trainable = not (delta is not None and freeze)
+                w_mu, w_rho, w_prior = _moped_pair(child.weight.data, delta)
+                setattr(mod, name, OracleEmbedding(w_mu, w_rho, w_prior, eps, child.padding_idx, trainable))
+            elif all_layers and child.__class__ is nn.LayerNorm and child.elementwise_affine:
+                trainable = not (delta is not None and freeze)
+                w_mu, w_rho, w_prior = _moped_pair(child.weight.data, delta)
+                b_mu = b_rho = b_prior = None
+                if child.bias is not None:
+                    b_mu, b_rho, b_prior = _moped_pair(child.bias.data, delta)
+                setattr(mod, name, OracleLayerNorm(child.normalized_shape, child.eps, w_mu, w_rho, b_mu, b_rho,
+                                                   w_prior, b_prior, eps, trainable))
             else:
                 walk(child)
 
@@ -293,8 +373,8 @@ def oracle_convert(model: nn.Module, delta: Optional[float], freeze: bool, eps: 
     return new
 
 
-def oracle_layers(model: nn.Module) -> List[OracleLinear]:
-    return [m for m in model.modules() if isinstance(m, OracleLinear)]
+def oracle_layers(model: nn.Module) -> List[nn.Module]:
+    return [m for m in model.modules() if isinstance(m, (OracleLinear, _OracleVariational))]
 
 
 def model_log_prior(model: nn.Module):

@@ -1,0 +1,25 @@
+#!/bin/bash
+# One entry point for the gpurun jobs of a round: `scripts/gpu_run.sh stage [stage ...]`, outputs under gpurun_out/.
+#   tests        pytest -m gpu (whole suite)                      tests2     the two-rank NCCL test only (needs --gpus 2)
+#   bench        default bench.py run (headline config)           configs    the other BASELINE.json configs, short
+#   launches     ncu launch list of one eager step                ncu        ncu --set full of every hand-written kernel
+#   micro        kernel microbenchmarks (scripts/gpu_microbench.py and friends)
+mkdir -p gpurun_out
+for stage in "$@"; do
+  echo "=================== $stage"
+  case "$stage" in
+    tests)    timeout -k 10 1500 python -m pytest tests -m gpu -q --maxfail=20 -x -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log ;;
+    tests_all) timeout -k 10 1800 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider -s 2>&1 | tail -80 | tee gpurun_out/pytest_gpu.log ;;
+    tests2)   timeout -k 10 900 python -m pytest tests/test_gpu_models.py -m gpu -q -k two_rank -s -p no:cacheprovider 2>&1 | tail -30 | tee gpurun_out/pytest_gpu2.log ;;
+    smoke)    timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ;;
+    bench)    timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "rc $?"; cut -c1-1500 gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err ;;
+    bench_quick) timeout -k 10 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "rc $?"; cut -c1-400 gpurun_out/bench_quick.json; python scripts/bench_kernels.py gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err ;;
+    configs)
+      for c in mlp linear bert_qa bert_large; do
+        timeout -k 10 900 python bench.py --config $c --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "$c rc $?"; cut -c1-600 gpurun_out/bench_$c.json; tail -2 gpurun_out/bench_$c.err
+      done ;;
+    launches) timeout -k 10 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 --warmup 1 --graph 0 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "rc $?"; tail -2 gpurun_out/ncu_launch.log | cut -c1-200; python scripts/launch_summary.py gpurun_out/launches.csv > gpurun_out/launches.md; head -30 gpurun_out/launches.md ;;
+    micro)    timeout -k 10 600 python scripts/gpu_microbench.py 2>&1 | tail -40 ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done

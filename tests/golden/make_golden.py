@@ -153,6 +153,11 @@ def gen_linear():
     _linear_case("moped", 48, 20, 7, 0.05, False, True, 12, out)
     _linear_case("moped_frozen", 36, 28, 5, 0.05, True, True, 13, out)
     _linear_case("nobias", 32, 16, 6, None, False, False, 14, out)
+    # MOPED (Gaussian prior) with in / out features that are multiples of 8, i.e. shapes the TMA-fed tcgen05 kernels
+    # take: trainable mu, frozen mu, and a frozen-mu case with several k-steps, ragged tiles and a ragged row count
+    _linear_case("moped_tc", 48, 24, 7, 0.05, False, True, 15, out)
+    _linear_case("moped_frozen_tc", 40, 32, 5, 0.05, True, True, 16, out)
+    _linear_case("moped_frozen_tiles", 136, 72, 130, 0.05, True, True, 17, out)
     save("linear.npz", **out)
 
 
@@ -310,6 +315,11 @@ def gen_tiny_bert():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    only = sys.argv[1:]
+    if only:  # e.g. `python tests/golden/make_golden.py gen_linear` regenerates one file
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     gen_gaussian_kat()
     gen_mixture_kat()
     gen_linear()

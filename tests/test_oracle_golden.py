@@ -63,7 +63,8 @@ def test_moped_bit_exact():
     assert np.isposinf(r[9])  # w=2000: +inf is left alone by the reference
 
 
-@pytest.mark.parametrize("tag", ["default", "moped", "moped_frozen", "nobias"])
+@pytest.mark.parametrize("tag", ["default", "moped", "moped_frozen", "nobias", "moped_tc", "moped_frozen_tc",
+                                 "moped_frozen_tiles"])
 def test_linear_forward_backward(tag):
     g = load_golden("linear.npz")
     in_f, out_f, batch, delta, freeze, bias = g[f"{tag}_meta"]
