@@ -125,7 +125,8 @@ def to_bayesian(model: tnn.Module, initialization: Optional[Initialization] = DE
       layers      registry to use; default `TORCH2BAYE` (nn.Linear only, like the
                   reference).  Pass `bnn.TORCH2BAYE_ALL` to convert Embedding and
                   LayerNorm as well.
-      gemm_dtype  "fp32" (reference precision) or "bf16" (tcgen05 tensor cores)
+      gemm_dtype  "fp32" (reference precision, FFMA kernels), "bf16" (tcgen05 tensor cores, 1e-2) or "fp32x3"
+                  (reference precision ON the tensor cores: 3-pass bf16 split, 1e-5)
       kl_grad     True lets the KL term (log q - log p) back-propagate; the
                   reference silently drops it (linear.py:99-102)
     """

@@ -60,6 +60,13 @@ SIGNATURES = {
                                              c_int32, c_void_p]),
     "bf_linear_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32,
                                   c_void_p]),
+    "bf_split_bf16x2": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "bf_linear_fwd_x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                   c_int64, c_void_p]),
+    "bf_linear_dgrad_x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                     c_void_p]),
+    "bf_linear_wgrad_x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                     c_void_p]),
     "bf_linear_fwd_gelu_supported": (c_int32, [c_int64, c_int64, c_int64, c_int64]),
     "bf_linear_fwd_gelu": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                      c_int64, c_void_p]),

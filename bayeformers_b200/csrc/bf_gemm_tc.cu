@@ -42,6 +42,10 @@ struct Params {
     int i_tiles, j_tiles, k_steps;
     const float* bias;  // [S][J] or null
     int accumulate;     // 1: the result tile is ADDED to D (TMA reduce-add) instead of stored
+    // 1: D = A B.  3: split-precision ("fp32x3") contraction of fp32 operands given as bf16 (hi, lo) pairs,
+    //    D = A_hi B_hi + A_hi B_lo + A_lo B_hi, three passes over the reduction into ONE fp32 TMEM accumulator
+    //    (the dropped A_lo B_lo term is 2^-16 of a product): reference-precision results on the tensor cores
+    int passes;
 };
 
 struct Item {
@@ -59,7 +63,8 @@ __device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
 template <bool A_MN, bool B_MN, bool OUT_F32, bool HAS_BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
     bayes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ Params p) {
+                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024 B alignment
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -81,6 +86,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         tma_prefetch_desc(&map_out);
+        if (p.passes > 1) {
+            tma_prefetch_desc(&map_a_lo);
+            tma_prefetch_desc(&map_b_lo);
+        }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -108,27 +117,32 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
                 const Item it = decode_item(p, L);
                 const int i0 = it.i_blk * BLOCK_M, j0 = it.j_blk * BLOCK_N;
-                for (int ks = 0; ks < p.k_steps; ++ks) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + A_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const int r0 = ks * BLOCK_K;
-                    if (A_MN) {
+                for (int pass = 0; pass < p.passes; ++pass) {
+                    // pass 0: (A_hi, B_hi)   pass 1: (A_hi, B_lo)   pass 2: (A_lo, B_hi)
+                    const CUtensorMap* const ma = pass == 2 ? &map_a_lo : &map_a;
+                    const CUtensorMap* const mb = pass == 1 ? &map_b_lo : &map_b;
+                    for (int ks = 0; ks < p.k_steps; ++ks) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                        const uint32_t b_dst = a_dst + A_BYTES;
+                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                        const int r0 = ks * BLOCK_K;
+                        if (A_MN) {
 #pragma unroll
-                        for (int a = 0; a < BLOCK_M / ATOM_MN; ++a)
-                            tma_load_3d(a_dst + a * ATOM_BYTES, &map_a, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
-                    } else {
-                        tma_load_3d(a_dst, &map_a, full_bar(stage), r0, i0, it.s);
-                    }
-                    if (B_MN) {
+                            for (int a = 0; a < BLOCK_M / ATOM_MN; ++a)
+                                tma_load_3d(a_dst + a * ATOM_BYTES, ma, full_bar(stage), i0 + a * ATOM_MN, r0, it.s);
+                        } else {
+                            tma_load_3d(a_dst, ma, full_bar(stage), r0, i0, it.s);
+                        }
+                        if (B_MN) {
 #pragma unroll
-                        for (int a = 0; a < BLOCK_N / ATOM_MN; ++a)
-                            tma_load_3d(b_dst + a * ATOM_BYTES, &map_b, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
-                    } else {
-                        tma_load_3d(b_dst, &map_b, full_bar(stage), r0, j0, it.s);
+                            for (int a = 0; a < BLOCK_N / ATOM_MN; ++a)
+                                tma_load_3d(b_dst + a * ATOM_BYTES, mb, full_bar(stage), j0 + a * ATOM_MN, r0, it.s);
+                        } else {
+                            tma_load_3d(b_dst, mb, full_bar(stage), r0, j0, it.s);
+                        }
+                        if (++stage == kStages) stage = 0, phase ^= 1u;
                     }
-                    if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
             }
         }
@@ -145,7 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int ks = 0; ks < p.k_steps; ++ks) {
+                const int total_steps = p.k_steps * p.passes;  // split-precision: 3 passes into the same accumulator
+                for (int ks = 0; ks < total_steps; ++ks) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_src = smem_base + stage * STAGE_BYTES;
@@ -264,27 +279,29 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 template <bool A_MN, bool B_MN, bool OUT_F32, bool HAS_BIAS>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Params& p,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, Params p, cudaStream_t st,
+                  const CUtensorMap* ma_lo = nullptr, const CUtensorMap* mb_lo = nullptr) {
     auto kern = bayes_gemm_kernel<A_MN, B_MN, OUT_F32, HAS_BIAS>;
     BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int64_t n_items = p.S * p.i_tiles * p.j_tiles;
     const int64_t sms = bf_num_sms();
     const int grid = (int)(n_items < sms ? n_items : sms);
-    kern<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mo, p);
+    p.passes = (ma_lo && mb_lo) ? 3 : 1;
+    kern<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mo, ma_lo ? *ma_lo : ma, mb_lo ? *mb_lo : mb, p);
     BF_LAUNCH_OK();
     return 0;
 }
 
 template <bool A_MN, bool B_MN>
 static int launch_out(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const Params& p,
-                      bool out_f32, cudaStream_t st) {
+                      bool out_f32, cudaStream_t st, const CUtensorMap* ma_lo = nullptr,
+                      const CUtensorMap* mb_lo = nullptr) {
     const bool bias = p.bias != nullptr;
     if (out_f32)
-        return bias ? launch<A_MN, B_MN, true, true>(ma, mb, mo, p, st)
-                    : launch<A_MN, B_MN, true, false>(ma, mb, mo, p, st);
-    return bias ? launch<A_MN, B_MN, false, true>(ma, mb, mo, p, st)
-                : launch<A_MN, B_MN, false, false>(ma, mb, mo, p, st);
+        return bias ? launch<A_MN, B_MN, true, true>(ma, mb, mo, p, st, ma_lo, mb_lo)
+                    : launch<A_MN, B_MN, true, false>(ma, mb, mo, p, st, ma_lo, mb_lo);
+    return bias ? launch<A_MN, B_MN, false, true>(ma, mb, mo, p, st, ma_lo, mb_lo)
+                : launch<A_MN, B_MN, false, false>(ma, mb, mo, p, st, ma_lo, mb_lo);
 }
 
 }  // namespace tc
@@ -354,4 +371,111 @@ int bf_linear_wgrad_bf16(const void* gy, const void* x, float* dw, int64_t S, in
     p.S = S, p.I = N, p.J = K, p.R = M;
     p.i_tiles = cdiv(N, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(M, BLOCK_K);
     return launch_out<true, true>(ma, mb, mo, p, true, st);
+}
+
+// ------------------------------------------------------------------ split-precision ("fp32x3") contractions
+// fp32 operands travel as bf16 (hi, lo) pairs (bf_split_bf16x2); three tcgen05 passes per tile accumulate
+// A_hi B_hi + A_hi B_lo + A_lo B_hi in fp32 (single-CTA 128 x 256 kernel, fp32 results).  Reference precision
+// (bayeformers/nn/layers/linear.py:104 computes in fp32 with TF32 off) at tensor-core speed: the parity mode that
+// the FFMA kernels of bf_gemm_simt.cu serve at 2 % of the tensor peak.
+namespace {
+__global__ void __launch_bounds__(256) split_bf16x2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n && (reinterpret_cast<uintptr_t>(src + i) & 15u) == 0 &&
+            (reinterpret_cast<uintptr_t>(hi + i) & 7u) == 0 && (reinterpret_cast<uintptr_t>(lo + i) & 7u) == 0) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+            const float f[4] = {v.x, v.y, v.z, v.w};
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = __float2bfloat16_rn(f[j]);
+                l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+            }
+            *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+        } else {
+            for (int j = 0; j < 4 && i + j < n; ++j) {
+                const float f = src[i + j];
+                const __nv_bfloat16 h = __float2bfloat16_rn(f);
+                hi[i + j] = h;
+                lo[i + j] = __float2bfloat16_rn(f - __bfloat162float(h));
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" int bf_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+    BF_CHECK_ARG(n >= 0, "bad n");
+    if (n == 0) return 0;
+    BF_CHECK_ARG(src && hi && lo, "null pointer");
+    const int64_t want = (n + 1023) / 1024, cap = (int64_t)bf_num_sms() * 16;
+    split_bf16x2_kernel<<<(int)(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        src, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n);
+    BF_LAUNCH_OK();
+    return 0;
+}
+
+#define BF_X3_CHECK()                                                                            \
+    BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1");                 \
+    BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "tensor-core path needs K % 8 == 0 and N % 8 == 0")
+
+// y[s] = x[s] w[s]^T + bias[s]
+extern "C" int bf_linear_fwd_x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                                const float* bias, float* y, int64_t S, int64_t M, int64_t N, int64_t K, void* stream) {
+    using namespace tc;
+    BF_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && y, "null pointer");
+    BF_X3_CHECK();
+    CUtensorMap ma, mb, mo, mal, mbl;
+    int rc;
+    if ((rc = encode_map(&ma, x_hi, S, M, K, BLOCK_M))) return rc;
+    if ((rc = encode_map(&mal, x_lo, S, M, K, BLOCK_M))) return rc;
+    if ((rc = encode_map(&mb, w_hi, S, N, K, BLOCK_N))) return rc;
+    if ((rc = encode_map(&mbl, w_lo, S, N, K, BLOCK_N))) return rc;
+    if ((rc = encode_map(&mo, y, S, M, N, BLOCK_M, true))) return rc;
+    Params p{};
+    p.S = S, p.I = M, p.J = N, p.R = K;
+    p.i_tiles = cdiv(M, BLOCK_M), p.j_tiles = cdiv(N, BLOCK_N), p.k_steps = cdiv(K, BLOCK_K);
+    p.bias = bias;
+    return launch_out<false, false>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
+}
+
+// dx[s] = gy[s] w[s]
+extern "C" int bf_linear_dgrad_x3(const void* gy_hi, const void* gy_lo, const void* w_hi, const void* w_lo, float* dx,
+                                  int64_t S, int64_t M, int64_t N, int64_t K, void* stream) {
+    using namespace tc;
+    BF_CHECK_ARG(gy_hi && gy_lo && w_hi && w_lo && dx, "null pointer");
+    BF_X3_CHECK();
+    CUtensorMap ma, mb, mo, mal, mbl;
+    int rc;
+    if ((rc = encode_map(&ma, gy_hi, S, M, N, BLOCK_M))) return rc;
+    if ((rc = encode_map(&mal, gy_lo, S, M, N, BLOCK_M))) return rc;
+    if ((rc = encode_map(&mb, w_hi, S, N, K, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mbl, w_lo, S, N, K, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mo, dx, S, M, K, BLOCK_M, true))) return rc;
+    Params p{};
+    p.S = S, p.I = M, p.J = K, p.R = N;
+    p.i_tiles = cdiv(M, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(N, BLOCK_K);
+    return launch_out<false, true>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
+}
+
+// dw[s] = gy[s]^T x[s]
+extern "C" int bf_linear_wgrad_x3(const void* gy_hi, const void* gy_lo, const void* x_hi, const void* x_lo, float* dw,
+                                  int64_t S, int64_t M, int64_t N, int64_t K, void* stream) {
+    using namespace tc;
+    BF_CHECK_ARG(gy_hi && gy_lo && x_hi && x_lo && dw, "null pointer");
+    BF_X3_CHECK();
+    CUtensorMap ma, mb, mo, mal, mbl;
+    int rc;
+    if ((rc = encode_map(&ma, gy_hi, S, M, N, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mal, gy_lo, S, M, N, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mb, x_hi, S, M, K, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mbl, x_lo, S, M, K, BLOCK_K))) return rc;
+    if ((rc = encode_map(&mo, dw, S, N, K, BLOCK_M, true))) return rc;
+    Params p{};
+    p.S = S, p.I = N, p.J = K, p.R = M;
+    p.i_tiles = cdiv(N, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(M, BLOCK_K);
+    return launch_out<true, true>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
 }

@@ -64,7 +64,7 @@ class Embedding(BayesianLayer):
         if fused:
             # rows are sampled on lookup; log q / log p still cover the whole table (module docstring)
             stream = pre[5] if pre is not None else self.weight.next_stream(S)
-            spec = ops.EmbeddingSpec(S=S, kl_grad=kl_grad, prior=prior, stream=stream, out_dtype=self._gemm_dtype(),
+            spec = ops.EmbeddingSpec(S=S, kl_grad=kl_grad, prior=prior, stream=stream, out_dtype=runtime.activation_dtype(self._gemm_dtype()),
                                      padding_idx=self.padding_idx,
                                      presampled=None if pre is None else (pre[3], pre[4]))
             self._last_streams = (stream, None)

@@ -450,6 +450,18 @@ class LinearSpec:
     sink: Optional[object] = None         # runtime.GradSink of the input: add dx into its buffer instead of returning it
 
 
+def split_bf16x2(t: torch.Tensor):
+    """fp32 tensor -> bf16 [2, *shape]: out[0] = hi, out[1] = lo with hi + lo == t to 2^-17 relative (operands of the
+    fp32x3 contractions)."""
+    lib = _lib.load()
+    t = t.contiguous()
+    out = torch.empty((2,) + tuple(t.shape), dtype=torch.bfloat16, device=t.device)
+    rc = lib.bf_split_bf16x2(_ptr(t), _ptr(out[0]), _ptr(out[1]), t.numel(), _stream(t.device))
+    _lib.check(rc, "bf_split_bf16x2")
+    stats["launches"] += 1
+    return out
+
+
 def tc_eligible(N: int, K: int) -> bool:
     """Shapes the TMA-fed tcgen05 path accepts (16-byte global row strides)."""
     return N % 8 == 0 and K % 8 == 0
@@ -478,6 +490,8 @@ class BayesLinear(torch.autograd.Function):
             raise ValueError(f"input {tuple(x.shape)} incompatible with weight {(N, K)} and mc_samples={S}")
         M = rows // S
         use_tc = spec.gemm_dtype == torch.bfloat16 and tc_eligible(N, K)
+        # "fp32x3": fp32 operands, split into bf16 (hi, lo) pairs, three tensor-core passes per tile (1e-5 parity mode)
+        use_x3 = spec.gemm_dtype == "fp32x3" and tc_eligible(N, K) and M > 0
         cdt = torch.bfloat16 if use_tc else torch.float32
         xg = x.detach().reshape(S, M, K).to(cdt).contiguous()
         has_bias = b_mu is not None
@@ -506,7 +520,14 @@ class BayesLinear(torch.autograd.Function):
         fused_act = (act == "gelu" and use_tc and has_bias and out_dtype == torch.bfloat16 and M > 0
                      and bool(lib.bf_linear_fwd_gelu_supported(S, M, N, K)))
         y = torch.empty((S, M, N), dtype=out_dtype, device=dev)
-        if fused_act:
+        if use_x3:
+            # the (hi, lo) pairs replace the fp32 operands in what backward keeps (same bytes)
+            xg, W = split_bf16x2(xg), split_bf16x2(W)
+            rc = _timed("gemm_fwd_x3", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_fwd_x3(
+                _ptr(xg[0]), _ptr(xg[1]), _ptr(W[0]), _ptr(W[1]), _ptr(b), _ptr(y), S, M, N, K, _stream(dev)))
+            _lib.check(rc, "bf_linear_fwd_x3")
+            stats["launches"] += 1
+        elif fused_act:
             z = torch.empty((S, M, N), dtype=torch.bfloat16, device=dev)
             rc = _timed("gemm_fwd_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_fwd_gelu(
                 _ptr(xg), _ptr(W), _ptr(b), _ptr(z), _ptr(y), S, M, N, K, _stream(dev)))
@@ -521,7 +542,7 @@ class BayesLinear(torch.autograd.Function):
             z = y
             y = torch.nn.functional.gelu(z)
         ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z)
-        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape), fused_act)
+        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape), fused_act, use_x3)
         if not spec.kl_grad:
             ctx.mark_non_differentiable(logq, logp)
         if x.dtype != out_dtype:
@@ -533,7 +554,7 @@ class BayesLinear(torch.autograd.Function):
     def backward(ctx, gy, glq, glp):
         lib = _lib.load()
         xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z = ctx.saved_tensors
-        spec, use_tc, M, x_dtype, x_shape, fused_act = ctx.meta
+        spec, use_tc, M, x_dtype, x_shape, fused_act, use_x3 = ctx.meta
         S = spec.S
         N, K = w_mu.shape
         dev = xg.device
@@ -564,7 +585,15 @@ class BayesLinear(torch.autograd.Function):
                 gyc = gz
             elif z is not None:
                 gyc = torch.ops.aten.gelu_backward(gyc, z.reshape(S, M, N).to(cdt)).contiguous()
-            if ctx.needs_input_grad[0]:
+            gy_split = split_bf16x2(gyc) if use_x3 else None
+            if ctx.needs_input_grad[0] and use_x3:
+                dx = torch.empty((S, M, K), dtype=torch.float32, device=dev)
+                rc = _timed("gemm_dgrad_x3", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_dgrad_x3(
+                    _ptr(gy_split[0]), _ptr(gy_split[1]), _ptr(W[0]), _ptr(W[1]), _ptr(dx), S, M, N, K, st))
+                _lib.check(rc, "bf_linear_dgrad_x3")
+                stats["launches"] += 1
+                g_x = dx.view(x_shape).to(x_dtype)
+            elif ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 sink = spec.sink
                 buf = None if sink is None else sink.buffer
@@ -616,9 +645,14 @@ class BayesLinear(torch.autograd.Function):
                 stats["launches"] += 2  # contraction + fixed-order reduction
             else:
                 dW = torch.empty((S, N, K), dtype=torch.float32, device=dev)
-                rc = _timed("gemm_wgrad_f32", 2.0 * S * M * N * K, dev,
-                            lambda: lib.bf_linear_wgrad(_ptr(gyc), _ptr(xg), _ptr(dW), S, M, N, K, BF_F32, st))
-                _lib.check(rc, "bf_linear_wgrad")
+                if use_x3:
+                    rc = _timed("gemm_wgrad_x3", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_wgrad_x3(
+                        _ptr(gy_split[0]), _ptr(gy_split[1]), _ptr(xg[0]), _ptr(xg[1]), _ptr(dW), S, M, N, K, st))
+                    _lib.check(rc, "bf_linear_wgrad_x3")
+                else:
+                    rc = _timed("gemm_wgrad_f32", 2.0 * S * M * N * K, dev,
+                                lambda: lib.bf_linear_wgrad(_ptr(gyc), _ptr(xg), _ptr(dW), S, M, N, K, BF_F32, st))
+                    _lib.check(rc, "bf_linear_wgrad")
                 stats["launches"] += 1
                 g_wmu, g_wrho = sample_kl_backward(dW.view(S, -1), w_mu.detach(), w_rho.detach(), w_prior,
                                                    spec.w_stream, S, glq, glp, need_wmu)

@@ -136,15 +136,24 @@ def get_kl_grad() -> bool:
     return _global["kl_grad"]
 
 
-def _as_dtype(d) -> torch.dtype:
+FP32X3 = "fp32x3"  # reference precision on the tensor cores: 3-pass bf16 (hi, lo) split contractions
+
+
+def _as_dtype(d):
+    """torch.float32 (FFMA parity kernels), torch.bfloat16 (tcgen05, 1e-2) or FP32X3 (tcgen05 split precision, 1e-5)."""
     if isinstance(d, torch.dtype):
         out = d
     else:
         out = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16,
-               "bfloat16": torch.bfloat16}[str(d)]
-    if out not in (torch.float32, torch.bfloat16):
-        raise ValueError("gemm_dtype must be fp32 or bf16")
+               "bfloat16": torch.bfloat16, "fp32x3": FP32X3}[str(d)]
+    if out not in (torch.float32, torch.bfloat16, FP32X3):
+        raise ValueError("gemm_dtype must be fp32, bf16 or fp32x3")
     return out
+
+
+def activation_dtype(d) -> torch.dtype:
+    """dtype activations / sampled rows travel in under GEMM mode `d`."""
+    return torch.bfloat16 if d == torch.bfloat16 else torch.float32
 
 
 def set_gemm_dtype(d) -> None:

@@ -199,6 +199,19 @@ int bf_linear_wgrad(const void* gy, const void* x, float* dw, int64_t S, int64_t
 int bf_linear_dgrad_accumulate(const void* gy, const void* w, void* dx, int64_t S, int64_t M, int64_t N, int64_t K,
                                int32_t dtype, int32_t dx_dtype, void* stream);
 
+/* Split-precision ("fp32x3") contractions: reference precision (linear.py:104 computes in fp32, TF32 off) on the
+ * tensor cores.  fp32 operands are given as bf16 (hi, lo) pairs, hi = bf16(v), lo = bf16(v - hi)
+ * (bf_split_bf16x2); each output tile accumulates A_hi B_hi + A_hi B_lo + A_lo B_hi in one fp32 TMEM accumulator
+ * (tcgen05, three passes over the reduction); the dropped A_lo B_lo term is ~2^-16 of a product.  Results fp32,
+ * norm-wise error ~4e-6 of the fp32 result.  Shapes as bf_linear_fwd / _dgrad / _wgrad; N % 8 == 0 and K % 8 == 0. */
+int bf_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream);
+int bf_linear_fwd_x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                     int64_t S, int64_t M, int64_t N, int64_t K, void* stream);
+int bf_linear_dgrad_x3(const void* gy_hi, const void* gy_lo, const void* w_hi, const void* w_lo, float* dx, int64_t S,
+                       int64_t M, int64_t N, int64_t K, void* stream);
+int bf_linear_wgrad_x3(const void* gy_hi, const void* gy_lo, const void* x_hi, const void* x_lo, float* dw, int64_t S,
+                       int64_t M, int64_t N, int64_t K, void* stream);
+
 /* Extension: forward with the bias + GELU (exact, erf form) epilogue fused, for layers used as
  * y = gelu(F.linear(x, w, b)) (linear.py:104 followed by the host model's activation), and the matching
  * backward elementwise pass.  bf16 tensor-core path only, bias required.

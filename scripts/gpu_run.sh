@@ -9,7 +9,8 @@ for stage in "$@"; do
   echo "=================== $stage"
   case "$stage" in
     tests)    timeout -k 10 1500 python -m pytest tests -m gpu -q --maxfail=20 -x -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log ;;
-    tests_all) timeout -k 10 1800 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider -s 2>&1 | tail -80 | tee gpurun_out/pytest_gpu.log ;;
+    tests_all) timeout -k 10 1800 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider -s > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log ;;
+    tests_models) timeout -k 10 1800 python -m pytest tests/test_gpu_models.py -m gpu -q --maxfail=30 -p no:cacheprovider -s > gpurun_out/pytest_gpu_models.log 2>&1; grep -E "^\[|passed|failed|^E  |Error" gpurun_out/pytest_gpu_models.log | head -60 ;;
     tests2)   timeout -k 10 900 python -m pytest tests/test_gpu_models.py -m gpu -q -k two_rank -s -p no:cacheprovider 2>&1 | tail -30 | tee gpurun_out/pytest_gpu2.log ;;
     smoke)    timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ;;
     bench)    timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "rc $?"; cut -c1-1500 gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err ;;

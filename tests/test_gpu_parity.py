@@ -1134,3 +1134,76 @@ def test_row_kernels_take_misaligned_views():
     rc = lib.bf_resln_fwd(h.data_ptr(), r.data_ptr(), BF_BF16, g.data_ptr(), b.data_ptr(), 0, 1, rows, H, 1e-5, 0.0, 1, 0, 1,
                           z.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"16-byte aligned" in lib.bf_last_error()
+
+
+# ------------------------------------------------------------------ reference precision on the tensor cores (fp32x3)
+@pytest.mark.parametrize("S,M,N,K", [(1, 128, 256, 64), (2, 256, 512, 256), (3, 200, 136, 264), (2, 1000, 768, 3072),
+                                     (4, 4096, 768, 768)])
+def test_x3_contractions_vs_float64(S, M, N, K):
+    """bf_linear_{fwd,dgrad,wgrad}_x3: fp32 operands split into bf16 (hi, lo) pairs, three tcgen05 passes per tile;
+    results must sit within 1e-5 (norm-wise) of the float64 contraction of the fp32 operands -- the tolerance the north
+    star gives the fp32 mode -- where plain bf16 operands would be ~3e-3 off."""
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(S * 7 + M + K)
+    x = torch.randn(S, M, K, generator=gen).to(DEV)
+    w = (torch.randn(S, N, K, generator=gen) * 0.05).to(DEV)
+    b = torch.randn(S, N, generator=gen).to(DEV)
+    gy = torch.randn(S, M, N, generator=gen).to(DEV)
+    xs, ws, gs = ops.split_bf16x2(x), ops.split_bf16x2(w), ops.split_bf16x2(gy)
+    assert rel_err((xs[0].double() + xs[1].double()).cpu().numpy(), x.double().cpu().numpy()) < 2 ** -16
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty(S, M, N, device=DEV)
+    _lib.check(lib.bf_linear_fwd_x3(xs[0].data_ptr(), xs[1].data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), b.data_ptr(),
+                                    y.data_ptr(), S, M, N, K, st), "fwd_x3")
+    want = torch.einsum("smk,snk->smn", x.double(), w.double()) + b.double()[:, None, :]
+    e_fwd = rel_err(y.cpu().numpy(), want.cpu().numpy())
+    dx = torch.empty(S, M, K, device=DEV)
+    _lib.check(lib.bf_linear_dgrad_x3(gs[0].data_ptr(), gs[1].data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), dx.data_ptr(),
+                                      S, M, N, K, st), "dgrad_x3")
+    e_dg = rel_err(dx.cpu().numpy(), torch.einsum("smn,snk->smk", gy.double(), w.double()).cpu().numpy())
+    dw = torch.empty(S, N, K, device=DEV)
+    _lib.check(lib.bf_linear_wgrad_x3(gs[0].data_ptr(), gs[1].data_ptr(), xs[0].data_ptr(), xs[1].data_ptr(), dw.data_ptr(),
+                                      S, M, N, K, st), "wgrad_x3")
+    e_wg = rel_err(dw.cpu().numpy(), torch.einsum("smn,smk->snk", gy.double(), x.double()).cpu().numpy())
+    print(f"[x3 {S}x{M}x{N}x{K}] fwd {e_fwd:.2e} dgrad {e_dg:.2e} wgrad {e_wg:.2e}")
+    assert max(e_fwd, e_dg, e_wg) < FP32_TOL
+
+
+@pytest.mark.parametrize("tag", ["default", "nobias", "moped_tc", "moped_frozen_tc", "moped_frozen_tiles"])
+def test_linear_fp32x3_matches_reference(tag):
+    """gemm_dtype="fp32x3" against outputs of the unmodified reference at the fp32 tolerance (1e-5), with every
+    contraction on the tensor cores."""
+    g = load_golden("linear.npz")
+    layer, bias, freeze = _layer_from_golden(g, tag, "fp32x3")
+    x = T(g[f"{tag}_x"]).requires_grad_()
+    ops.enable_kernel_timing(True)
+    try:
+        y = layer(x)
+        y.backward(T(g[f"{tag}_gy"]))
+        torch.cuda.synchronize()
+        ran = set(ops.kernel_timing_summary())
+    finally:
+        ops.enable_kernel_timing(False)
+    assert {"gemm_fwd_x3", "gemm_dgrad_x3", "gemm_wgrad_x3"} <= ran, ran
+    assert rel_err(y.detach().cpu().numpy(), g[f"{tag}_y"]) < FP32_TOL
+    assert abs(float(layer.log_prior) - float(g[f"{tag}_log_prior"])) <= FP32_TOL * abs(float(g[f"{tag}_log_prior"]))
+    assert rel_err(x.grad.cpu().numpy(), g[f"{tag}_g_x"]) < FP32_TOL
+    assert rel_err(layer.weight.rho.grad.cpu().numpy(), g[f"{tag}_g_w_rho"]) < 2 * FP32_TOL
+    if not freeze:
+        assert rel_err(layer.weight.mu.grad.cpu().numpy(), g[f"{tag}_g_w_mu"]) < FP32_TOL
+    if bias:
+        assert rel_err(layer.bias.rho.grad.cpu().numpy(), g[f"{tag}_g_b_rho"]) < FP32_TOL
+
+
+def test_tiny_bert_fp32x3_mode_within_fp32_tolerance():
+    g = load_golden("tiny_bert.npz")
+    S = int(g["S"])
+    bm, layers = _tiny_bert(g, "fp32x3")
+    for i, l in enumerate(layers):
+        l.weight.normal = FixedEps(list(g[f"eps_w{i}"]))
+        l.bias.normal = FixedEps(list(g[f"eps_b{i}"]))
+    with bf.mc_samples(S):
+        out = bm(input_ids=T(g["ids"]).repeat(S, 1)).logits
+    raw = out.view(S, -1, out.shape[-1])
+    assert rel_err(raw.detach().float().cpu().numpy(), g["logits"]) < 5 * FP32_TOL
+    assert rel_err(bm.log_prior().cpu().numpy(), g["log_prior"]) < FP32_TOL
