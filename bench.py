@@ -431,7 +431,10 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
 
     def step_body(inp, tgt):
         bf.advance_step()
-        optim.zero_grad(set_to_none=True)
+        if sync.bucketed:
+            sync.zero_grad()  # gradients live in flat all-reduce buckets: one memset each
+        else:
+            optim.zero_grad(set_to_none=True)
         with bf.mc_samples(S):
             outs = wl.forward(bm, {k: v.repeat(S, *([1] * (v.dim() - 1))) for k, v in inp.items()})
         raws = [o.float().view(S, B, *o.shape[1:]) for o in outs]
@@ -468,7 +471,8 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        optim.zero_grad(set_to_none=True)
+        if not sync.bucketed:
+            optim.zero_grad(set_to_none=True)
         l0 = ops.stats["launches"]
         # bf.hf_capture_compat: keep HF on the mask-free fused-attention path while capturing (see its docstring)
         with bf.hf_capture_compat(), torch.cuda.graph(graph, stream=side):  # same stream as the warm-up
@@ -566,7 +570,9 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
         t = torch.tensor([ms, ms_e2e if ms_e2e is not None else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), (float(t[1]) if ms_e2e is not None else None)
+    ar_ms = sync.allreduce_alone_ms() if world > 1 else None
     res = {"ms": ms, "ms_e2e": ms_e2e, "units_per_step": B if sample_shard else B * world, "kern": kern,
+           "allreduce_alone_ms": ar_ms, "allreduce_launches": len(sync.buckets) if sync.bucketed else None,
            "kern_steps": kern_steps, "launches": launches, "clocks": clk, "graph_note": graph_note, "n_warm": n_warm,
            "h2d_bytes": h2d_bytes, "cfg": cfg, "hbm_peak_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
            "allreduce_bytes": sync.bytes_last_step, "use_graph": use_graph, "wl": wl}
@@ -679,6 +685,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's channel CTAs share the SMs with persistent one-CTA-per-SM contractions: keep them few (the message is
+        # a handful of 50-100 MB buckets over NVSwitch, far from needing every channel)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     if args.shard == "samples" and args.samples % world != 0:
         raise SystemExit(f"--shard samples needs S ({args.samples}) to be a multiple of the number of GPUs ({world})")
@@ -791,7 +800,11 @@ def run_ours(args):
                                              "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 12},
             "side_by_side": extras,
             "gpu_launches": res["launches"], "clocks": res["clocks"], "execution": res["graph_note"],
-            "hbm_peak_gb": res["hbm_peak_gb"], "grad_allreduce_bytes_per_step": res["allreduce_bytes"]}
+            "hbm_peak_gb": res["hbm_peak_gb"], "grad_allreduce_bytes_per_step": res["allreduce_bytes"],
+            "grad_allreduce": {"launches_per_step": res["allreduce_launches"], "ms_alone": res["allreduce_alone_ms"],
+                               "how": "flat gradient buckets all-reduced as they fill during backward (NCCL, captured in "
+                                      "the graph); ms_alone = the same buckets all-reduced with nothing else running, "
+                                      "CUDA events, after the timed region", "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}}
     print(json.dumps(line), flush=True)
     leave()
 

@@ -29,7 +29,7 @@ def _worker(rank, world, port, ret):
     seed = parallel.broadcast_seed(0)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.Linear(64, 3))  # 4096-element weight = "large"
-    sync = parallel.GradSync(net, large_numel=1024)
+    sync = parallel.GradSync(net, large_numel=1024, bucketed=False)  # per-tensor mode
     x = torch.full((4, 64), float(rank + 1))
     net(x).sum().backward()
     local = [p.grad.clone() for p in net.parameters()]
@@ -40,6 +40,24 @@ def _worker(rank, world, port, ret):
                n_small=n_small, bytes=sync.bytes_last_step)
     lq, lp = parallel.all_reduce_elbo(torch.tensor([1.0 + rank]), torch.tensor([10.0 * (rank + 1)]))
     out["elbo"] = (float(lq), float(lp))
+    # bucketed mode (the default when world > 1): gradients live in flat buffers, one all-reduce per bucket, launched
+    # from the hook of the bucket's last tensor; two steps to exercise zero_grad / re-arming
+    sync.remove()
+    for p in net.parameters():
+        p.grad = None
+    bs = parallel.GradSync(net, buckets=2)
+    assert bs.bucketed and 1 <= len(bs.buckets) <= 3
+    views = [p.grad.data_ptr() for p in net.parameters()]
+    steps = []
+    for k in range(2):
+        bs.zero_grad()
+        net(x * (k + 1)).sum().backward()
+        launched = sum(b.handle is not None for b in bs.buckets)
+        bs.finish()
+        steps.append(dict(grads=[p.grad.clone() for p in net.parameters()], launched=launched, bytes=bs.bytes_last_step))
+    out["bucketed"] = steps
+    out["views_kept"] = views == [p.grad.data_ptr() for p in net.parameters()]
+    out["n_buckets"] = len(bs.buckets)
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -58,6 +76,15 @@ def test_gradsync_world2_gloo():
             assert torch.allclose(g0, (l0 + l1) / 2)
         assert r0["bytes"] == sum(p.numel() * 4 for p in r0["grads"])
         assert r0["elbo"] == r1["elbo"] == (3.0, 30.0)
+        # bucketed mode gives the same averaged gradients (step k uses x * (k+1): the gradient of the weights scales)
+        assert r0["views_kept"] and r1["views_kept"]
+        for k in range(2):
+            b0, b1 = r0["bucketed"][k], r1["bucketed"][k]
+            assert b0["launched"] == r0["n_buckets"]  # every bucket's all-reduce started inside backward
+            for g0, g1 in zip(b0["grads"], b1["grads"]):
+                assert torch.equal(g0, g1)
+            assert torch.allclose(b0["grads"][0], r0["grads"][0] * (k + 1))
+            assert b0["bytes"] >= sum(p.numel() * 4 for p in r0["grads"])
 
 
 def test_gradsync_single_process_is_noop():
