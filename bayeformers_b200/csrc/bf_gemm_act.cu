@@ -310,6 +310,245 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
 }
 
+// ------------------------------------------------------------------ dgrad with the GELU derivative in its epilogue
+// gz[s] = (gy[s] . w[s]) o gelu'(z[s]): the input gradient of the Linear that CONSUMES a = gelu(z), already multiplied
+// by the activation's derivative, i.e. the gradient of the pre-activation z of the layer that PRODUCED a.  Replaces
+// bf_linear_dgrad (linear.py:104's autograd) followed by the separate GELU' pass: the [S*M, N] gradient makes one trip
+// through HBM instead of three (write da, read da + z, write gz -> read z, write gz).
+//
+// Kernel = the CTA-pair dgrad of bf_gemm_tc2.cu (A = gy K-major, B = w MN-major, UMMA 256 x 256 x 16) with the 8-warp /
+// 2-group epilogue of the fused GELU forward.  The z tile travels like an operand: the TMA warp loads its four
+// 128 x 64 boxes into dedicated buffers right after the tile's last operand stage (by then the previous tile's epilogue
+// has released them), each epilogue group multiplies its boxes by gelu'(z) read from shared memory.
+namespace dgelu {
+using namespace act;
+
+constexpr int kStages = 4;
+constexpr int kThreads = 32 * (3 + EPI_WARPS);  // warp 0 operand TMA, warp 1 MMA, warp 2 z TMA, warps 3..10 epilogue
+constexpr int Z_BYTES = BOXES * BOX_BYTES;             // 4 boxes of the tile's z rows: 64 KiB
+constexpr int OUT_BYTES = EPI_GROUPS * BOX_BYTES;      // one staging box per epilogue group
+constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + Z_BYTES + OUT_BYTES + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    bayes_gemm2_dgelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                             const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
+                             const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t z_base = smem_base + kStages * STAGE_BYTES;
+    uint8_t* const z_gen = smem_gen + kStages * STAGE_BYTES;
+    const uint32_t out_base = z_base + Z_BYTES;
+    uint8_t* const out_gen = z_gen + Z_BYTES;
+    const uint32_t bar_base = out_base + OUT_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    auto zfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 4 + b); };
+    auto zempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 4 + BOXES + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4 + 2 * BOXES);
+    volatile uint32_t* const tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(out_gen + OUT_BYTES + 8 * (2 * kStages + 4 + 2 * BOXES));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_z);
+        tma_prefetch_desc(&map_out);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 2 * EPI_WARPS);  // leader's copy: epilogue warps of both CTAs
+        }
+        for (int b = 0; b < BOXES; ++b) {
+            mbar_init(zfull_bar(b), 1);   // own CTA: the TMA thread's arrive.expect_tx
+            mbar_init(zempty_bar(b), 4);  // own CTA: the four warps of the group that reads box b
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): operands, then this CTA's z boxes =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t L = cluster_id; L < n_items; L += n_clusters) {
+                const Item it = decode_item(p, L);
+                const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M;  // this CTA's rows of A / D
+                const int j0 = it.j_blk * BLOCK_N;
+                for (int ks = 0; ks < p.k_steps; ++ks) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + A_BYTES;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    const int r0 = ks * BLOCK_K;
+                    tma_load_3d_2sm(a_dst, &map_a, full_bar(stage), r0, i0, it.s);  // gy: K-major
+#pragma unroll
+                    for (int a = 0; a < LOAD_N / ATOM_MN; ++a)                      // w: MN-major, this CTA's half
+                        tma_load_3d_2sm(b_dst + a * ATOM_BYTES, &map_b, full_bar(stage),
+                                        j0 + (int)rank * LOAD_N + a * ATOM_MN, r0, it.s);
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== z loader (both CTAs, own rows): runs ahead of the epilogue by one tile ===============
+        if (lane == 0) {
+            uint32_t zphase = 0;
+            for (int64_t L = cluster_id; L < n_items; L += n_clusters) {
+                const Item it = decode_item(p, L);
+                const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+                const int j0 = it.j_blk * BLOCK_N;
+                int n_boxes = BOXES;
+                if ((int64_t)j0 + BLOCK_N > p.J) n_boxes = (int)((p.J - j0 + BOX_COLS - 1) / BOX_COLS);
+                for (int b = 0; b < BOXES; ++b) {
+                    mbar_wait(zempty_bar(b), zphase ^ 1u);  // the previous tile's readers of this buffer are done
+                    if (b < n_boxes) {
+                        mbar_expect_tx(zfull_bar(b), BOX_BYTES);
+                        tma_load_3d(z_base + b * BOX_BYTES, &map_z, zfull_bar(b), j0 + b * BOX_COLS, i0, it.s);
+                    } else {
+                        mbar_arrive(zfull_bar(b));  // box outside the matrix: nothing to load, keep the phases in step
+                    }
+                }
+                zphase ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(false, true, 2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ks = 0; ks < p.k_steps; ++ks) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + stage * STAGE_BYTES;
+                    const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_2sm(d_tmem, operand_desc<false>(a_src, k), operand_desc<true>(b_src, k), idesc,
+                                      (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(empty_bar(stage));
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+                umma_commit_2sm(tfull_bar(acc));
+            }
+        }
+    } else {
+        // ===================== epilogue: 2 groups x 4 warps, own TMEM half; group g takes boxes b % 2 == g ==========
+        const int q = warp & 3;  // TMEM lane quarter this warp may touch (warps 3..6 and 7..10 each cover all four)
+        const int grp = (warp - 3) >> 2;
+        const int row = q * 32 + lane;
+        const bool store_thread = ((warp - 3) & 3) == 0 && lane == 0;
+        const uint32_t my_out = out_base + grp * BOX_BYTES;
+        uint8_t* const o_row = out_gen + grp * BOX_BYTES + row * 128;
+        int iter = 0;
+        for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
+            const Item it = decode_item(p, L);
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const uint32_t zphase = iter & 1;
+            const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M, j0 = it.j_blk * BLOCK_N;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            int n_boxes = BOXES;
+            if ((int64_t)j0 + BLOCK_N > p.J) n_boxes = (int)((p.J - j0 + BOX_COLS - 1) / BOX_COLS);
+            int last_b = -1;
+            for (int b = grp; b < n_boxes; b += EPI_GROUPS) last_b = b;
+            if (last_b < 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+            }
+#pragma unroll 1
+            for (int b = grp; b < BOXES; b += EPI_GROUPS) {
+                if (b >= n_boxes) {  // nothing to compute, but the z buffer's phases must advance
+                    mbar_wait(zfull_bar(b), zphase);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(zempty_bar(b));
+                    continue;
+                }
+                uint32_t r[2][32];
+                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS), r[0]);
+                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS + 32), r[1]);
+                if (store_thread) tma_store_wait_read<0>();  // this group's previous store has read its staging box
+                tmem_ld_wait();
+                if (b == last_b) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+                }
+                mbar_wait(zfull_bar(b), zphase);  // this tile's z box has landed
+                named_bar_sync_dyn(1 + grp, 128);  // ... and the staging box is free
+                const uint8_t* const z_row = z_gen + b * BOX_BYTES + row * 128;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {  // 8 columns = one 16-byte chunk of the bf16 row
+                        const int ch = h * 4 + t;
+                        const uint4 zz = *reinterpret_cast<const uint4*>(z_row + ((ch ^ (row & 7)) << 4));
+                        const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bf_f2 g2 = bf_pack2(__uint_as_float(r[h][8 * t + 2 * e]), __uint_as_float(r[h][8 * t + 2 * e + 1]));
+                            const bf_f2 z2 = bf_pack2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u));
+                            float o0, o1;
+                            bf_unpack2(bf_mul2(g2, gelu_erf_grad2(z2)), o0, o1);
+                            const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
+                            ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
+                        }
+                        *reinterpret_cast<uint4*>(o_row + ((ch ^ (row & 7)) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(zempty_bar(b));  // this warp's reads of the z box are done
+                fence_proxy_async();
+                named_bar_sync_dyn(1 + grp, 128);
+                if (store_thread) {
+                    tma_store_3d(&map_out, my_out, j0 + b * BOX_COLS, i0, it.s);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (store_thread) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace dgelu
+
 // ------------------------------------------------------------------ backward: gz = gy * gelu'(z), db = colsum(gz)
 constexpr int kBwThreads = 256, kBwWarps = 8, kBwCols = 256;  // 32 lanes x 8 bf16 columns
 
@@ -465,6 +704,38 @@ extern "C" int bf_gelu_bwd_bias_grad(const void* gy, const void* z, void* gz, fl
     gelu_bwd_bias_grad_kernel<<<grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(z),
         reinterpret_cast<__nv_bfloat16*>(gz), db, partial, counters, M, N, rps);
+    BF_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bf_linear_dgrad_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K) {
+    // same occupancy rule as the fused forward: enough 256 x 256 tiles of the [M, K] result for every SM pair
+    return bf_linear_fwd_gelu_supported(S, M, K, N);
+}
+
+// gz[s] = (gy[s] . w[s]) o gelu'(z[s])   gy [S,M,N], w [S,N,K], z / gz [S,M,K], all bf16
+extern "C" int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z, void* gz, int64_t S, int64_t M,
+                                    int64_t N, int64_t K, void* stream) {
+    namespace dg = act::dgelu;
+    BF_CHECK_ARG(gy && w && z && gz, "null pointer");
+    BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1");
+    BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "bf16 path needs K % 8 == 0 and N % 8 == 0");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ma, mb, mz, mo;
+    int rc;
+    if ((rc = tc::encode_map(&ma, gy, S, M, N, act::BLOCK_M))) return rc;  // A: K-major over r = N
+    if ((rc = tc::encode_map(&mb, w, S, N, K, tc::BLOCK_K))) return rc;    // B: MN-major, rows = r = N, cols = K
+    if ((rc = tc::encode_map(&mz, z, S, M, K, act::BLOCK_M))) return rc;
+    if ((rc = tc::encode_map(&mo, gz, S, M, K, act::BLOCK_M))) return rc;
+    act::Params p{};
+    p.S = S, p.I = M, p.J = K, p.R = N;
+    p.i_pairs = tc::cdiv(M, 2 * act::BLOCK_M), p.j_tiles = tc::cdiv(K, act::BLOCK_N), p.k_steps = tc::cdiv(N, tc::BLOCK_K);
+    BF_CUDA_OK(cudaFuncSetAttribute(dg::bayes_gemm2_dgelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    dg::SMEM_BYTES));
+    const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
+    const int64_t pairs = bf_num_sms() / 2;
+    const int grid = 2 * (int)(n_items < pairs ? n_items : pairs);
+    dg::bayes_gemm2_dgelu_kernel<<<grid, dg::kThreads, dg::SMEM_BYTES, st>>>(ma, mb, mz, mo, p);
     BF_LAUNCH_OK();
     return 0;
 }

@@ -46,18 +46,30 @@ struct Params {
     //    D = A_hi B_hi + A_hi B_lo + A_lo B_hi, three passes over the reduction into ONE fp32 TMEM accumulator
     //    (the dropped A_lo B_lo term is 2^-16 of a product): reference-precision results on the tensor cores
     int passes;
+    // reduction chunks (>= 1).  The tensor core's fp32 accumulator truncates: ~3e-8 relative per accumulated MMA, which
+    // the split-precision mode cannot afford over thousands of k-steps.  With r_chunks > 1 a work item covers
+    // `ks_per_chunk` k-steps only and its tile is ADDED to D in global memory (TMA reduce-add, a properly rounded fp32
+    // add in L2); D must be zero-filled by the caller, the bias rides on chunk 0.
+    int r_chunks, ks_per_chunk;
 };
 
 struct Item {
-    int s, i_blk, j_blk;
+    int s, i_blk, j_blk, chunk;
 };
 __device__ __forceinline__ Item decode_item(const Params& p, int64_t L) {
     Item it;
     it.j_blk = (int)(L % p.j_tiles);
-    const int64_t q = L / p.j_tiles;
+    int64_t q = L / p.j_tiles;
     it.i_blk = (int)(q % p.i_tiles);
-    it.s = (int)(q / p.i_tiles);
+    q /= p.i_tiles;
+    it.chunk = (int)(q % p.r_chunks);
+    it.s = (int)(q / p.r_chunks);
     return it;
+}
+// k-steps [first, first + count) of the reduction handled by chunk `c`
+__device__ __forceinline__ void chunk_range(const Params& p, int c, int& first, int& count) {
+    first = c * p.ks_per_chunk;
+    count = p.k_steps - first < p.ks_per_chunk ? p.k_steps - first : p.ks_per_chunk;
 }
 
 template <bool A_MN, bool B_MN, bool OUT_F32, bool HAS_BIAS>
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int64_t n_items = p.S * p.i_tiles * p.j_tiles;
+    const int64_t n_items = p.S * p.r_chunks * p.i_tiles * p.j_tiles;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -117,11 +129,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int64_t L = blockIdx.x; L < n_items; L += gridDim.x) {
                 const Item it = decode_item(p, L);
                 const int i0 = it.i_blk * BLOCK_M, j0 = it.j_blk * BLOCK_N;
+                int ks0, ks_n;
+                chunk_range(p, it.chunk, ks0, ks_n);
                 for (int pass = 0; pass < p.passes; ++pass) {
-                    // pass 0: (A_hi, B_hi)   pass 1: (A_hi, B_lo)   pass 2: (A_lo, B_hi)
-                    const CUtensorMap* const ma = pass == 2 ? &map_a_lo : &map_a;
-                    const CUtensorMap* const mb = pass == 1 ? &map_b_lo : &map_b;
-                    for (int ks = 0; ks < p.k_steps; ++ks) {
+                    // split precision: the two small cross terms first, (A_hi, B_hi) last -- the accumulator's
+                    // truncation error is relative to its magnitude, so only the last third of the MMAs pays it in full
+                    //   pass 0: (A_lo, B_hi)   pass 1: (A_hi, B_lo)   pass 2: (A_hi, B_hi);   passes == 1: (A, B)
+                    const CUtensorMap* const ma = (p.passes > 1 && pass == 0) ? &map_a_lo : &map_a;
+                    const CUtensorMap* const mb = (p.passes > 1 && pass == 1) ? &map_b_lo : &map_b;
+                    for (int ks = ks0; ks < ks0 + ks_n; ++ks) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         const uint32_t b_dst = a_dst + A_BYTES;
@@ -159,7 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                const int total_steps = p.k_steps * p.passes;  // split-precision: 3 passes into the same accumulator
+                int ks0, ks_n;
+                chunk_range(p, decode_item(p, L).chunk, ks0, ks_n);
+                const int total_steps = ks_n * p.passes;  // split-precision: 3 passes into the same accumulator
                 for (int ks = 0; ks < total_steps; ++ks) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -198,7 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int u = 0; u < BLOCK_N / (EPI_WARPS * 32); ++u) {
                     const int64_t jc = (int64_t)j0 + et + u * (EPI_WARPS * 32);
-                    bias_gen[et + u * (EPI_WARPS * 32)] = jc < p.J ? __ldg(p.bias + (int64_t)it.s * p.J + jc) : 0.0f;
+                    bias_gen[et + u * (EPI_WARPS * 32)] =
+                        (jc < p.J && it.chunk == 0) ? __ldg(p.bias + (int64_t)it.s * p.J + jc) : 0.0f;
                 }
             }
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -261,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
                 named_bar_sync<1, EPI_WARPS * 32>();
                 if (store_thread) {
-                    if (p.accumulate) tma_reduce_add_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    if (p.accumulate || p.r_chunks > 1)
+                        tma_reduce_add_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
                     else tma_store_3d(&map_out, out_base + buf * OUT_BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
                     tma_store_commit();
                 }
@@ -283,10 +303,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
                   const CUtensorMap* ma_lo = nullptr, const CUtensorMap* mb_lo = nullptr) {
     auto kern = bayes_gemm_kernel<A_MN, B_MN, OUT_F32, HAS_BIAS>;
     BF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const int64_t n_items = p.S * p.i_tiles * p.j_tiles;
+    p.passes = (ma_lo && mb_lo) ? 3 : 1;
+    if (p.r_chunks < 1) p.r_chunks = 1, p.ks_per_chunk = p.k_steps;
+    const int64_t n_items = p.S * p.r_chunks * p.i_tiles * p.j_tiles;
     const int64_t sms = bf_num_sms();
     const int grid = (int)(n_items < sms ? n_items : sms);
-    p.passes = (ma_lo && mb_lo) ? 3 : 1;
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mo, ma_lo ? *ma_lo : ma, mb_lo ? *mb_lo : mb, p);
     BF_LAUNCH_OK();
     return 0;
@@ -422,6 +443,20 @@ extern "C" int bf_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, 
     BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1");                 \
     BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "tensor-core path needs K % 8 == 0 and N % 8 == 0")
 
+// at most kX3ChunkSteps k-steps (x 4 MMAs x 3 passes) are accumulated inside the tensor core; longer reductions are
+// chunked and the chunk tiles added in global memory (Params::r_chunks), which needs a zero-filled output
+constexpr int kX3ChunkSteps = 8;
+static int x3_chunks(tc::Params& p, void* out, size_t out_bytes, cudaStream_t st) {
+    p.ks_per_chunk = kX3ChunkSteps;
+    p.r_chunks = tc::cdiv(p.k_steps, kX3ChunkSteps);
+    if (p.r_chunks <= 1) {
+        p.r_chunks = 1, p.ks_per_chunk = p.k_steps;
+        return 0;
+    }
+    BF_CUDA_OK(cudaMemsetAsync(out, 0, out_bytes, st));
+    return 0;
+}
+
 // y[s] = x[s] w[s]^T + bias[s]
 extern "C" int bf_linear_fwd_x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                                 const float* bias, float* y, int64_t S, int64_t M, int64_t N, int64_t K, void* stream) {
@@ -439,7 +474,9 @@ extern "C" int bf_linear_fwd_x3(const void* x_hi, const void* x_lo, const void* 
     p.S = S, p.I = M, p.J = N, p.R = K;
     p.i_tiles = cdiv(M, BLOCK_M), p.j_tiles = cdiv(N, BLOCK_N), p.k_steps = cdiv(K, BLOCK_K);
     p.bias = bias;
-    return launch_out<false, false>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((rc = x3_chunks(p, y, (size_t)S * M * N * sizeof(float), st))) return rc;
+    return launch_out<false, false>(ma, mb, mo, p, true, st, &mal, &mbl);
 }
 
 // dx[s] = gy[s] w[s]
@@ -458,7 +495,9 @@ extern "C" int bf_linear_dgrad_x3(const void* gy_hi, const void* gy_lo, const vo
     Params p{};
     p.S = S, p.I = M, p.J = K, p.R = N;
     p.i_tiles = cdiv(M, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(N, BLOCK_K);
-    return launch_out<false, true>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((rc = x3_chunks(p, dx, (size_t)S * M * K * sizeof(float), st))) return rc;
+    return launch_out<false, true>(ma, mb, mo, p, true, st, &mal, &mbl);
 }
 
 // dw[s] = gy[s]^T x[s]
@@ -477,5 +516,7 @@ extern "C" int bf_linear_wgrad_x3(const void* gy_hi, const void* gy_lo, const vo
     Params p{};
     p.S = S, p.I = N, p.J = K, p.R = M;
     p.i_tiles = cdiv(N, BLOCK_M), p.j_tiles = cdiv(K, BLOCK_N), p.k_steps = cdiv(M, BLOCK_K);
-    return launch_out<true, true>(ma, mb, mo, p, true, reinterpret_cast<cudaStream_t>(stream), &mal, &mbl);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((rc = x3_chunks(p, dw, (size_t)S * N * K * sizeof(float), st))) return rc;
+    return launch_out<true, true>(ma, mb, mo, p, true, st, &mal, &mbl);
 }

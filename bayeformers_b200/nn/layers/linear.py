@@ -68,12 +68,22 @@ class Linear(BayesianLayer):
         spec.bias_grad_box, self._bias_grad_box = self._bias_grad_box, None
         if runtime.grad_sinks_enabled() and torch.is_grad_enabled() and input.requires_grad:
             spec.sink = runtime.sink_for(input, create=True)
+        links = runtime.gelu_links_enabled() and torch.is_grad_enabled()
+        if links:
+            spec.gelu_in = getattr(input, "_bf_gelu_link", None)  # input = gelu(z) of a fused Bayesian Linear?
+            if self.activation == "gelu":
+                spec.gelu_out = []
         self._last_streams = (spec.w_stream, spec.b_stream)  # identity of this forward's eps draw (tests, debugging)
         y, logq, logp = ops.BayesLinear.apply(
             input, self.weight.mu, self.weight.rho,
             self.bias.mu if has_bias else None, self.bias.rho if has_bias else None,
             w_prior.mu, w_prior.rho, b_prior.mu, b_prior.rho, spec)
         self._publish(logq, logp, S, kl_grad, means=pre[7] if pre is not None and len(pre) > 7 else None)
+        if spec.gelu_out:  # fused GELU ran: let the consumer of y fold gelu'(z) into its dgrad (runtime.GeluLink)
+            link = spec.gelu_out[0]
+            y._bf_gelu_link = link
+            if y.requires_grad:
+                y.register_hook(link.check)
         return y
 
     @classmethod

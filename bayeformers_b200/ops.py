@@ -448,6 +448,8 @@ class LinearSpec:
     activation: Optional[str] = None    # None | "gelu": y = act(x w^T + b) with the activation fused where possible
     bias_grad_box: Optional[list] = None  # filled by ResidualLayerNormFn.backward with sum_m gy[s][m][:] ([S, N] fp32)
     sink: Optional[object] = None         # runtime.GradSink of the input: add dx into its buffer instead of returning it
+    gelu_in: Optional[object] = None      # runtime.GeluLink of the INPUT (it is gelu(z) of a fused layer): dgrad applies gelu'
+    gelu_out: Optional[list] = None       # filled by forward with the GeluLink of this layer's fused-GELU output
 
 
 def split_bf16x2(t: torch.Tensor):
@@ -542,7 +544,12 @@ class BayesLinear(torch.autograd.Function):
             z = y
             y = torch.nn.functional.gelu(z)
         ctx.save_for_backward(xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z)
-        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape), fused_act, use_x3)
+        link_out = None
+        if fused_act and spec.gelu_out is not None:
+            from .runtime import GeluLink
+            link_out = GeluLink(z)
+            spec.gelu_out.append(link_out)
+        ctx.meta = (spec, use_tc, M, x.dtype, tuple(x.shape), fused_act, use_x3, link_out)
         if not spec.kl_grad:
             ctx.mark_non_differentiable(logq, logp)
         if x.dtype != out_dtype:
@@ -554,7 +561,7 @@ class BayesLinear(torch.autograd.Function):
     def backward(ctx, gy, glq, glp):
         lib = _lib.load()
         xg, W, w_mu, w_rho, b_mu, b_rho, wp_mu, wp_rho, bp_mu, bp_rho, z = ctx.saved_tensors
-        spec, use_tc, M, x_dtype, x_shape, fused_act, use_x3 = ctx.meta
+        spec, use_tc, M, x_dtype, x_shape, fused_act, use_x3, link_out = ctx.meta
         S = spec.S
         N, K = w_mu.shape
         dev = xg.device
@@ -573,7 +580,11 @@ class BayesLinear(torch.autograd.Function):
         db = None
         if have_gy:
             gyc = gy.reshape(S, M, N).to(cdt).contiguous()
-            if z is not None and fused_act:
+            if z is not None and fused_act and link_out is not None and link_out.done:
+                # the consumer's dgrad already multiplied by gelu'(z) (bf_linear_dgrad_gelu): gy IS the gradient of z;
+                # only the bias gradient's column sums are left (db is None -> bf_bias_grad below)
+                link_out.done = False
+            elif z is not None and fused_act:
                 # gz = gy * gelu'(z) and the bias gradient's column sums in ONE pass over gy
                 gz = torch.empty_like(gyc)
                 db = torch.empty((S, N), dtype=torch.float32, device=dev)
@@ -593,6 +604,18 @@ class BayesLinear(torch.autograd.Function):
                 _lib.check(rc, "bf_linear_dgrad_x3")
                 stats["launches"] += 1
                 g_x = dx.view(x_shape).to(x_dtype)
+            elif (ctx.needs_input_grad[0] and use_tc and spec.gelu_in is not None and x_dtype == torch.bfloat16
+                  and spec.gelu_in.z is not None and spec.gelu_in.z.numel() == S * M * K
+                  and bool(lib.bf_linear_dgrad_gelu_supported(S, M, N, K))):
+                # x = gelu(z) of a fused layer: dx o gelu'(z) straight from the dgrad epilogue, handed on as "dx"
+                link = spec.gelu_in
+                gz_in = torch.empty((S, M, K), dtype=torch.bfloat16, device=dev)
+                rc = _timed("gemm_dgrad_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_dgrad_gelu(
+                    _ptr(gyc), _ptr(W), _ptr(link.z), _ptr(gz_in), S, M, N, K, st))
+                _lib.check(rc, "bf_linear_dgrad_gelu")
+                stats["launches"] += 1
+                g_x = gz_in.view(x_shape)
+                link.done, link.buffer = True, g_x
             elif ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 sink = spec.sink

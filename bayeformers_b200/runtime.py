@@ -100,6 +100,38 @@ class GradSink:
                                "accelerate_host_(..., grad_sinks=False)")
 
 
+class GeluLink:
+    """Hand-off between a Bayesian Linear with a fused GELU (producer of a = gelu(z)) and the Bayesian Linear that
+    consumes a.  Attached to the tensor a by the producer's forward.  The consumer's backward multiplies its input
+    gradient by gelu'(z) inside the dgrad kernel (`bf_linear_dgrad_gelu`) and returns that product AS the gradient of
+    a; `done` tells the producer's backward that what arrives is already the gradient of z, so it skips its own GELU'
+    pass.  Valid when a has no other consumer (HF BertIntermediate -> BertOutput): a tensor hook on a checks that the
+    gradient autograd finally delivers is exactly the buffer the fused kernel wrote, and raises otherwise."""
+    __slots__ = ("z", "done", "buffer")
+
+    def __init__(self, z: torch.Tensor) -> None:
+        self.z, self.done, self.buffer = z, False, None
+
+    def check(self, grad: torch.Tensor) -> None:
+        if self.done and (grad is None or self.buffer is None or grad.data_ptr() != self.buffer.data_ptr()):
+            raise RuntimeError("bayeformers_b200: the output of a GELU-fused Bayesian Linear feeds more than the next "
+                               "Bayesian Linear, so the fused GELU' dgrad is not valid for this model; call "
+                               "bayeformers_b200.runtime.enable_gelu_links(False)")
+        self.buffer = None
+
+
+_gelu_links = {"on": True}
+
+
+def enable_gelu_links(flag: bool = True) -> None:
+    """Process-wide switch of the fused GELU' dgrad (on by default; only ever active behind a fused-GELU layer)."""
+    _gelu_links["on"] = bool(flag)
+
+
+def gelu_links_enabled() -> bool:
+    return _gelu_links["on"]
+
+
 _sinks_enabled = {"on": False}
 
 

@@ -43,7 +43,7 @@ N_BATCHES = 1000  # the reference divides the KL term by len(train_loader) (bert
 CONFIGS = {
     "bert_cls": ("bayes_bert_base_train_seqs_per_s", "seq/s", 128, 4, 512, 8),
     "bert_qa": ("bayes_bert_base_qa_train_seqs_per_s", "seq/s", 384, 8, 64, 2),
-    "bert_large": ("bayes_bert_large_all_bayesian_train_seqs_per_s", "seq/s", 512, 16, 12, 1),
+    "bert_large": ("bayes_bert_large_all_bayesian_train_seqs_per_s", "seq/s", 512, 16, 8, 1),
     "mlp": ("bayes_mlp_784_512_10_train_imgs_per_s", "img/s", 0, 1, 64, 64),
     "linear": ("bayes_linear_4096_fwd_bwd_rows_per_s", "rows/s", 0, 4, 8192, 8192),
 }

@@ -223,6 +223,15 @@ int bf_linear_wgrad_x3(const void* gy_hi, const void* gy_lo, const void* x_hi, c
 int bf_linear_fwd_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K);
 int bf_linear_fwd_gelu(const void* x, const void* w, const float* bias, void* z, void* y, int64_t S, int64_t M,
                        int64_t N, int64_t K, void* stream);
+/* dgrad of the Linear that CONSUMES a = gelu(z), with the activation's derivative in its epilogue:
+ *   bf_linear_dgrad_gelu   gz[s] = (gy[s] . w[s]) o gelu'(z[s])    gy [S,M,N], w [S,N,K], z / gz [S,M,K], all bf16
+ * i.e. bf_linear_dgrad followed by the elementwise half of bf_gelu_bwd_bias_grad in one kernel: the [S*M, K] gradient
+ * crosses HBM once instead of three times (the z tile is TMA-loaded next to the operands).  The bias gradient of the
+ * layer that produced z is then bf_bias_grad(gz).  bf_linear_dgrad_gelu_supported: 1 when the CTA-pair kernel takes
+ * the shape, else the caller composes bf_linear_dgrad with bf_gelu_bwd_bias_grad. */
+int bf_linear_dgrad_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K);
+int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z, void* gz, int64_t S, int64_t M, int64_t N,
+                         int64_t K, void* stream);
 int64_t bf_gelu_bwd_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N);
 int bf_gelu_bwd_bias_grad(const void* gy, const void* z, void* gz, float* db, int64_t S, int64_t M, int64_t N,
                           void* workspace, void* stream);

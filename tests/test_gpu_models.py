@@ -82,13 +82,16 @@ def _oracle_loop(om, call, S):
 
 
 # ------------------------------------------------------------------ full-width BERT-base (BASELINE configs[2] shape)
-@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32x3", "bf16", "bf16_bench"])
 def test_bert_base_full_width_matches_oracle_s_loop(mode):
     """BERT-base (12 layers, H=768, 12 heads, FF=3072), T=128, S=4, B=2, to_bayesian(delta=0.05, freeze=True):
     per-sample logits and log-probs of ONE folded forward against the oracle's sequential S-loop on the CPU
     (pattern of examples/bert_glue.py:56-73), plus rho gradients of the first / last layers in fp32 mode.
-    bf16 mode runs the configuration bench.py times (fused GELU, fused dropout+residual+LayerNorm in eval mode,
-    native LayerNorm, gradient sinks, multi-tensor sampling switched off by the injected eps)."""
+    "bf16" = the north star's bf16 GEMM mode (bf16 operands, fp32 accumulate, fp32 host model): 1e-2.  "bf16_bench" =
+    the configuration bench.py times: additionally the host model's embeddings / LayerNorm outputs and every activation
+    between the layers travel in bf16 (cast_frequentist_), with the fused GELU, fused dropout+residual+LayerNorm (eval
+    mode here), native LayerNorm and gradient sinks on -- twelve layers of bf16 activations sit at ~1.2e-2, checked
+    against 2e-2 and reported."""
     from transformers import BertConfig, BertForSequenceClassification
     torch.manual_seed(0)
     cfg = BertConfig(num_labels=2)
@@ -98,11 +101,14 @@ def test_bert_base_full_width_matches_oracle_s_loop(mode):
     gen = torch.Generator().manual_seed(2)
     ids = torch.randint(0, cfg.vocab_size, (B, Tn), generator=gen)
     labels = torch.randint(0, 2, (B,), generator=gen)
+    bench_cfg = mode == "bf16_bench"
+    if bench_cfg:
+        mode = "bf16"
     bm = bf.to_bayesian(model, delta=0.05, freeze=True, gemm_dtype=mode)
-    if mode == "bf16":
+    if bench_cfg:
         bf.accelerate_host_(bm, layernorm=True, fuse_gelu=True, fuse_residual=True, grad_sinks=True)
     bm = bm.eval().to(DEV)
-    if mode == "bf16":
+    if bench_cfg:
         bf.cast_frequentist_(bm, torch.bfloat16)
     om = O.oracle_convert(model, 0.05, True).eval()
     assert _inject_same_eps(bm, om, S, 3) == 74
@@ -121,10 +127,11 @@ def test_bert_base_full_width_matches_oracle_s_loop(mode):
     o_nll = torch.nn.functional.cross_entropy(o_raw.mean(0), labels)
     o_loss = (o_lq.mean() - o_lp.mean()) / n_batches + o_nll
     o_loss.backward()
-    tol = BF16_TOL if mode == "bf16" else FP32_TOL
+    tol = (2 * BF16_TOL if bench_cfg else BF16_TOL) if mode == "bf16" else FP32_TOL
     e_logits = rel_err(raw.detach().cpu().numpy(), o_raw.detach().numpy())
     e_lp, e_lq = rel_err(lp_s.cpu().numpy(), o_lp.numpy()), rel_err(lq_s.cpu().numpy(), o_lq.numpy())
-    print(f"[bert-base {mode}] logits {e_logits:.2e}  log p {e_lp:.2e}  log q {e_lq:.2e}")
+    tag = "bf16_bench" if bench_cfg else mode
+    print(f"[bert-base {tag}] logits {e_logits:.2e}  log p {e_lp:.2e}  log q {e_lq:.2e}")
     assert e_logits < (tol if mode == "bf16" else 5 * tol)  # 12 encoder layers deep
     assert e_lp < FP32_TOL and e_lq < FP32_TOL                # the log-probs never depend on the GEMM dtype
     assert abs(float(loss) - float(o_loss)) <= (1e-3 if mode == "bf16" else 1e-5) * abs(float(o_loss))
@@ -135,7 +142,7 @@ def test_bert_base_full_width_matches_oracle_s_loop(mode):
                  "bert.encoder.layer.11.attention.self.value", "bert.encoder.layer.0.intermediate.dense",
                  "bert.encoder.layer.0.attention.self.query"):
         e = rel_err(ours[name].weight.rho.grad.cpu().numpy(), theirs[name].w_rho.grad.numpy())
-        print(f"[bert-base {mode}] d rho {name}: {e:.2e}")
+        print(f"[bert-base {tag}] d rho {name}: {e:.2e}")
         assert e < gtol, name
         assert ours[name].weight.mu.grad is None
 
@@ -234,8 +241,10 @@ def test_embedding_kernels_against_materialised_table(out_dtype, kl):
     rloss.backward()
     tol = 2e-6 if out_dtype == torch.float32 else 4e-3
     assert rel_err(out.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) < tol
-    assert rel_err(be.weight.rho.grad.cpu().numpy(), rho.grad.cpu().numpy()) < 1e-5
-    assert rel_err(be.weight.mu.grad.cpu().numpy(), mu.grad.cpu().numpy()) < 1e-5
+    # a bf16 output makes autograd round the incoming gradient to bf16 (2^-9 per element)
+    gtol = 1e-5 if out_dtype == torch.float32 else 4e-3
+    assert rel_err(be.weight.rho.grad.cpu().numpy(), rho.grad.cpu().numpy()) < gtol
+    assert rel_err(be.weight.mu.grad.cpu().numpy(), mu.grad.cpu().numpy()) < gtol
     if not kl:
         assert float(be.weight.rho.grad[2].abs().max()) == 0.0   # padding row
         assert float(be.weight.rho.grad[299].abs().max()) == 0.0 or (ids == 299).any()

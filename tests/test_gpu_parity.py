@@ -1207,3 +1207,82 @@ def test_tiny_bert_fp32x3_mode_within_fp32_tolerance():
     raw = out.view(S, -1, out.shape[-1])
     assert rel_err(raw.detach().float().cpu().numpy(), g["logits"]) < 5 * FP32_TOL
     assert rel_err(bm.log_prior().cpu().numpy(), g["log_prior"]) < FP32_TOL
+
+
+# ------------------------------------------------------------------ GELU' folded into the consumer's dgrad
+@pytest.mark.parametrize("S,M,N,K", [(2, 2560, 768, 3072), (4, 1280, 264, 520), (1, 4736, 64, 256)])
+def test_dgrad_gelu_kernel_vs_float64(S, M, N, K):
+    """bf_linear_dgrad_gelu: gz = (gy . w) o gelu'(z) from the dgrad epilogue (z tile TMA-loaded next to the operands)
+    against float64; ragged tiles and a tile count that is not a multiple of the SM-pair count included."""
+    lib = _lib.load()
+    if not lib.bf_linear_dgrad_gelu_supported(S, M, N, K):
+        pytest.skip("shape below the CTA-pair kernel's occupancy threshold")
+    gen = torch.Generator().manual_seed(S + M + N + K)
+    gy = torch.randn(S, M, N, generator=gen).bfloat16().to(DEV)
+    w = (torch.randn(S, N, K, generator=gen) * 0.05).bfloat16().to(DEV)
+    z = (torch.randn(S, M, K, generator=gen) * 1.5).bfloat16().to(DEV)
+    gz = torch.full((S, M, K), float("nan"), dtype=torch.bfloat16, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.bf_linear_dgrad_gelu(gy.data_ptr(), w.data_ptr(), z.data_ptr(), gz.data_ptr(), S, M, N, K, st), "dgrad_gelu")
+    zd = z.double()
+    dgelu = 0.5 * (1 + torch.erf(zd / np.sqrt(2))) + zd * torch.exp(-0.5 * zd * zd) / np.sqrt(2 * np.pi)
+    want = torch.einsum("smn,snk->smk", gy.double(), w.double()) * dgelu
+    assert torch.isfinite(gz.float()).all()
+    assert rel_err(gz.float().cpu().numpy(), want.cpu().numpy()) < 4e-3  # bf16 rounding of the result
+    # bit-identical to the unfused composition's arithmetic up to the intermediate bf16 rounding of dx
+    dx = torch.empty(S, M, K, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st), "dgrad")
+    assert rel_err(gz.float().cpu().numpy(), (dx.double() * dgelu).cpu().numpy()) < 6e-3
+
+
+def test_ffn_block_with_and_without_gelu_link():
+    """up(gelu) -> down: with the GeluLink the down layer's dgrad applies gelu'(z) and the up layer skips its GELU' pass;
+    outputs are identical and every gradient agrees with the unlinked path to bf16 rounding.  A second consumer of the
+    activation must be detected."""
+    import copy
+    torch.manual_seed(3)
+    H, F_, S, B = 768, 3072, 2, 1280
+    up, down = torch.nn.Linear(H, F_), torch.nn.Linear(F_, H)
+    bf.manual_seed(5)
+    a_up = bnn.Linear.from_frequentist(up, delta=0.05, freeze=True).to(DEV)
+    a_down = bnn.Linear.from_frequentist(down, delta=0.05, freeze=True).to(DEV)
+    for l in (a_up, a_down):
+        l.gemm_dtype = torch.bfloat16
+    a_up.activation = "gelu"
+    x = torch.randn(S * B, H, device=DEV).bfloat16()
+    gy = torch.randn(S * B, H, device=DEV).bfloat16()
+    results = {}
+    for linked in (True, False):
+        bf.runtime.enable_gelu_links(linked)
+        try:
+            for l in (a_up, a_down):
+                l.weight.step = l.bias.step = 0
+                l.zero_grad(set_to_none=True)
+            xa = x.clone().requires_grad_()
+            ops.enable_kernel_timing(True)
+            with bf.mc_samples(S):
+                a = a_up(xa)
+                assert (getattr(a, "_bf_gelu_link", None) is not None) == linked
+                y = a_down(a)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            ran = ops.kernel_timing_summary()
+            ops.enable_kernel_timing(False)
+            assert ("gelu_bwd_bias_grad" in ran) == (not linked)
+            results[linked] = (y.detach().clone(), xa.grad.clone(), a_up.weight.rho.grad.clone(), a_up.bias.rho.grad.clone(),
+                               a_down.weight.rho.grad.clone())
+        finally:
+            ops.enable_kernel_timing(False)
+            bf.runtime.enable_gelu_links(True)
+    assert torch.equal(results[True][0], results[False][0])
+    for got, want in zip(results[True][1:], results[False][1:]):
+        assert rel_err(got.float().cpu().numpy(), want.float().cpu().numpy()) < 6e-3
+    # a second consumer of the activation: the hook must refuse
+    for l in (a_up, a_down):
+        l.zero_grad(set_to_none=True)
+    xa = x.clone().requires_grad_()
+    with bf.mc_samples(S):
+        a = a_up(xa)
+        y = a_down(a)
+    with pytest.raises(RuntimeError, match="fused GELU"):
+        (y.float().sum() + a.float().sum()).backward()
