@@ -470,6 +470,8 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
                 step_body(static_inp, static_tgt)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        optim.zero_grad(set_to_none=True) if not sync.bucketed else None
+        torch.cuda.empty_cache()  # the eager warm-up's activation blocks: the graph gets its own pool
         graph = torch.cuda.CUDAGraph()
         if not sync.bucketed:
             optim.zero_grad(set_to_none=True)
@@ -546,10 +548,23 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     launches = ops.stats["launches"] - launches0
     kern = ops.kernel_timing_summary()
     ops.enable_kernel_timing(False)
+    # ---- timed region 2: end to end through the public API with HOST buffers (e2e)
+    ms_e2e = None
+    if e2e and not args.profile:
+        barrier()
+        ms_e2e = run_steps(steps, True)
+        barrier()
+
     kern_steps = steps
     if use_graph and timing:
-        # CUDA events cannot bracket kernels inside a replayed graph: take the per-kernel durations from
-        # eager, instrumented executions of the same step right after the timed region
+        # CUDA events cannot bracket kernels inside a replayed graph: take the per-kernel durations from eager,
+        # instrumented executions of the same step after the timed regions.  The graph (and its private memory pool,
+        # half of the GPU at the default batch) is released first.
+        static_out = None
+        graph = None
+        step = step_body
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
         kern_steps = 2
         step_body(inp_dev, tgt_dev)
         barrier()
@@ -559,13 +574,6 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
         barrier()
         kern = ops.kernel_timing_summary()
         ops.enable_kernel_timing(False)
-
-    # ---- timed region 2: end to end through the public API with HOST buffers (e2e)
-    ms_e2e = None
-    if e2e and not args.profile:
-        barrier()
-        ms_e2e = run_steps(steps, True)
-        barrier()
     if world > 1:
         t = torch.tensor([ms, ms_e2e if ms_e2e is not None else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
