@@ -47,8 +47,8 @@ SIGNATURES = {
                                    c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "bf_sample_kl_multi_chunk_quads": (c_int32, []),
     "bf_sample_kl_multi_workspace_bytes": (c_int64, [c_int64]),
-    "bf_sample_kl_fwd_multi": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_uint64, c_uint32,
-                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bf_sample_kl_fwd_multi": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_uint64,
+                                         c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_sample_kl_bwd": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                    c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_int32, c_uint64,
                                    c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

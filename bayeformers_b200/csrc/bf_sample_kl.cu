@@ -716,29 +716,24 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
     }
 }
 
-template <int SC>
-__global__ void __launch_bounds__(kThreads) sample_kl_multi_kernel(const MultiParams mp) {
+// One instantiation per prior kind (a block skips the chunks of other kinds): the scale-mixture arithmetic needs ~30
+// registers more than the Gaussian one, and a kernel that inlines both runs every tensor at the larger footprint
+// (96 registers = 2 blocks per SM; the Gaussian / no-prior instantiations fit 3).
+template <int SC, int PRIOR>
+__global__ void __launch_bounds__(kThreads, (PRIOR == BF_PRIOR_MIXTURE || SC > 4) ? 2 : 3) sample_kl_multi_kernel(const MultiParams mp) {
     __shared__ float red[2 * kMaxSC][kThreads / 32];
     const uint32_t step = mp.step + (mp.step_ptr ? __ldg(mp.step_ptr) : 0u);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = blockIdx.x; c < mp.n_chunks; c += gridDim.x) {
         const int2 ch = __ldg(mp.chunks + c);
         const bf_tensor_desc d = mp.descs[ch.x];
+        if (d.prior_kind != PRIOR) continue;  // uniform per block
         float q_acc[SC], p_acc[SC];
 #pragma unroll
         for (int s = 0; s < SC; ++s) q_acc[s] = p_acc[s] = 0.0f;
         const int64_t qb = (int64_t)ch.y;
-        const bool bf = d.w_dtype == BF_BF16;
-        if (d.prior_kind == BF_PRIOR_GAUSSIAN) {
-            if (bf) multi_chunk<BF_PRIOR_GAUSSIAN, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
-            else multi_chunk<BF_PRIOR_GAUSSIAN, float, SC>(d, mp, qb, step, q_acc, p_acc);
-        } else if (d.prior_kind == BF_PRIOR_MIXTURE) {
-            if (bf) multi_chunk<BF_PRIOR_MIXTURE, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
-            else multi_chunk<BF_PRIOR_MIXTURE, float, SC>(d, mp, qb, step, q_acc, p_acc);
-        } else {
-            if (bf) multi_chunk<BF_PRIOR_NONE, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
-            else multi_chunk<BF_PRIOR_NONE, float, SC>(d, mp, qb, step, q_acc, p_acc);
-        }
+        if (d.w_dtype == BF_BF16) multi_chunk<PRIOR, __nv_bfloat16, SC>(d, mp, qb, step, q_acc, p_acc);
+        else multi_chunk<PRIOR, float, SC>(d, mp, qb, step, q_acc, p_acc);
 #pragma unroll
         for (int s = 0; s < SC; ++s) {
             const float a = bf_warp_sum(q_acc[s]);
@@ -756,6 +751,16 @@ __global__ void __launch_bounds__(kThreads) sample_kl_multi_kernel(const MultiPa
             mp.partials[(int64_t)c * 2 * SC + threadIdx.x] = t;
         }
         __syncthreads();
+    }
+}
+
+template <int PRIOR>
+static void launch_multi(const MultiParams& mp, int sc, int grid, cudaStream_t st) {
+    switch (sc) {
+        case 1: sample_kl_multi_kernel<1, PRIOR><<<grid, kThreads, 0, st>>>(mp); break;
+        case 2: sample_kl_multi_kernel<2, PRIOR><<<grid, kThreads, 0, st>>>(mp); break;
+        case 4: sample_kl_multi_kernel<4, PRIOR><<<grid, kThreads, 0, st>>>(mp); break;
+        default: sample_kl_multi_kernel<8, PRIOR><<<grid, kThreads, 0, st>>>(mp); break;
     }
 }
 
@@ -985,11 +990,12 @@ extern "C" int64_t bf_sample_kl_multi_workspace_bytes(int64_t n_chunks) {
 }
 
 extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t* chunks, int32_t n_chunks,
-                                      const int32_t* slot_ranges, int32_t n_slots, int32_t S, uint64_t seed,
-                                      uint32_t step, float* logq_out, float* logp_out, void* workspace, void* w_base,
-                                      void* stream) {
+                                      const int32_t* slot_ranges, int32_t n_slots, int32_t prior_mask, int32_t S,
+                                      uint64_t seed, uint32_t step, float* logq_out, float* logp_out, void* workspace,
+                                      void* w_base, void* stream) {
     BF_CHECK_ARG(descs && chunks && slot_ranges && logq_out && logp_out && workspace, "null pointer");
     BF_CHECK_ARG(n_chunks >= 1 && n_slots >= 1 && S >= 1, "bad counts");
+    BF_CHECK_ARG(prior_mask > 0 && prior_mask < 8, "prior_mask: bit k set when a descriptor has prior_kind == k");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     MultiParams mp{};
     mp.descs = descs, mp.chunks = reinterpret_cast<const int2*>(chunks), mp.n_chunks = n_chunks;
@@ -1004,12 +1010,9 @@ extern "C" int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t
         int sc = 1;
         while (sc * 2 <= kMaxSC && s0 + sc * 2 <= S) sc *= 2;
         mp.s0 = s0;
-        switch (sc) {
-            case 1: sample_kl_multi_kernel<1><<<grid, kThreads, 0, st>>>(mp); break;
-            case 2: sample_kl_multi_kernel<2><<<grid, kThreads, 0, st>>>(mp); break;
-            case 4: sample_kl_multi_kernel<4><<<grid, kThreads, 0, st>>>(mp); break;
-            default: sample_kl_multi_kernel<8><<<grid, kThreads, 0, st>>>(mp); break;
-        }
+        if (prior_mask & (1 << BF_PRIOR_MIXTURE)) launch_multi<BF_PRIOR_MIXTURE>(mp, sc, grid, st);
+        if (prior_mask & (1 << BF_PRIOR_GAUSSIAN)) launch_multi<BF_PRIOR_GAUSSIAN>(mp, sc, grid, st);
+        if (prior_mask & (1 << BF_PRIOR_NONE)) launch_multi<BF_PRIOR_NONE>(mp, sc, grid, st);
         BF_LAUNCH_OK();
         sample_kl_multi_finish_kernel<<<n_slots, 256, 0, st>>>(mp.partials, reinterpret_cast<const int2*>(slot_ranges), sc,
                                                              s0, S, logq_out, logp_out);

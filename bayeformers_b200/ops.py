@@ -296,6 +296,7 @@ class SamplePair(torch.autograd.Function):
         has_bias = b_mu is not None
         if spec.presampled is not None:
             w, b, logq, logp = spec.presampled
+            spec.presampled = None  # outputs of this node must not be reachable from its own ctx (see BayesLinear)
         else:
             logq = torch.empty(S, dtype=torch.float32, device=dev)
             logp = torch.empty(S, dtype=torch.float32, device=dev)
@@ -377,6 +378,7 @@ class EmbeddingFn(torch.autograd.Function):
         prior = PriorSpec(spec.prior.kind, spec.prior.pi, spec.prior.sigma1, spec.prior.sigma2, prior_mu, prior_rho)
         if spec.presampled is not None:
             logq, logp = spec.presampled
+            spec.presampled = None  # outputs of this node must not be reachable from its own ctx (see BayesLinear)
         else:
             logq = torch.empty(S, dtype=torch.float32, device=dev)
             logp = torch.empty(S, dtype=torch.float32, device=dev)
@@ -500,6 +502,10 @@ class BayesLinear(torch.autograd.Function):
 
         if spec.presampled is not None:
             W, b, logq, logp = spec.presampled
+            # `spec` is kept by ctx for backward and logq / logp become OUTPUTS of this node: leaving them in the spec
+            # would make the node reference itself (node -> spec -> output -> grad_fn = node), a cycle only the garbage
+            # collector frees -- one sampled-weight arena plus the saved activations leaked per step
+            spec.presampled = None
             if W.dtype != cdt or (has_bias and b is None):
                 raise RuntimeError("presampled weights do not match this layer's GEMM mode")
         else:
@@ -615,7 +621,7 @@ class BayesLinear(torch.autograd.Function):
                 _lib.check(rc, "bf_linear_dgrad_gelu")
                 stats["launches"] += 1
                 g_x = gz_in.view(x_shape)
-                link.done, link.buffer = True, g_x
+                link.done, link.buffer, link.z = True, g_x, None
             elif ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 sink = spec.sink

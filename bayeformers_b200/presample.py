@@ -108,6 +108,9 @@ class Presampler:
         self.offsets = offsets
         self.tensors = tensors
         self.n_chunks, self.n_slots = len(chunks) // 2, len(slot_ranges) // 2
+        self.prior_mask = 0
+        for _, _, pr, _ in tensors:
+            self.prior_mask |= 1 << pr.kind
         raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
         self.d_descs = raw.to(dev)
         self.d_chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
@@ -151,12 +154,12 @@ class Presampler:
                           (4 if pr.rho is not None else 0)
             nbytes += n * (8 + p_bytes + (0 if dt is None else S * (2 if dt == torch.bfloat16 else 4)))
         rc = ops._timed("sample_kl_fwd", nbytes, dev, lambda: lib.bf_sample_kl_fwd_multi(
-            self.d_descs.data_ptr(), self.d_chunks.data_ptr(), self.n_chunks, self.d_slots.data_ptr(), self.n_slots, S,
-            seed, step, logq.data_ptr(), logp.data_ptr(), self.d_ws.data_ptr(), arena.data_ptr(),
+            self.d_descs.data_ptr(), self.d_chunks.data_ptr(), self.n_chunks, self.d_slots.data_ptr(), self.n_slots,
+            self.prior_mask, S, seed, step, logq.data_ptr(), logp.data_ptr(), self.d_ws.data_ptr(), arena.data_ptr(),
             ops._stream(dev)))
         _lib.check(rc, "bf_sample_kl_fwd_multi")
         n_sc = bin(S).count("1") if S <= 8 else (S // 8 + bin(S % 8).count("1"))
-        ops.stats["launches"] += 2 * n_sc
+        ops.stats["launches"] += (bin(self.prior_mask).count("1") + 1) * n_sc
         # hand every layer its slice
         means = (None, None)
         if S > 1:  # 0-dim values of the layers' registered scalars (see BayesianLayer._publish), all layers at once

@@ -123,6 +123,8 @@ int bf_sample_kl_fwd(const float* mu, const float* rho, int32_t prior_kind, cons
  *              one tensor, entries of one output slot contiguous
  * slot_ranges  DEVICE int32 pairs {first chunk, last chunk + 1} per output slot; a slot
  *              is what one (logq, logp) pair sums over -- typically weight + bias of a layer
+ * prior_mask   bit k set when some descriptor has prior_kind == k (the descriptors live on the device; one kernel
+ *              instantiation per prior kind present is launched over the chunk list)
  * logq_out, logp_out  [n_slots][S] fp32 (overwritten)
  * step         added to every descriptor's own `step`
  * w_base       NULL, or a base address: descriptors' `w_out` are then byte OFFSETS from it
@@ -148,8 +150,8 @@ typedef struct bf_tensor_desc {
 int32_t bf_sample_kl_multi_chunk_quads(void);
 int64_t bf_sample_kl_multi_workspace_bytes(int64_t n_chunks);
 int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t* chunks, int32_t n_chunks,
-                           const int32_t* slot_ranges, int32_t n_slots, int32_t S, uint64_t seed, uint32_t step,
-                           float* logq_out, float* logp_out, void* workspace, void* w_base, void* stream);
+                           const int32_t* slot_ranges, int32_t n_slots, int32_t prior_mask, int32_t S, uint64_t seed,
+                           uint32_t step, float* logq_out, float* logp_out, void* workspace, void* w_base, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Backward of the above (stand-alone form): eps is RECOMPUTED from the seed.

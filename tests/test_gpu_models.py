@@ -383,3 +383,45 @@ def test_two_rank_nccl_batch_and_sample_sharding():
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
     assert "MULTIRANK OK" in r.stdout
+
+
+# ------------------------------------------------------------------ no per-step memory growth
+def test_eager_training_steps_do_not_leak_device_memory():
+    """Eager training steps with every extension on (multi-tensor sampling, fused blocks, gradient sinks, GELU links,
+    kl_grad): the device memory in use after a step must not grow from step to step WITHOUT help from the garbage
+    collector.  (An autograd node whose ctx reaches one of its own outputs is a reference cycle; one such cycle used to
+    pin a whole sampled-weight arena and the GELU pre-activations of every step.)"""
+    import gc
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=100, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                     intermediate_size=1024, max_position_embeddings=32, num_labels=2)
+    model = BertForSequenceClassification(cfg)
+    bm = bf.to_bayesian(model, delta=0.05, freeze=True, layers=bnn.TORCH2BAYE_ALL, gemm_dtype="bf16", kl_grad=True)
+    bf.accelerate_host_(bm, fuse_residual=True, grad_sinks=True)
+    bm = bm.to(DEV).train()
+    bf.enable_presample(bm)
+    bf.cast_frequentist_(bm, torch.bfloat16)
+    opt = bf.optim.ClipAdamW([p for p in bm.parameters() if p.requires_grad], lr=1e-4, max_grad_norm=1.0)
+    S, B, Tn = 4, 64, 32  # 8192 folded rows: enough 256 x 256 tiles for the fused GELU / GELU' kernels
+    ids = torch.randint(0, 100, (B, Tn), device=DEV)
+    labels = torch.randint(0, 2, (B,), device=DEV)
+    used = []
+    gc.collect()
+    gc.disable()
+    try:
+        for _ in range(5):
+            opt.zero_grad()
+            with bf.mc_samples(S):
+                logits = bm(input_ids=ids.repeat(S, 1)).logits
+            loss = torch.nn.functional.cross_entropy(logits.float().view(S, B, -1).mean(0), labels)
+            loss = loss + (bm.log_variational_posterior().mean() - bm.log_prior().mean()) / 100
+            loss.backward()
+            opt.step()
+            del logits, loss
+            torch.cuda.synchronize()
+            used.append(torch.cuda.memory_allocated())
+    finally:
+        gc.enable()
+        bf.runtime.enable_grad_sinks(False)
+    assert used[4] == used[3] == used[2], used
