@@ -79,6 +79,8 @@ def parse():
     ap.add_argument("--host-ln", type=int, default=1)
     ap.add_argument("--fuse-residual", type=int, default=1)
     ap.add_argument("--grad-sinks", type=int, default=1)
+    ap.add_argument("--gelu-links", type=int, default=1,
+                    help="fold GELU' into the dgrad epilogue of the Linear that consumes a fused-GELU layer's output")
     ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
     ap.add_argument("--profile", action="store_true",
                     help="for runs under ncu only: allow < 3 warm-up steps, skip the e2e and CPU legs (numbers invalid)")
@@ -362,7 +364,9 @@ def workload_config(args, world):
             "global_batch": global_batch, "gemm": args.gemm, "kl_grad": bool(args.kl_grad),
             "optimizer": "bf.optim.ClipAdamW (fused clip + AdamW)" if args.fused_optim else "clip_grad_norm_ + torch AdamW(fused)",
             "sampling": "multi-tensor (1 launch per forward)" if args.presample else "per layer",
-            "ffn_gelu": ("fused into bnn.Linear (epilogue + GELU'/bias-grad pass)" if args.fuse_gelu else "torch") if bert else "n/a",
+            "ffn_gelu": (("fused into bnn.Linear (forward epilogue; GELU' in the consumer's dgrad epilogue)" if args.gelu_links
+                          else "fused into bnn.Linear (forward epilogue + GELU'/bias-grad pass)")
+                         if args.fuse_gelu else "torch") if bert else "n/a",
             "host_layernorm": ("native kernels (bf_layernorm_*)" if args.host_ln else "torch") if bert else "n/a",
             "output_blocks": ("dropout + residual + LayerNorm fused (bf_resln_*, Philox mask, bias grad handed to the Linear)"
                               if args.fuse_residual else "torch dropout + add, separate LayerNorm") if bert else "n/a",
@@ -386,6 +390,7 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     bert = args.config.startswith("bert")
     model, cfg = wl.build()
     bf.manual_seed(1234)
+    bf.runtime.enable_gelu_links(bool(args.gelu_links))
     layers = bnn.TORCH2BAYE_ALL if args.config == "bert_large" else None
     bm = bf.to_bayesian(model, delta=0.05, freeze=(args.config != "mlp"), gemm_dtype=gemm, kl_grad=bool(args.kl_grad),
                         layers=layers)
