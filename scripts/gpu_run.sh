@@ -24,6 +24,23 @@ for stage in "$@"; do
       for v in 0 1 0 1; do
         timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --gelu-links $v > gpurun_out/bench_links$v.json 2> gpurun_out/bench_links$v.err; echo "links=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_links$v.json | head -2
       done ;;
+    multi2)
+      scripts/gpu_run.sh tests2
+      TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+      for spec in "2 bert_cls batch" "2 bert_qa samples" "2 bert_qa batch" "1 bert_qa batch"; do
+        set -- $spec
+        NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 900 $TR --nproc-per-node $1 --master-port 2950$1 bench.py --gpus $1 --config $2 --shard $3 --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/scale_$2_$3_n$1.json 2> gpurun_out/scale_$2_$3_n$1.err; echo "N=$1 $2 $3 rc $?"
+        grep -m3 -E "NCCL INFO (comm|Connected|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
+        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json | head -1
+      done ;;
+    multi8)
+      TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+      for spec in "8 bert_qa samples" "8 bert_qa batch" "4 bert_qa samples" "4 bert_qa batch" "8 bert_cls batch" "4 bert_cls batch" "8 bert_large samples"; do
+        set -- $spec
+        NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 900 $TR --nproc-per-node $1 --master-port 2951$1 bench.py --gpus $1 --config $2 --shard $3 --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/scale_$2_$3_n$1.json 2> gpurun_out/scale_$2_$3_n$1.err; echo "N=$1 $2 $3 rc $?"
+        grep -m2 -E "NCCL INFO (comm|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
+        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json | head -1
+      done ;;
     micro)    timeout -k 10 600 python scripts/gpu_microbench.py 2>&1 | tail -40 ;;
     *) echo "unknown stage $stage" ;;
   esac
