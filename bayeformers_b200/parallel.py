@@ -45,31 +45,38 @@ class _Bucket:
 
 
 class GradSync:
-    """Overlapped gradient reduction for a model containing Bayesian layers.
+    """Gradient reduction for a model containing Bayesian layers.
 
         sync = GradSync(model)            # after to_bayesian(...).to(device)
         sync.zero_grad()                  # instead of optimizer.zero_grad() (bucketed mode keeps .grad alive)
         loss.backward()
         sync.finish()                     # before clip / optimizer.step()
 
-    bucketed (default when world_size > 1): the gradients of all trainable tensors live in at most `buckets` flat
-    buffers per dtype, laid out in reverse parameter order (~ the order backward produces them); every `p.grad` is a
-    persistent view into its bucket, autograd accumulates into it in place, and the moment the last tensor of a bucket
-    has its gradient the WHOLE bucket is all-reduced asynchronously -- a handful of large NCCL launches per step that
-    overlap the rest of backward, instead of one launch per tensor (74 for BERT-base) whose channel CTAs each hold
-    SMs the persistent one-CTA-per-SM contractions then wait for.  `zero_grad()` is one memset per bucket.
-    Unbucketed (`bucketed=False`, the round-1 behaviour): tensors with at least `large_numel` elements are
-    all-reduced in place from a post-accumulate-grad hook, smaller ones flattened into a single message in `finish()`.
+    bucketed (default when world_size > 1): after the FIRST backward the gradients of the tensors that actually received
+    one (MOPED priors are trainable-looking Parameters that never do, quirk Q5) move into at most `buckets` flat
+    buffers per dtype; from then on every such `p.grad` is a persistent view into its bucket, autograd accumulates in
+    place, `zero_grad()` is one memset per bucket and `finish()` all-reduces a handful of large messages -- instead of one
+    NCCL launch per tensor (74 for BERT-base).
+    overlap=False (default): the buckets are reduced in `finish()`, after backward.  The whole message of a BERT-base
+    step (~390 MB) is about 1 ms over NVLink 5 / NVSwitch, while a collective launched DURING backward shares the SMs
+    with persistent one-CTA-per-SM contractions: the CTAs of a contraction that cannot be scheduled next to NCCL's
+    channel CTAs start late, and the contraction ends late by as much as the collective lasts (measured: +8..11 ms per
+    step for the overlapped variants).  overlap=True launches each bucket's all-reduce from the post-accumulate hook of
+    its last tensor.
+    bucketed=False (the round-1 behaviour): tensors with at least `large_numel` elements are all-reduced in place from a
+    post-accumulate-grad hook, smaller ones flattened into a single message in `finish()`.
     `average=False` sums instead (sample sharding).  With world_size == 1 everything is a no-op.
-    Gradient accumulation over several backward passes per step is not supported (each finished backward reduces).
+    Gradient accumulation over several backward passes per step is not supported (each `finish()` reduces what is there).
     """
 
     def __init__(self, model: torch.nn.Module, group=None, large_numel: int = 1 << 18, average: bool = True,
-                 bucketed: Optional[bool] = None, buckets: int = 6):
+                 bucketed: Optional[bool] = None, buckets: int = 4, overlap: bool = False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.large_numel = int(large_numel)
         self.average = average
+        self.overlap = bool(overlap)
+        self.n_buckets = int(buckets)
         self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self._handles = []
         self._small: List[torch.nn.Parameter] = []
@@ -79,9 +86,8 @@ class GradSync:
         self.bucketed = (self.world > 1) if bucketed is None else (bool(bucketed) and self.world > 1)
         self.buckets: List[_Bucket] = []
         self._bucket_of = {}
+        self._order: List[torch.nn.Parameter] = []  # first backward: the order gradients appear in
         if self.world > 1:
-            if self.bucketed:
-                self._make_buckets(int(buckets))
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(
                     self._on_grad_bucketed if self.bucketed else self._on_grad))
@@ -93,13 +99,15 @@ class GradSync:
         return dist.ReduceOp.SUM, self.average
 
     # ---- bucketed mode ---------------------------------------------------------------------
-    def _make_buckets(self, n_buckets: int) -> None:
+    def _make_buckets(self) -> None:
+        """Called by the first finish(): `self._order` lists the tensors that received a gradient, in the order backward
+        produced them.  Their gradients move into flat buffers (values kept)."""
         by_dtype = {}
-        for p in reversed(self.params):  # reverse registration order ~ the order backward finishes them
-            by_dtype.setdefault((p.dtype, p.device), []).append(p)
+        for p in self._order:
+            by_dtype.setdefault((p.grad.dtype, p.grad.device), []).append(p)
         for (dtype, dev), plist in by_dtype.items():
             total = sum(p.numel() for p in plist)
-            target = max((total + n_buckets - 1) // n_buckets, 1)
+            target = max((total + self.n_buckets - 1) // self.n_buckets, 1)
             groups, cur, cur_n = [], [], 0
             for p in plist:
                 cur.append(p)
@@ -117,25 +125,36 @@ class GradSync:
                     n += (p.numel() + 7) // 8 * 8
                 flat = torch.zeros(n, dtype=dtype, device=dev)
                 for p, o in zip(g, offs):
-                    p.grad = flat[o:o + p.numel()].view_as(p)
+                    view = flat[o:o + p.numel()].view_as(p)
+                    view.copy_(p.grad)
+                    p.grad = view
                 b = _Bucket(flat, g)
+                b.pending = 0  # this step's gradients are complete
                 self.buckets.append(b)
                 for p in g:
                     self._bucket_of[id(p)] = b
 
     def _on_grad_bucketed(self, p: torch.nn.Parameter) -> None:
-        b = self._bucket_of[id(p)]
+        b = self._bucket_of.get(id(p))
+        if b is None:
+            if not self.buckets:
+                self._order.append(p)  # first backward: remember who gets gradients, and in which order
+            return
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and self.overlap:
             op, scale_after = self._op()
             b.handle = (dist.all_reduce(b.flat, op=op, group=self.group, async_op=True), scale_after)
             self._bytes += b.flat.numel() * b.flat.element_size()
 
     def zero_grad(self) -> None:
-        """Bucketed mode: one memset per bucket (the .grad views stay alive).  Otherwise: set every .grad to None."""
-        if self.bucketed:
+        """Bucketed mode: one memset per bucket (the .grad views stay alive), tensors outside the buckets get None.
+        Otherwise: set every .grad to None."""
+        if self.bucketed and self.buckets:
             for b in self.buckets:
                 b.flat.zero_()
+            for p in self.params:
+                if id(p) not in self._bucket_of:
+                    p.grad = None
         else:
             for p in self.params:
                 p.grad = None
@@ -154,19 +173,28 @@ class GradSync:
             self._small.append(p)
 
     def finish(self) -> None:
-        """Wait for the in-flight reductions (and reduce what has not been launched yet)."""
+        """Reduce (or wait for) this step's gradients."""
         if self.world == 1:
             return
         if self.bucketed:
+            if not self.buckets:
+                self._make_buckets()
+            op, scale_after = self._op()
             for b in self.buckets:
-                if b.handle is None:  # a tensor of this bucket got no gradient this step: reduce it now
-                    op, scale_after = self._op()
+                if b.handle is None:
                     b.handle = (dist.all_reduce(b.flat, op=op, group=self.group, async_op=True), scale_after)
                     self._bytes += b.flat.numel() * b.flat.element_size()
-            for b in self.buckets:
-                h, scale_after = b.handle
-                h.wait()
+            # a tensor that received its first gradient after the buckets were built (rare): reduced on its own
+            late = [p for p in self.params if p.grad is not None and id(p) not in self._bucket_of]
+            for p in late:
+                dist.all_reduce(p.grad, op=op, group=self.group)
                 if scale_after:
+                    p.grad.div_(self.world)
+                self._bytes += p.grad.numel() * p.grad.element_size()
+            for b in self.buckets:
+                h, sa = b.handle
+                h.wait()
+                if sa:
                     b.flat.div_(self.world)
                 b.handle, b.pending = None, len(b.params)
             self.bytes_last_step, self._bytes = self._bytes, 0

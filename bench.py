@@ -698,9 +698,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's channel CTAs share the SMs with persistent one-CTA-per-SM contractions: keep them few (the message is
-        # a handful of 50-100 MB buckets over NVSwitch, far from needing every channel)
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     if args.shard == "samples" and args.samples % world != 0:
         raise SystemExit(f"--shard samples needs S ({args.samples}) to be a multiple of the number of GPUs ({world})")
@@ -815,9 +812,11 @@ def run_ours(args):
             "gpu_launches": res["launches"], "clocks": res["clocks"], "execution": res["graph_note"],
             "hbm_peak_gb": res["hbm_peak_gb"], "grad_allreduce_bytes_per_step": res["allreduce_bytes"],
             "grad_allreduce": {"launches_per_step": res["allreduce_launches"], "ms_alone": res["allreduce_alone_ms"],
-                               "how": "flat gradient buckets all-reduced as they fill during backward (NCCL, captured in "
-                                      "the graph); ms_alone = the same buckets all-reduced with nothing else running, "
-                                      "CUDA events, after the timed region", "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}}
+                               "how": "the gradients that exist live in flat buckets, all-reduced after backward (NCCL, "
+                                      "captured in the graph; not overlapped: a collective next to persistent "
+                                      "one-CTA-per-SM contractions delays them by more than it saves); ms_alone = the "
+                                      "same buckets all-reduced with nothing else running, CUDA events, after the timed "
+                                      "region"}}
     print(json.dumps(line), flush=True)
     leave()
 

@@ -11,7 +11,7 @@ for stage in "$@"; do
     tests)    timeout -k 10 1500 python -m pytest tests -m gpu -q --maxfail=20 -x -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log ;;
     tests_all) timeout -k 10 1800 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider -s > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log ;;
     tests_models) timeout -k 10 1800 python -m pytest tests/test_gpu_models.py -m gpu -q --maxfail=30 -p no:cacheprovider -s > gpurun_out/pytest_gpu_models.log 2>&1; grep -E "^\[|passed|failed|^E  |Error" gpurun_out/pytest_gpu_models.log | head -60 ;;
-    tests2)   timeout -k 10 900 python -m pytest tests/test_gpu_models.py -m gpu -q -k two_rank -s -p no:cacheprovider 2>&1 | tail -30 | tee gpurun_out/pytest_gpu2.log ;;
+    tests2)   timeout -k 10 900 python -m pytest tests/test_gpu_models.py -m gpu -q -k two_rank -s -p no:cacheprovider > gpurun_out/pytest_gpu2.log 2>&1; grep -E "MULTIRANK|Error|assert|passed|failed" gpurun_out/pytest_gpu2.log | head -20 ;;
     smoke)    timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ;;
     bench)    timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "rc $?"; cut -c1-1500 gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err ;;
     bench_quick) timeout -k 10 900 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "rc $?"; cut -c1-400 gpurun_out/bench_quick.json; python scripts/bench_kernels.py gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err ;;
@@ -31,7 +31,7 @@ for stage in "$@"; do
         set -- $spec
         NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 900 $TR --nproc-per-node $1 --master-port 2950$1 bench.py --gpus $1 --config $2 --shard $3 --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/scale_$2_$3_n$1.json 2> gpurun_out/scale_$2_$3_n$1.err; echo "N=$1 $2 $3 rc $?"
         grep -m3 -E "NCCL INFO (comm|Connected|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
-        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json | head -1
+        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json 2>/dev/null | head -1; python -c "import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print('   allreduce', d['grad_allreduce']['launches_per_step'], d['grad_allreduce']['ms_alone'], d['grad_allreduce_bytes_per_step'])" gpurun_out/scale_$2_$3_n$1.json
       done ;;
     multi8)
       TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
@@ -39,7 +39,7 @@ for stage in "$@"; do
         set -- $spec
         NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 900 $TR --nproc-per-node $1 --master-port 2951$1 bench.py --gpus $1 --config $2 --shard $3 --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/scale_$2_$3_n$1.json 2> gpurun_out/scale_$2_$3_n$1.err; echo "N=$1 $2 $3 rc $?"
         grep -m2 -E "NCCL INFO (comm|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
-        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json | head -1
+        python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json 2>/dev/null | head -1; python -c "import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print('   allreduce', d['grad_allreduce']['launches_per_step'], d['grad_allreduce']['ms_alone'], d['grad_allreduce_bytes_per_step'])" gpurun_out/scale_$2_$3_n$1.json
       done ;;
     micro)    timeout -k 10 600 python scripts/gpu_microbench.py 2>&1 | tail -40 ;;
     *) echo "unknown stage $stage" ;;

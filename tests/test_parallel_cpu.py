@@ -45,19 +45,24 @@ def _worker(rank, world, port, ret):
     sync.remove()
     for p in net.parameters():
         p.grad = None
-    bs = parallel.GradSync(net, buckets=2)
-    assert bs.bucketed and 1 <= len(bs.buckets) <= 3
-    views = [p.grad.data_ptr() for p in net.parameters()]
-    steps = []
-    for k in range(2):
+    frozen = torch.nn.Parameter(torch.ones(3))  # trainable-looking, never gets a gradient (a MOPED prior, quirk Q5)
+    net.register_parameter("never_used", frozen)
+    bs = parallel.GradSync(net, buckets=2, overlap=bool(rank >= 0 and os.environ.get("BF_TEST_OVERLAP") == "1"))
+    assert bs.bucketed and not bs.buckets  # buckets are built by the first finish()
+    steps, views = [], None
+    for k in range(3):
         bs.zero_grad()
         net(x * (k + 1)).sum().backward()
         launched = sum(b.handle is not None for b in bs.buckets)
         bs.finish()
-        steps.append(dict(grads=[p.grad.clone() for p in net.parameters()], launched=launched, bytes=bs.bytes_last_step))
+        if k == 0:
+            views = [p.grad.data_ptr() for p in net.parameters() if p.grad is not None]
+        steps.append(dict(grads=[p.grad.clone() for p in net.parameters() if p.grad is not None], launched=launched,
+                          bytes=bs.bytes_last_step))
     out["bucketed"] = steps
-    out["views_kept"] = views == [p.grad.data_ptr() for p in net.parameters()]
+    out["views_kept"] = views == [p.grad.data_ptr() for p in net.parameters() if p.grad is not None]
     out["n_buckets"] = len(bs.buckets)
+    out["frozen_untouched"] = frozen.grad is None and id(frozen) not in bs._bucket_of
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -77,14 +82,14 @@ def test_gradsync_world2_gloo():
         assert r0["bytes"] == sum(p.numel() * 4 for p in r0["grads"])
         assert r0["elbo"] == r1["elbo"] == (3.0, 30.0)
         # bucketed mode gives the same averaged gradients (step k uses x * (k+1): the gradient of the weights scales)
-        assert r0["views_kept"] and r1["views_kept"]
-        for k in range(2):
+        assert r0["views_kept"] and r1["views_kept"] and r0["frozen_untouched"] and 1 <= r0["n_buckets"] <= 3
+        for k in range(3):
             b0, b1 = r0["bucketed"][k], r1["bucketed"][k]
-            assert b0["launched"] == r0["n_buckets"]  # every bucket's all-reduce started inside backward
+            assert b0["launched"] == 0  # default: nothing is launched during backward (see GradSync docstring)
             for g0, g1 in zip(b0["grads"], b1["grads"]):
                 assert torch.equal(g0, g1)
             assert torch.allclose(b0["grads"][0], r0["grads"][0] * (k + 1))
-            assert b0["bytes"] >= sum(p.numel() * 4 for p in r0["grads"])
+            assert sum(p.numel() * 4 for p in r0["grads"]) <= b0["bytes"] <= sum(p.numel() * 4 for p in r0["grads"]) + 256
 
 
 def test_gradsync_single_process_is_noop():
