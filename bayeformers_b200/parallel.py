@@ -103,7 +103,11 @@ class GradSync:
         """Called by the first finish(): `self._order` lists the tensors that received a gradient, in the order backward
         produced them.  Their gradients move into flat buffers (values kept)."""
         by_dtype = {}
+        seen = set()
         for p in self._order:
+            if id(p) in seen or p.grad is None:  # (a hook may fire for a tensor whose gradient was dropped again)
+                continue
+            seen.add(id(p))
             by_dtype.setdefault((p.grad.dtype, p.grad.device), []).append(p)
         for (dtype, dev), plist in by_dtype.items():
             total = sum(p.numel() for p in plist)

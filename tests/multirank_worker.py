@@ -119,6 +119,9 @@ def main():
     sl = slice(rank * B // world, (rank + 1) * B // world)
     loss, lq, lp = local_step(bm, ids_all[sl], labels_all[sl], S)
     loss.backward()
+    odd = [n for n, p in bm.named_parameters() if p.requires_grad and p.grad is None and any(p is q for q in sync._order)]
+    if odd and rank == 0:
+        print("tensors whose hook fired without a gradient:", odd[:8], flush=True)
     sync.finish()
     sync.remove()
     both = [torch.empty_like(lq) for _ in range(world)]
