@@ -35,7 +35,7 @@ for stage in "$@"; do
       done ;;
     multi8)
       TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-      for spec in "8 bert_qa samples" "8 bert_qa batch" "4 bert_qa samples" "4 bert_qa batch" "8 bert_cls batch" "4 bert_cls batch" "8 bert_large samples"; do
+      for spec in "8 bert_cls batch" "8 bert_qa samples" "8 bert_qa batch" "4 bert_qa samples" "8 bert_large samples"; do
         set -- $spec
         NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout -k 10 900 $TR --nproc-per-node $1 --master-port 2951$1 bench.py --gpus $1 --config $2 --shard $3 --steps 6 --warmup 3 --no-cpu-baseline --extras 0 > gpurun_out/scale_$2_$3_n$1.json 2> gpurun_out/scale_$2_$3_n$1.err; echo "N=$1 $2 $3 rc $?"
         grep -m2 -E "NCCL INFO (comm|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
