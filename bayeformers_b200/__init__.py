@@ -66,7 +66,7 @@ def _is_exact_gelu(fn) -> bool:
 
 
 def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True,
-                     fuse_residual: bool = False, grad_sinks: bool = False) -> tnn.Module:
+                     fuse_residual: bool = False, grad_sinks: bool = False, attention: bool = False) -> tnn.Module:
     """Opt-in plumbing for the frequentist code AROUND the Bayesian layers of a host model.  In place; parameters,
     state_dict names and numerics (to rounding) are unchanged.
 
@@ -84,13 +84,19 @@ def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool 
                of a fused output block gets its gradient accumulated in place: the block's backward writes its part
                first, the Linear dgrad kernels add theirs into that buffer by TMA reduce-add, and autograd's separate
                add passes disappear.  Valid when such an input has no further consumers (HF BERT); a tensor hook
-               raises otherwise (runtime.GradSink)."""
+               raises otherwise (runtime.GradSink).
+    attention  transformers models: route self-attention over short sequences (bf16, no mask, T <= 128, head width 64)
+               through the native whole-sequence kernels (nn/layers/attention.py); other cases keep torch's SDPA.  The
+               attention dropout mask then comes from the Philox counter stream."""
     from .nn.layers.fused import fuse_output_block_, is_output_block
     from .nn.layers.layernorm import HostLayerNorm
     from .nn.layers.linear import Linear
 
     if grad_sinks and not fuse_residual:
         raise ValueError("grad_sinks=True needs fuse_residual=True")
+    if attention:
+        from .nn.layers.attention import use_native_attention_
+        use_native_attention_(model)
     if grad_sinks:
         runtime.enable_grad_sinks(True)  # process-wide; runtime.enable_grad_sinks(False) switches it off again
     if fuse_residual:

@@ -28,7 +28,7 @@
 
 namespace attn {
 
-constexpr int TMAX = 128, D = 64, kWarps = 8, kThreads = 256;
+constexpr int TMAX = 128, D = 64, kThreads = 256;  // 8 warps x 16 query rows (phase B of the backward: x 16 keys)
 constexpr int TILE_BYTES = TMAX * D * 2;      // one [128, 64] bf16 tile: 16 KiB
 constexpr int SQ_BYTES = TMAX * TMAX * 2;     // one [128, 128] bf16 tile: 32 KiB
 constexpr int FWD_SMEM = 3 * TILE_BYTES;                    // q, k, v

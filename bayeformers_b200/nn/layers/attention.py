@@ -1,0 +1,66 @@
+"""Short-sequence attention of the host model routed through the native kernels (opt-in).
+
+The reference leaves attention to the host model (HuggingFace BERT calls torch's scaled_dot_product_attention between the
+Bayesian query / key / value projections and the Bayesian output projection, examples/bert_glue.py).  With every Linear on
+the tensor cores that library call became the largest non-contraction block of the training step at sequence length 128,
+so `bayeformers_b200.accelerate_host_(model, attention=True)` registers an attention function with transformers'
+`AttentionInterface` and points the model's config at it.  The function takes the case the kernels cover -- bf16, no
+attention mask, not causal, T <= 128 (a multiple of 16), head width 64 -- and hands everything else to transformers' own
+"sdpa" function, so results never depend on the switch beyond rounding and the dropout stream (Philox counter based,
+regenerated in backward, instead of torch's generator).
+"""
+from __future__ import annotations
+
+import torch
+
+from ... import ops, runtime
+
+NAME = "bayeformers_b200"
+_registered = {"done": False}
+
+
+def _fallback():
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    return ALL_ATTENTION_FUNCTIONS["sdpa"]
+
+
+def attention_forward(module, query, key, value, attention_mask, dropout: float = 0.0, scaling=None, **kwargs):
+    """transformers attention-interface signature: query / key / value [B, heads, T, d]; returns ([B, T, heads, d], None)."""
+    usable = (attention_mask is None and not kwargs.get("is_causal", False) and not getattr(module, "is_causal", False)
+              and ops.attention_supported(query, key, value))
+    if not usable:
+        return _fallback()(module, query, key, value, attention_mask, dropout=dropout, scaling=scaling, **kwargs)
+    if not hasattr(module, "_bf_site"):
+        module._bf_site, module._bf_calls = runtime.next_tensor_id(), 0
+    module._bf_calls += 1
+    drop = ops.DropoutSpec(p=float(dropout), seed=runtime.seed(), site_id=module._bf_site,
+                           step=module._bf_calls & 0xFFFFFFFF)
+    module._last_dropout = drop  # identity of this forward's mask (tests, debugging)
+    scale = float(scaling) if scaling is not None else float(query.shape[-1]) ** -0.5
+    return ops.AttentionFn.apply(query, key, value, scale, drop), None
+
+
+def use_native_attention_(model: torch.nn.Module) -> int:
+    """Point every transformers config found in `model` at the native attention function.  Returns how many configs
+    were switched (0: not a transformers model, nothing done)."""
+    try:
+        from transformers import AttentionInterface
+    except Exception:  # pragma: no cover
+        return 0
+    if not _registered["done"]:
+        AttentionInterface.register(NAME, attention_forward)
+        _registered["done"] = True
+    seen, n = set(), 0
+    for mod in model.modules():
+        cfg = getattr(mod, "config", None)
+        if cfg is None or id(cfg) in seen or not hasattr(cfg, "_attn_implementation"):
+            continue
+        seen.add(id(cfg))
+        if getattr(cfg, "_attn_implementation", None) in ("sdpa", "eager", None, NAME):
+            cfg._attn_implementation = NAME
+            n += 1
+    # dropout sites get their stream ids now (same construction order on every rank)
+    for mod in model.modules():
+        if type(mod).__name__.endswith("SelfAttention") and not hasattr(mod, "_bf_site"):
+            mod._bf_site, mod._bf_calls = runtime.next_tensor_id(), 0
+    return n

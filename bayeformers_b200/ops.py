@@ -841,6 +841,74 @@ class ResidualLayerNormFn(torch.autograd.Function):
         return dhv, dzv, dg, db, None, None, None, None, None
 
 
+class AttentionFn(torch.autograd.Function):
+    """O = dropout_p(softmax(q k^T * scale)) v for short sequences (`bf_attention_fwd` / `_bwd`): the host model's
+    attention between the Bayesian projections.  q, k, v: bf16 [B, H, T, 64] views with unit inner stride (HF passes
+    transposed views of the [B, T, H*64] projection outputs: read in place); returns [B, T, H, 64].  The keep mask is
+    regenerated in backward from (seed, site, step)."""
+
+    @staticmethod
+    @_guarded
+    def forward(ctx, q, k, v, scale: float, drop: DropoutSpec):
+        _require_cuda(q, "query")
+        lib = _lib.load()
+        dev = q.device
+        B, H, T, Dh = q.shape
+        fix = lambda t: t if (t.stride(-1) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0) \
+            else t.contiguous()
+        qc, kc, vc = fix(q.detach()), fix(k.detach()), fix(v.detach())
+        strides = torch.tensor([t.stride(i) for t in (qc, kc, vc) for i in (0, 1, 2)], dtype=torch.int64)
+        out = torch.empty((B, T, H, Dh), dtype=torch.bfloat16, device=dev)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=dev)
+        flops = 4.0 * B * H * T * T * Dh
+        rc = _timed("attention_fwd", flops, dev, lambda: lib.bf_attention_fwd(
+            _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), B, H, T, float(scale), float(drop.p), drop.seed,
+            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(out), _ptr(lse), _stream(dev)))
+        _lib.check(rc, "bf_attention_fwd")
+        stats["launches"] += 1
+        ctx.save_for_backward(qc, kc, vc, out, lse)
+        ctx.meta = (float(scale), drop, strides)
+        return out
+
+    @staticmethod
+    @_guarded
+    def backward(ctx, gout):
+        lib = _lib.load()
+        qc, kc, vc, out, lse = ctx.saved_tensors
+        scale, drop, strides = ctx.meta
+        dev = qc.device
+        B, H, T, Dh = qc.shape
+        g = gout.to(torch.bfloat16).contiguous()
+        dq = torch.empty((B, T, H, Dh), dtype=torch.bfloat16, device=dev)
+        dk, dv = torch.empty_like(dq), torch.empty_like(dq)
+        flops = 10.0 * B * H * T * T * Dh
+        rc = _timed("attention_bwd", flops, dev, lambda: lib.bf_attention_bwd(
+            _ptr(g), _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), _ptr(out), _ptr(lse), B, H, T, scale, float(drop.p),
+            drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dq), _ptr(dk), _ptr(dv), _stream(dev)))
+        _lib.check(rc, "bf_attention_bwd")
+        stats["launches"] += 1
+        # [B, T, H, D] buffers seen as [B, H, T, D]: the layout the inputs came in (views of [B, T, H*D] rows), so the
+        # transposes / reshapes of the surrounding model stay free
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None
+
+
+def attention_supported(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:
+    return (q.is_cuda and q.dtype == k.dtype == v.dtype == torch.bfloat16 and q.dim() == 4 and q.shape == k.shape == v.shape
+            and bool(_lib.load().bf_attention_supported(int(q.shape[2]), int(q.shape[3]))))
+
+
+def attention_dropout_mask(B: int, H: int, T: int, drop: DropoutSpec, device) -> torch.Tensor:
+    """The keep mask `AttentionFn` applies, as uint8 [B, H, T, T] (1 = kept) -- tests."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    out = torch.empty((B, H, T, T), dtype=torch.uint8, device=dev)
+    with on_device(dev):
+        rc = lib.bf_attention_dropout_mask(_ptr(out), B, H, T, float(drop.p), drop.seed, drop.step & 0xFFFFFFFF,
+                                           drop.site_id, _stream(dev))
+    _lib.check(rc, "bf_attention_dropout_mask")
+    return out
+
+
 def dropout_mask(n: int, drop: DropoutSpec, device) -> torch.Tensor:
     """The keep mask (uint8, 1 = kept) `ResidualLayerNormFn` applies to a flat tensor of n elements -- tests."""
     lib = _lib.load()

@@ -255,7 +255,7 @@ def rng_state(model: torch.nn.Module) -> dict:
     for name, mod in model.named_modules():
         if isinstance(mod, Gaussian):
             out["gaussians"][name] = {"tensor_id": int(mod.tensor_id), "step": int(mod.step)}
-        if hasattr(mod, "_bf_site"):
+        if hasattr(mod, "_bf_site"):  # fused output blocks and native-attention modules
             out["dropout_sites"][name] = {"site": int(mod._bf_site), "calls": int(getattr(mod, "_bf_calls", 0))}
     ps = getattr(model, "_presampler", None)
     if ps is not None:

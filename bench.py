@@ -79,6 +79,8 @@ def parse():
     ap.add_argument("--host-ln", type=int, default=1)
     ap.add_argument("--fuse-residual", type=int, default=1)
     ap.add_argument("--grad-sinks", type=int, default=1)
+    ap.add_argument("--attention", type=int, default=1,
+                    help="route the host model's short-sequence attention (T <= 128) through the native kernels")
     ap.add_argument("--gelu-links", type=int, default=1,
                     help="fold GELU' into the dgrad epilogue of the Linear that consumes a fused-GELU layer's output")
     ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
@@ -370,6 +372,8 @@ def workload_config(args, world):
             "host_layernorm": ("native kernels (bf_layernorm_*)" if args.host_ln else "torch") if bert else "n/a",
             "output_blocks": ("dropout + residual + LayerNorm fused (bf_resln_*, Philox mask, bias grad handed to the Linear)"
                               if args.fuse_residual else "torch dropout + add, separate LayerNorm") if bert else "n/a",
+            "attention": ("native whole-sequence kernels (bf_attention_*, Philox dropout mask) for T <= 128, else torch SDPA"
+                          if args.attention else "torch SDPA (cuDNN)") if bert else "n/a",
             "shared_input_grads": ("accumulated in place by the dgrad kernels (TMA reduce-add)"
                                    if (args.grad_sinks and args.fuse_residual) else "autograd add passes") if bert else "n/a",
             "parallelism": f"dp{world} ({shard})",
@@ -394,12 +398,12 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     layers = bnn.TORCH2BAYE_ALL if args.config == "bert_large" else None
     bm = bf.to_bayesian(model, delta=0.05, freeze=(args.config != "mlp"), gemm_dtype=gemm, kl_grad=bool(args.kl_grad),
                         layers=layers)
-    if bert and (args.host_ln or args.fuse_gelu or args.fuse_residual):
+    if bert and (args.host_ln or args.fuse_gelu or args.fuse_residual or args.attention):
         # same parameters and numerics: native LayerNorm kernels (fp32 gamma/beta); FFN GELU fused into the layer;
         # dropout + residual + LayerNorm of the output blocks in one pass each way (Philox dropout mask)
         bf.accelerate_host_(bm, layernorm=bool(args.host_ln), fuse_gelu=bool(args.fuse_gelu),
                             fuse_residual=bool(args.fuse_residual),
-                            grad_sinks=bool(args.grad_sinks and args.fuse_residual))
+                            grad_sinks=bool(args.grad_sinks and args.fuse_residual), attention=bool(args.attention))
     bm = bm.to(dev).train()
     if args.presample:
         bf.enable_presample(bm)

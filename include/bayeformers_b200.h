@@ -358,6 +358,32 @@ int bf_dropout_mask(uint8_t* out, int64_t n, float p_drop, uint64_t seed, uint32
                     void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Short-sequence self-attention of the host model between the Bayesian q / k / v and output projections
+ * (opt-in extension; the reference leaves attention to the host model, i.e. to torch's
+ * scaled_dot_product_attention):  O = dropout_p(softmax(q k^T * scale)) v  for whole sequences of
+ * T <= 128 tokens (T % 16 == 0) and head width 64, one (sequence, head) per thread block, forward
+ * and backward; no attention mask, not causal.  bf16 in / out, fp32 accumulation and softmax.
+ *
+ * q, k, v   bf16, element (b, h, t, j) at  base + b*strides[3i] + h*strides[3i+1] + t*strides[3i+2] + j
+ *           (i = 0 q, 1 k, 2 v; unit inner stride): read in place from the [B, T, heads*64] projection
+ *           outputs, no transposed copies
+ * out, dout, dq, dk, dv   bf16 [B, T, H, 64] densely packed
+ * lse       fp32 [B, H, T]: base-2 log-sum-exp of the scaled scores, written by fwd, read by bwd
+ * The dropout keep mask is a pure function of (seed, site, step [+ device step counter], b, h, q, k)
+ * (Philox4x32-10; see bf_attention.cu) and is regenerated in backward; bf_attention_dropout_mask
+ * writes it as bytes [B, H, T, T] (tests).  Deterministic: every output element is written once.
+ * ------------------------------------------------------------------------- */
+int bf_attention_supported(int64_t T, int64_t head_dim);
+int bf_attention_fwd(const void* q, const void* k, const void* v, const int64_t* strides, int64_t B, int64_t H, int64_t T,
+                     float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* out, float* lse,
+                     void* stream);
+int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
+                     const void* out, const float* lse, int64_t B, int64_t H, int64_t T, float scale, float p_drop,
+                     uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk, void* dv, void* stream);
+int bf_attention_dropout_mask(uint8_t* out, int64_t B, int64_t H, int64_t T, float p_drop, uint64_t seed, uint32_t step,
+                              uint32_t site, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Fused global-norm clipping + AdamW over all trainable tensors.
  * Replaces clip_grad_norm_(params, max_norm) + AdamW.step() of the reference's
  * training loop (examples/bert_glue.py:240-241); arithmetic of torch.optim.AdamW

@@ -1286,3 +1286,116 @@ def test_ffn_block_with_and_without_gelu_link():
         y = a_down(a)
     with pytest.raises(RuntimeError, match="fused GELU"):
         (y.float().sum() + a.float().sum()).backward()
+
+
+# ------------------------------------------------------------------ native short-sequence attention (host model, opt-in)
+@pytest.mark.parametrize("B,H,Tn", [(3, 12, 128), (2, 4, 64), (5, 2, 16), (2, 3, 112), (150, 2, 128)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_kernels_vs_float64(B, H, Tn, p):
+    """bf_attention_fwd / _bwd (whole sequence per block, mma.sync, Philox keep mask regenerated in backward) against a
+    float64 composition softmax(q k^T * scale) -> mask / keep-probability -> . v and its autograd.  q, k, v are the
+    transposed views of [B, T, H*64] buffers HuggingFace hands its attention function."""
+    Dh = 64
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + Tn)
+    bufs = [(torch.randn(B, Tn, H * Dh, generator=gen) * 0.8).bfloat16().to(DEV).requires_grad_() for _ in range(3)]
+    q, k, v = (t.view(B, Tn, H, Dh).transpose(1, 2) for t in bufs)
+    drop = ops.DropoutSpec(p=p, seed=0xABCDEF0123, site_id=7, step=3)
+    scale = Dh ** -0.5
+    out = ops.AttentionFn.apply(q, k, v, scale, drop)
+    assert out.shape == (B, Tn, H, Dh) and out.dtype == torch.bfloat16
+    gout = torch.randn(out.shape, generator=gen).bfloat16().to(DEV)
+    out.backward(gout)
+    keep = ops.attention_dropout_mask(B, H, Tn, drop, DEV).double()
+    if p == 0.0:
+        assert bool((keep == 1).all())
+        keep_prob = 1.0
+    else:
+        keep_prob = 1.0 - round(p * 65536) / 65536
+        assert abs(float(keep.mean()) - keep_prob) < 5.0 * np.sqrt(p * (1 - p) / keep.numel()) + 1e-4
+    qd, kd, vd = (t.detach().double().view(B, Tn, H, Dh).transpose(1, 2).requires_grad_() for t in bufs)
+    P = torch.softmax(qd @ kd.transpose(-1, -2) * scale, dim=-1)
+    ref = ((P * keep / keep_prob) @ vd).transpose(1, 2)  # [B, T, H, D]
+    ref.backward(gout.double())
+    assert rel_err(out.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) < 6e-3
+    for got, want, name in zip(bufs, (qd, kd, vd), "qkv"):
+        g = got.grad.view(B, Tn, H, Dh).transpose(1, 2)
+        e = rel_err(g.float().cpu().numpy(), want.grad.cpu().numpy())
+        assert e < 1.5e-2, (name, e)
+    # deterministic: a second run gives the same bits
+    for t in bufs:
+        t.grad = None
+    out2 = ops.AttentionFn.apply(q, k, v, scale, drop)
+    out2.backward(gout)
+    assert torch.equal(out, out2)
+    g1 = bufs[0].grad.clone()
+    for t in bufs:
+        t.grad = None
+    ops.AttentionFn.apply(q, k, v, scale, drop).backward(gout)
+    assert torch.equal(g1, bufs[0].grad)
+
+
+def test_attention_dropout_masks_are_independent_across_sites_and_steps():
+    B, H, Tn = 4, 12, 128
+    base = ops.DropoutSpec(p=0.1, seed=11, site_id=3, step=5)
+    m0 = ops.attention_dropout_mask(B, H, Tn, base, DEV).float().flatten()
+    n = m0.numel()
+    for other in (ops.DropoutSpec(0.1, 11, 4, 5), ops.DropoutSpec(0.1, 11, 3, 6), ops.DropoutSpec(0.1, 12, 3, 5)):
+        m1 = ops.attention_dropout_mask(B, H, Tn, other, DEV).float().flatten()
+        corr = float(torch.corrcoef(torch.stack([m0, m1]))[0, 1])
+        assert abs(corr) < 5.0 / np.sqrt(n)
+    m = m0.view(B * H * Tn, Tn)
+    assert abs(float(torch.corrcoef(torch.stack([m[:, :-1].flatten(), m[:, 1:].flatten()]))[0, 1])) < 5.0 / np.sqrt(n)
+    assert torch.equal(m0, ops.attention_dropout_mask(B, H, Tn, base, DEV).float().flatten())
+
+
+def test_accelerate_host_native_attention_matches_sdpa():
+    """accelerate_host_(attention=True) on a HuggingFace BERT: eval-mode logits and gradients agree with the torch SDPA
+    path to bf16 rounding, the native kernels really ran, and a masked batch falls back to SDPA."""
+    import copy
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(2)
+    cfg = BertConfig(vocab_size=100, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                     intermediate_size=512, max_position_embeddings=128, num_labels=2)
+    base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True, gemm_dtype="bf16")
+    fast = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, attention=True)
+    base, fast = base.eval().to(DEV), fast.eval().to(DEV)
+    for m in (base, fast):
+        bf.cast_frequentist_(m, torch.bfloat16)
+    S, B, Tn = 2, 3, 128
+    ids = torch.randint(0, 100, (B, Tn), generator=torch.Generator().manual_seed(1)).to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    for la, lb in zip(base.bayesian_children, fast.bayesian_children):
+        ew = [torch.randn(la.weight.mu.shape, generator=gen) for _ in range(S)]
+        eb = [torch.randn(la.bias.mu.shape, generator=gen) for _ in range(S)]
+        la.weight.normal, lb.weight.normal = FixedEps(ew), FixedEps([e.clone() for e in ew])
+        la.bias.normal, lb.bias.normal = FixedEps(eb), FixedEps([e.clone() for e in eb])
+    outs = []
+    for m in (base, fast):
+        ops.enable_kernel_timing(True)
+        try:
+            with bf.mc_samples(S):
+                logits = m(input_ids=ids.repeat(S, 1)).logits
+            logits.float().square().sum().backward()
+            torch.cuda.synchronize()
+            ran = set(ops.kernel_timing_summary())
+        finally:
+            ops.enable_kernel_timing(False)
+        assert ({"attention_fwd", "attention_bwd"} <= ran) == (m is fast)
+        outs.append((logits.detach().float(), [l.weight.rho.grad.clone() for l in m.bayesian_children]))
+    assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < 2e-2
+    for ga, gb in zip(outs[0][1], outs[1][1]):
+        assert rel_err(gb.cpu().numpy(), ga.cpu().numpy()) < 5e-2
+    # an attention mask is outside the kernels' case: transformers' own SDPA function takes it
+    mask = torch.ones(B, Tn, dtype=torch.long, device=DEV)
+    mask[:, 100:] = 0
+    for l in fast.bayesian_children:  # back to the Philox stream
+        l.weight.normal = torch.distributions.Normal(l.weight.zero, l.weight.one)
+        l.bias.normal = torch.distributions.Normal(l.bias.zero, l.bias.one)
+    ops.enable_kernel_timing(True)
+    try:
+        fast(input_ids=ids, attention_mask=mask)
+        torch.cuda.synchronize()
+        ran = set(ops.kernel_timing_summary())
+    finally:
+        ops.enable_kernel_timing(False)
+    assert "attention_fwd" not in ran
