@@ -41,6 +41,11 @@ for stage in "$@"; do
         grep -m2 -E "NCCL INFO (comm|NVLS)" gpurun_out/scale_$2_$3_n$1.err | cut -c1-160
         python scripts/bench_kernels.py gpurun_out/scale_$2_$3_n$1.json 2>/dev/null | head -1; python -c "import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print('   allreduce', d['grad_allreduce']['launches_per_step'], d['grad_allreduce']['ms_alone'], d['grad_allreduce_bytes_per_step'])" gpurun_out/scale_$2_$3_n$1.json
       done ;;
+    ab_attn)
+      for v in 0 1 0 1; do
+        timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --attention $v > gpurun_out/bench_attn$v.json 2> gpurun_out/bench_attn$v.err; echo "attention=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_attn$v.json 2>/dev/null | head -2
+      done
+      python scripts/bench_kernels.py gpurun_out/bench_attn1.json 2>/dev/null | head -14 ;;
     micro)    timeout -k 10 600 python scripts/gpu_microbench.py 2>&1 | tail -40 ;;
     *) echo "unknown stage $stage" ;;
   esac
