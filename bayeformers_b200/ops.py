@@ -28,8 +28,27 @@ def enable_kernel_timing(flag: bool) -> None:
     _timing["records"] = []
 
 
+_nvtx = {"on": False}
+
+
+def enable_nvtx(flag: bool = True) -> None:
+    """Wrap every C-ABI launch in an NVTX range named after its kernel family (sample_kl_fwd, gemm_fwd_tc,
+    gemm_dgrad_tc, gemm_wgrad_fused_tc, resln_*, clip_adamw, ...): the ranges ncu / nsys group launches by."""
+    _nvtx["on"] = bool(flag)
+
+
 def _timed(name: str, work: float, dev, fn):
     """Run fn() (which launches on the current stream), counting and optionally timing it."""
+    if _nvtx["on"]:
+        torch.cuda.nvtx.range_push("bf:" + name)
+        try:
+            return _timed_inner(name, work, dev, fn)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _timed_inner(name, work, dev, fn)
+
+
+def _timed_inner(name: str, work: float, dev, fn):
     if not _timing["on"]:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

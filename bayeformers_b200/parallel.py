@@ -184,6 +184,9 @@ class GradSync:
             if not self.buckets:
                 self._make_buckets()
             op, scale_after = self._op()
+            nvtx = self.buckets and self.buckets[0].flat.is_cuda
+            if nvtx:
+                torch.cuda.nvtx.range_push("bf:grad_allreduce")
             for b in self.buckets:
                 if b.handle is None:
                     b.handle = (dist.all_reduce(b.flat, op=op, group=self.group, async_op=True), scale_after)
@@ -201,6 +204,8 @@ class GradSync:
                 if sa:
                     b.flat.div_(self.world)
                 b.handle, b.pending = None, len(b.params)
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
             self.bytes_last_step, self._bytes = self._bytes, 0
             return
         if self._small:
