@@ -46,6 +46,14 @@ for stage in "$@"; do
         timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --attention $v > gpurun_out/bench_attn$v.json 2> gpurun_out/bench_attn$v.err; echo "attention=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_attn$v.json 2>/dev/null | head -2
       done
       python scripts/bench_kernels.py gpurun_out/bench_attn1.json 2>/dev/null | head -14 ;;
+    ncu2)
+      timeout -k 10 1500 ncu --set full --clock-control none --import-source on -k regex:"gelu_kernel|dgelu_kernel|bayes_gemm2_kernel|bayes_gemm_kernel|sample_kl_multi_kernel|embedding_|attention_fwd|attention_bwd|split_bf16" -c 14 -f -o gpurun_out/prof_r02 python scripts/profile_r02.py > gpurun_out/ncu_r02.log 2>&1; echo "rc $?"; tail -2 gpurun_out/ncu_r02.log
+      rm -f gpurun_out/r02_ncu_full_kernels.md; python scripts/ncu_summary.py gpurun_out/prof_r02.ncu-rep gpurun_out/r02_ncu_full_kernels.md; cat gpurun_out/r02_ncu_full_kernels.md | cut -c1-330
+      python scripts/ncu_traffic.py gpurun_out/prof_r02.ncu-rep gpurun_out/traffic.json | head -40
+      ls -la gpurun_out/prof_r02.ncu-rep ;;
+    sanitize)
+      timeout -k 10 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "dgrad_gelu and 2560 or x3_contractions and 200 or attention_kernels and 5-2-16 or attention_kernels and 2-4-64 or fused_wgrad_epilogue and 200 or embedding_and_layernorm" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc $?"; tail -6 gpurun_out/sanitizer_memcheck.log
+      timeout -k 10 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 5-2-16 or attention_kernels and 2-4-64 or resln_vs_torch and 33 or tc_contractions and 128-256-64" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc $?"; tail -6 gpurun_out/sanitizer_racecheck.log ;;
     micro)    timeout -k 10 600 python scripts/gpu_microbench.py 2>&1 | tail -40 ;;
     *) echo "unknown stage $stage" ;;
   esac
