@@ -604,6 +604,43 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     return res
 
 
+def sample_kl_sweep(args, dev, pk):
+    """The multi-tensor sample+KL launch of THIS workload's model alone (no other kernel running), S = 1, 4, 16: CUDA
+    events around each launch, algorithmic bytes as in SURVEY.md 8d.  The kernel is instruction-bound (Philox4x32-10 +
+    Box-Muller per element-sample), so GB/s falls with S while element-samples/s rises; the in-step figure
+    (`roofline_sample_kl`) is the same kernel at the power-capped clock of the step."""
+    import bayeformers_b200 as bf
+    import bayeformers_b200.nn as bnn
+    from bayeformers_b200 import ops
+
+    wl = Workload(args)
+    model, _ = wl.build()
+    bm = bf.to_bayesian(model, delta=0.05, freeze=(args.config != "mlp"), gemm_dtype=args.gemm,
+                        layers=bnn.TORCH2BAYE_ALL if args.config == "bert_large" else None).to(dev)
+    bf.enable_presample(bm)
+    rows = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for S in (1, 4, 16):
+        for _ in range(3):
+            bm._presampler.run(S)
+        torch.cuda.synchronize()
+        ops.enable_kernel_timing(True)
+        for _ in range(5):
+            flush.fill_(1)
+            bm._presampler.run(S)
+        torch.cuda.synchronize()
+        k = ops.kernel_timing_summary()["sample_kl_fwd"]
+        ops.enable_kernel_timing(False)
+        gbs = k["work"] / (k["ms"] / 1e3) / 1e9
+        n_elem = sum(n for _, n, _ in bm._presampler.offsets)
+        rows.append({"S": S, "us_per_launch": k["ms"] / k["calls"] * 1e3, "GB/s": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"],
+                     "G_element_samples_per_s": n_elem * S / (k["ms"] / k["calls"] / 1e3) / 1e9,
+                     "algorithmic_bytes_per_launch": k["work"] / k["calls"]})
+    del bm, model
+    torch.cuda.empty_cache()
+    return rows
+
+
 def traffic_record(kernel_key):
     """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) of the dominant kernel from a committed
     ncu capture AT THE BENCH SHAPE: profiles/traffic.json, written by scripts/ncu_traffic.py from an `ncu --set full`
@@ -798,6 +835,7 @@ def run_ours(args):
                                     "ms_per_step": r32["ms"],
                                     "gemm": "fp32x3: reference-precision mode (1e-5), fp32 operands as bf16 (hi, lo) pairs, "
                                             "3 tcgen05 passes per tile, fp32 activations"}
+            extras["sample_kl_alone"] = sample_kl_sweep(args, dev, pk)
             rb = measure(args, dev, 1, 0, local, batch=args.ref_batch, gemm="bf16", steps=10, warmup=3, timing=False, e2e=True)
             extras["reference_batch"] = {"batch_per_gpu": args.ref_batch, "value": args.ref_batch / (rb["ms"] / 1e3),
                                          "e2e": args.ref_batch / (rb["ms_e2e"] / 1e3), "unit": args.unit,
