@@ -49,6 +49,15 @@ def use_native_attention_(model: torch.nn.Module) -> int:
         return 0
     if not _registered["done"]:
         AttentionInterface.register(NAME, attention_forward)
+        # transformers builds NO mask for attention names it does not know ("custom attention without equivalent mask
+        # creation"): register torch-SDPA's mask builder under our name, so a padded batch still arrives with its
+        # [B, 1, T, T] mask and is handed to the SDPA fallback instead of silently attending to the padding
+        try:
+            from transformers.masking_utils import AttentionMaskInterface, sdpa_mask
+            AttentionMaskInterface.register(NAME, sdpa_mask)
+        except Exception as e:  # pragma: no cover
+            raise RuntimeError("this transformers version has no AttentionMaskInterface: the native attention cannot be "
+                               "enabled safely (padded batches would lose their mask)") from e
         _registered["done"] = True
     seen, n = set(), 0
     for mod in model.modules():
