@@ -23,13 +23,13 @@ class BfTensorDesc(ctypes.Structure):
     _fields_ = [("mu", c_void_p), ("rho", c_void_p), ("prior_mu", c_void_p), ("prior_rho", c_void_p),
                 ("w_out", c_void_p), ("n", c_int64), ("w_stride", c_int64), ("tensor_id", c_uint32),
                 ("step", c_uint32), ("prior_kind", c_int32), ("w_dtype", c_int32), ("pi", c_float),
-                ("sigma1", c_float), ("sigma2", c_float), ("vec", c_int32)]
+                ("sigma1", c_float), ("sigma2", c_float), ("vec", c_int32), ("sigma", c_void_p)]
 
 
 class BfOptDesc(ctypes.Structure):
     """`bf_opt_desc` of include/bayeformers_b200.h (fused clip + AdamW)."""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
-                ("n", c_int64), ("dtype", c_int32), ("vec", c_int32), ("master", c_void_p)]
+                ("n", c_int64), ("dtype", c_int32), ("vec", c_int32), ("master", c_void_p), ("sigma_out", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/bayeformers_b200.h one to one
@@ -45,6 +45,7 @@ SIGNATURES = {
     "bf_sample_kl_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_int64, c_int32, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_int32,
                                    c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "bf_softplus_fwd": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "bf_sample_kl_multi_chunk_quads": (c_int32, []),
     "bf_sample_kl_multi_workspace_bytes": (c_int64, [c_int64]),
     "bf_sample_kl_fwd_multi": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_uint64,

@@ -107,6 +107,7 @@ __device__ __forceinline__ void adamw_chunk(const bf_opt_desc& d, int64_t lo, in
     T* const p = reinterpret_cast<T*>(d.param);
     const T* const g = reinterpret_cast<const T*>(d.grad);
     float* const master = d.master;  // fp32 master copy of a bf16 parameter (nullable): the update runs on it
+    float* const sig = d.sigma_out;  // sigma cache of a rho tensor (nullable): softplus of the updated value
     auto upd = [&](float pv, float gv, float& m, float& v) {
         gv *= clip;
         pv *= decay;                               // p.mul_(1 - lr*wd)
@@ -125,6 +126,9 @@ __device__ __forceinline__ void adamw_chunk(const bf_opt_desc& d, int64_t lo, in
             pv.z = upd(pv.z, gv.z, m.z, v.z), pv.w = upd(pv.w, gv.w, m.w, v.w);
             opt_st4<T>(p + i, pv);
             if (master) *reinterpret_cast<float4*>(master + i) = pv;
+            if (sig)
+                *reinterpret_cast<float4*>(sig + i) =
+                    make_float4(bf_softplus(pv.x), bf_softplus(pv.y), bf_softplus(pv.z), bf_softplus(pv.w));
             *reinterpret_cast<float4*>(d.exp_avg + i) = m;
             *reinterpret_cast<float4*>(d.exp_avg_sq + i) = v;
         }
@@ -135,6 +139,7 @@ __device__ __forceinline__ void adamw_chunk(const bf_opt_desc& d, int64_t lo, in
             if (sizeof(T) == 2) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(pn);
             else reinterpret_cast<float*>(p)[i] = pn;
             if (master) master[i] = pn;
+            if (sig) sig[i] = bf_softplus(pn);
             d.exp_avg[i] = m, d.exp_avg_sq[i] = v;
         }
     }

@@ -27,6 +27,7 @@ struct SampleKlParams {
     const float* prior_mu;
     const float* prior_rho;
     const float* eps_in;  // [S_total * n] or null
+    const float* sigma;   // multi-tensor path: cached softplus(rho), read instead of rho (or null)
     void* w_out;          // [S_total][w_stride] or null
     float* logq_out;      // [S_total]
     float* logp_out;
@@ -253,7 +254,7 @@ struct RawQuad {  // the raw 16-byte loads of one quad, kept in flight across th
 template <int PRIOR>
 __device__ __forceinline__ void load_raw(const SampleKlParams& p, int64_t i0, RawQuad& R) {
     R.mu = __ldg(reinterpret_cast<const float4*>(p.mu + i0));
-    R.rho = __ldg(reinterpret_cast<const float4*>(p.rho + i0));
+    R.rho = __ldg(reinterpret_cast<const float4*>((p.sigma ? p.sigma : p.rho) + i0));  // sigma cache: R.rho holds sigma
     if (PRIOR == BF_PRIOR_GAUSSIAN) {
         R.pmu = __ldg(reinterpret_cast<const float4*>(p.prior_mu + i0));
         if (p.prior_rho != nullptr) R.prho = __ldg(reinterpret_cast<const float4*>(p.prior_rho + i0));
@@ -271,7 +272,7 @@ __device__ __forceinline__ void derive_quad(const SampleKlParams& p, const RawQu
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        Q.sigma[j] = bf_softplus(rho[j]);
+        Q.sigma[j] = p.sigma ? rho[j] : bf_softplus(rho[j]);  // cached sigma (written by the optimizer) or rho
         Q.qc[j] = -BF_LOG_SQRT_2PI - bf_log_sum_term(Q.sigma[j]);
         Q.qiv[j] = bf_rcp_approx(2.0f * __fmul_rn(Q.sigma[j], Q.sigma[j]));
         if (PRIOR == BF_PRIOR_GAUSSIAN) {
@@ -590,6 +591,7 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
                                             uint32_t step, float (&q_acc)[SC], float (&p_acc)[SC]) {
     SampleKlParams p{};
     p.mu = d.mu, p.rho = d.rho, p.prior_mu = d.prior_mu, p.prior_rho = d.prior_rho;
+    p.sigma = d.vec ? d.sigma : nullptr;  // the scalar path below reads rho itself
     p.mix.pi = d.pi;
     // w_out == (void*)-1: log-probs only (Embedding tables: rows are sampled on lookup, bf_embedding_fwd)
     const bool no_out = reinterpret_cast<intptr_t>(d.w_out) == (intptr_t)-1;
@@ -661,11 +663,12 @@ __device__ __forceinline__ void multi_chunk(const bf_tensor_desc& d, const Multi
             // the next iteration's parameter lines: without this every iteration exposes the full DRAM latency at
             // 16 resident warps per SM (ncu source page: 21 % of all stall samples on the first use of rho)
             const int64_t in = (q + kThreads) << 2;
+            const float* const r_or_s = p.sigma ? p.sigma : d.rho;
             if (mp.prefetch == 1) {
-                prefetch_l1(d.mu + in), prefetch_l1(d.rho + in);
+                prefetch_l1(d.mu + in), prefetch_l1(r_or_s + in);
                 if (PRIOR == BF_PRIOR_GAUSSIAN) prefetch_l1(d.prior_mu + in);
             } else {
-                prefetch_l2(d.mu + in), prefetch_l2(d.rho + in);
+                prefetch_l2(d.mu + in), prefetch_l2(r_or_s + in);
                 if (PRIOR == BF_PRIOR_GAUSSIAN) prefetch_l2(d.prior_mu + in);
             }
         }
@@ -980,6 +983,23 @@ int bf_sample_kl_bwd_impl_kl_only(const float* mu, const float* rho, int32_t pri
                                   cudaStream_t st) {
     return bf_sample_kl_bwd(nullptr, BF_F32, n, mu, rho, prior_kind, prior_mu, prior_rho, pi, sigma1, sigma2, g_logq,
                             g_logp, n, S, seed, step, tensor_id, eps_in, grad_mu, grad_rho, 1, st);
+}
+
+namespace {
+__global__ void __launch_bounds__(kThreads) softplus_fwd_kernel(const float* __restrict__ rho, float* __restrict__ sigma,
+                                                                int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        sigma[i] = bf_softplus(__ldg(rho + i));
+}
+}  // namespace
+
+extern "C" int bf_softplus_fwd(const float* rho, float* sigma, int64_t n, void* stream) {
+    BF_CHECK_ARG(n >= 0, "bad n");
+    if (n == 0) return 0;
+    BF_CHECK_ARG(rho && sigma, "null pointer");
+    softplus_fwd_kernel<<<grid_for((n + 3) >> 2, 8), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rho, sigma, n);
+    BF_LAUNCH_OK();
+    return 0;
 }
 
 // ---- multi-tensor entry points --------------------------------------------------------

@@ -74,6 +74,34 @@ class Gaussian(Parameter):
     def sigma(self) -> Tensor:
         return F.softplus(self.rho)
 
+    # ---- sigma cache (extension) -------------------------------------------
+    # sigma = softplus(rho) changes only when rho does.  `bf.optim.ClipAdamW(..., model=...)` writes softplus of the
+    # updated rho next to its update, and the multi-tensor sampling kernel then reads this tensor instead of rho (no
+    # exp / log1p per element).  The cache counts as valid only while (storage, version, device) of rho are what they were
+    # when it was written: any torch-side change of rho (load_state_dict, copy_, another optimizer, .to()) invalidates it
+    # and the kernels go back to computing softplus themselves.
+    def sigma_cache(self) -> Optional[Tensor]:
+        """The cached softplus(rho) when it is valid, else None."""
+        sig = getattr(self, "_sigma", None)
+        if sig is not None and self._sigma_key == (self.rho.data_ptr(), self.rho._version, self.rho.device):
+            return sig
+        return None
+
+    def refresh_sigma_cache(self, written_by_kernel: bool = False) -> Tensor:
+        """(Re)fill the cache from rho -- or, when a kernel has just written it, only mark it current."""
+        sig = getattr(self, "_sigma", None)
+        if sig is None or sig.shape != self.rho.shape or sig.device != self.rho.device:
+            sig = torch.empty_like(self.rho, dtype=torch.float32)
+            written_by_kernel = False
+        if not written_by_kernel:
+            from ... import _lib
+            with ops.on_device(self.rho.device):
+                _lib.check(_lib.load().bf_softplus_fwd(self.rho.data_ptr(), sig.data_ptr(), self.rho.numel(),
+                                                       ops._stream(self.rho.device)), "bf_softplus_fwd")
+        object.__setattr__(self, "_sigma", sig)  # a plain attribute: never a Parameter / buffer / state_dict entry
+        self._sigma_key = (self.rho.data_ptr(), self.rho._version, self.rho.device)
+        return sig
+
     # ---- eps stream -------------------------------------------------------
     def next_stream(self, S: int = 1) -> ops.StreamSpec:
         """Identity of this call's eps draw; advances the per-tensor step."""

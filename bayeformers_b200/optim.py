@@ -28,7 +28,11 @@ from ._lib import BF_BF16, BF_F32, BfOptDesc
 
 class ClipAdamW:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None) -> None:
+                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None,
+                 model: Optional[torch.nn.Module] = None) -> None:
+        """model: when given, every `Gaussian` of it whose rho is among `params` gets a sigma cache that this optimizer
+        keeps current (softplus of the updated rho is written next to the update), which the multi-tensor sampling
+        kernel then reads instead of recomputing softplus per element (nn/parameters/gaussian.py)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("ClipAdamW got no trainable parameters")
@@ -46,6 +50,16 @@ class ClipAdamW:
         self.device = dev
         # fp32 masters of the bf16 parameters (None for fp32 parameters, which are their own masters)
         self.master = [p.detach().float().clone() if p.dtype == torch.bfloat16 else None for p in self.params]
+        # sigma caches of the rho tensors (None for everything else)
+        self.gaussians = [None] * len(self.params)
+        if model is not None:
+            from .nn.parameters.gaussian import Gaussian
+            by_rho = {id(g.rho): g for g in model.modules() if isinstance(g, Gaussian)}
+            for i, p in enumerate(self.params):
+                g = by_rho.get(id(p))
+                if g is not None and p.dtype == torch.float32:
+                    g.refresh_sigma_cache()
+                    self.gaussians[i] = g
         self.exp_avg = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in self.params]
         self.exp_avg_sq = [torch.zeros(p.shape, dtype=torch.float32, device=dev) for p in self.params]
         self.step_count = torch.zeros(len(self.params), dtype=torch.float32, device=dev)  # per tensor, like torch
@@ -85,6 +99,8 @@ class ClipAdamW:
             d.param, d.exp_avg, d.exp_avg_sq = p.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr()
             d.n, d.dtype = p.numel(), (BF_BF16 if p.dtype == torch.bfloat16 else BF_F32)
             d.master = None if self.master[i] is None else self.master[i].data_ptr()
+            gs = self.gaussians[i]
+            d.sigma_out = None if (gs is None or getattr(gs, "_sigma", None) is None) else gs._sigma.data_ptr()
             if g is None:
                 d.grad = None
             else:
@@ -120,6 +136,11 @@ class ClipAdamW:
                 self.d_ws.data_ptr(), ops._stream(self.device)))
         _lib.check(rc, "bf_clip_adamw_step")
         ops.stats["launches"] += 2
+        for p, gs in zip(self.params, self.gaussians):
+            # the kernel has just written softplus(updated rho) for every tensor that had a gradient: if torch-side
+            # code had invalidated the cache in between (load_state_dict, ...), it is current again from here on
+            if gs is not None and p.grad is not None and gs.sigma_cache() is None and getattr(gs, "_sigma", None) is not None:
+                gs.refresh_sigma_cache(written_by_kernel=True)
         return self.grad_norm
 
     # ---- checkpointing (the reference saves no optimizer state, bert_glue.py:303-309; a resumable run needs it)

@@ -65,8 +65,9 @@ class Presampler:
     def _signature(self, S: int, tensors):
         sig = [S]
         for li, g, pr, dt in tensors:
+            sc = g.sigma_cache()
             sig += [g.mu.data_ptr(), g.rho.data_ptr(), pr.kind, 0 if pr.mu is None else pr.mu.data_ptr(),
-                    0 if pr.rho is None else pr.rho.data_ptr(), pr.sigma1, dt]
+                    0 if pr.rho is None else pr.rho.data_ptr(), pr.sigma1, dt, 0 if sc is None else sc.data_ptr()]
         return tuple(sig)
 
     def _build(self, S: int, tensors, dev: torch.device) -> None:
@@ -95,7 +96,9 @@ class Presampler:
             d.tensor_id, d.step = g.tensor_id, 0
             d.prior_kind, d.w_dtype = pr.kind, (BF_BF16 if dt == torch.bfloat16 else BF_F32)
             d.pi, d.sigma1, d.sigma2 = pr.pi, pr.sigma1, pr.sigma2
-            ptrs = [d.mu, d.rho, d.prior_mu or 0, d.prior_rho or 0]
+            sc = g.sigma_cache()  # softplus(rho) kept current by bf.optim.ClipAdamW: read instead of rho
+            d.sigma = None if sc is None else sc.data_ptr()
+            ptrs = [d.mu, d.rho, d.prior_mu or 0, d.prior_rho or 0, d.sigma or 0]
             d.vec = int(n % 4 == 0 and (n * esz) % 16 == 0 and all(p % 16 == 0 for p in ptrs))
             offsets.append((off, n, dt))
             if dt is not None:

@@ -82,6 +82,8 @@ def parse():
     ap.add_argument("--attention", type=int, default=0,
                     help="1: route the host model's short-sequence attention (T <= 128) through the native kernels "
                          "(correct, but at 110 TFLOP/s still behind cuDNN's fused attention: off by default)")
+    ap.add_argument("--sigma-cache", type=int, default=1,
+                    help="ClipAdamW writes softplus(updated rho) next to its update; the sampling kernel reads it")
     ap.add_argument("--gelu-links", type=int, default=1,
                     help="fold GELU' into the dgrad epilogue of the Linear that consumes a fused-GELU layer's output")
     ap.add_argument("--layers", type=int, default=0, help="debug: override num_hidden_layers")
@@ -422,7 +424,9 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     params = [p for p in bm.parameters() if p.requires_grad]
     use_graph = bool(args.graph) and not args.profile
     if args.fused_optim:  # global-norm clip + AdamW in two launches (section 8f row 3)
-        optim = bf.optim.ClipAdamW(params, lr=2e-5, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0)
+        # model=bm: the optimizer keeps a sigma = softplus(rho) cache current for the sampling kernel
+        optim = bf.optim.ClipAdamW(params, lr=2e-5, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
+                                   model=bm if args.sigma_cache else None)
     else:
         optim = torch.optim.AdamW(params, lr=2e-5, eps=1e-8, fused=True, capturable=use_graph)
     sync = parallel.GradSync(bm, average=not sample_shard)

@@ -145,8 +145,13 @@ typedef struct bf_tensor_desc {
     int32_t w_dtype;
     float pi, sigma1, sigma2;
     int32_t vec; /* 1: all pointers 16 B aligned, n % 4 == 0, (w_stride * elem) % 16 == 0 */
+    const float* sigma; /* NULL, or [n] fp32 = softplus(rho) kept up to date by the caller (bf_clip_adamw_step writes it
+                           through bf_opt_desc.sigma_out, bf_softplus_fwd fills it): read INSTEAD of rho, which spares
+                           the exp / log1p of the per-element prologue (vector path only; same bits as computing it) */
 } bf_tensor_desc;
 
+/* sigma[i] = softplus(rho[i]) with the library's own softplus (initial fill of a sigma cache) */
+int bf_softplus_fwd(const float* rho, float* sigma, int64_t n, void* stream);
 int32_t bf_sample_kl_multi_chunk_quads(void);
 int64_t bf_sample_kl_multi_workspace_bytes(int64_t n_chunks);
 int bf_sample_kl_fwd_multi(const bf_tensor_desc* descs, const int32_t* chunks, int32_t n_chunks,
@@ -409,6 +414,8 @@ typedef struct bf_opt_desc {
     int32_t vec;   /* 1: n % 4 == 0 and all pointers 16 B aligned (8 B for bf16 param / grad) */
     float* master; /* NULL, or [n] fp32 master copy of a BF_BF16 parameter: the update reads and writes the master
                       and stores its bf16 rounding in `param` (an update smaller than half a bf16 ulp is not lost) */
+    float* sigma_out; /* NULL, or [n] fp32: for a rho tensor, softplus(updated rho) is written next to the update, so
+                         the next forward's sampling reads sigma instead of recomputing it (bf_tensor_desc.sigma) */
 } bf_opt_desc;
 
 int32_t bf_optim_chunk_elems(void);

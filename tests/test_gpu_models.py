@@ -425,3 +425,51 @@ def test_eager_training_steps_do_not_leak_device_memory():
         gc.enable()
         bf.runtime.enable_grad_sinks(False)
     assert used[4] == used[3] == used[2], used
+
+
+# ------------------------------------------------------------------ sigma cache kept by the optimizer
+def test_sigma_cache_written_by_the_optimizer_changes_no_bit():
+    """ClipAdamW(model=...) writes softplus(updated rho) next to its update and the multi-tensor sampling kernel reads
+    that cache instead of rho: draws, log-probs and the next update must be bit-identical to the uncached path, before
+    and after optimizer steps, and a torch-side change of rho must invalidate the cache."""
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.Tanh(), torch.nn.Linear(512, 64))
+    x = torch.randn(3 * 16, 256, device=DEV)
+    S = 3
+    models, opts = [], []
+    for cached in (False, True):
+        bf.manual_seed(31)
+        bm = bf.to_bayesian(copy.deepcopy(net), delta=0.05, freeze=True, gemm_dtype="bf16", kl_grad=True).to(DEV)
+        bf.enable_presample(bm)
+        opts.append(bf.optim.ClipAdamW([p for p in bm.parameters() if p.requires_grad], lr=1e-2, max_grad_norm=1.0,
+                                       model=bm if cached else None))
+        models.append(bm)
+    gauss = [g for g in models[1].modules() if isinstance(g, bnn.Gaussian) and g.rho.requires_grad and g.rho.grad is None]
+    assert all(g.sigma_cache() is not None for g in gauss if any(g.rho is p for p in opts[1].params))
+    for step in range(3):
+        outs = []
+        for bm, opt in zip(models, opts):
+            opt.zero_grad()
+            with bf.mc_samples(S):
+                y = bm(x)
+            loss = y.float().square().mean() + 1e-3 * (bm.log_variational_posterior() - bm.log_prior()).mean()
+            loss.backward()
+            opt.step()
+            outs.append((y.detach().clone(), bm.log_prior().detach().clone(), bm.log_variational_posterior().detach().clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]), step
+        for pa, pb in zip(models[0].parameters(), models[1].parameters()):
+            assert torch.equal(pa, pb)
+    lin = [m for m in models[1].modules() if isinstance(m, bnn.Linear)][0]
+    sig = lin.weight.sigma_cache()
+    assert sig is not None and torch.equal(sig, bnn.Gaussian.sigma.fget(lin.weight).detach()) or \
+        rel_err(sig.cpu().numpy(), torch.nn.functional.softplus(lin.weight.rho.detach()).cpu().numpy()) < 1e-6
+    with torch.no_grad():
+        lin.weight.rho.add_(0.01)  # torch-side change: the cache must not be used any more
+    assert lin.weight.sigma_cache() is None
+    with bf.mc_samples(S):
+        models[1](x)  # uncached kernels for this tensor: no error, values follow the new rho
+    opts[1].zero_grad()
+    with bf.mc_samples(S):
+        models[1](x).float().sum().backward()
+    opts[1].step()
+    assert lin.weight.sigma_cache() is not None  # the optimizer's write made it current again
