@@ -444,6 +444,7 @@ def test_sigma_cache_written_by_the_optimizer_changes_no_bit():
         opts.append(bf.optim.ClipAdamW([p for p in bm.parameters() if p.requires_grad], lr=1e-2, max_grad_norm=1.0,
                                        model=bm if cached else None))
         models.append(bm)
+    bf.load_rng_state(models[1], bf.rng_state(models[0]))  # same stream ids and counters: both models draw the same eps
     gauss = [g for g in models[1].modules() if isinstance(g, bnn.Gaussian) and g.rho.requires_grad and g.rho.grad is None]
     assert all(g.sigma_cache() is not None for g in gauss if any(g.rho is p for p in opts[1].params))
     for step in range(3):
