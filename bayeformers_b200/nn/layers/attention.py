@@ -33,7 +33,7 @@ def attention_forward(module, query, key, value, attention_mask, dropout: float 
     if not hasattr(module, "_bf_site"):
         module._bf_site, module._bf_calls = runtime.next_tensor_id(), 0
     module._bf_calls += 1
-    drop = ops.DropoutSpec(p=float(dropout), seed=runtime.seed(), site_id=module._bf_site,
+    drop = ops.DropoutSpec(p=float(dropout), seed=runtime.dropout_seed(), site_id=module._bf_site,
                            step=module._bf_calls & 0xFFFFFFFF)
     module._last_dropout = drop  # identity of this forward's mask (tests, debugging)
     scale = float(scaling) if scaling is not None else float(query.shape[-1]) ** -0.5

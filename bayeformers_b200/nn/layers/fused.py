@@ -55,7 +55,7 @@ class FusedOutputMixin:
             raise ValueError(f"{h.numel() // h.shape[-1]} rows are not a multiple of mc_samples={S}")
         p = float(drop.p) if (drop.training and drop.p > 0) else 0.0
         self._bf_calls = getattr(self, "_bf_calls", 0) + 1
-        spec = ops.DropoutSpec(p=p, seed=runtime.seed(), site_id=self._bf_site, step=self._bf_calls & 0xFFFFFFFF)
+        spec = ops.DropoutSpec(p=p, seed=runtime.dropout_seed(), site_id=self._bf_site, step=self._bf_calls & 0xFFFFFFFF)
         self._last_dropout = spec  # identity of this forward's mask (tests, debugging)
         sink = runtime.sink_for(input_tensor, create=False) if runtime.grad_sinks_enabled() else None
         return ops.ResidualLayerNormFn.apply(h, input_tensor, gamma, beta, S, ln.eps, spec, box, sink)

@@ -34,6 +34,8 @@ def broadcast_seed(src: int = 0, group=None) -> int:
     t = torch.tensor([runtime.seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
     dist.broadcast(t, src=src, group=group)
     runtime.manual_seed(int(t.item()))
+    # same eps on every rank, but independent dropout masks on each rank's own rows (like per-rank torch generators)
+    runtime.set_dropout_salt(dist.get_rank(group))
     return runtime.seed()
 
 

@@ -22,7 +22,7 @@ import torch
 
 _state = threading.local()
 _tensor_ids = itertools.count(1)
-_global = {"seed": None, "kl_grad": False, "gemm_dtype": torch.float32}
+_global = {"seed": None, "kl_grad": False, "gemm_dtype": torch.float32, "dropout_salt": 0}
 
 
 def next_tensor_id() -> int:
@@ -42,6 +42,18 @@ def seed() -> int:
     if _global["seed"] is None:
         _global["seed"] = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
     return _global["seed"]
+
+
+def set_dropout_salt(salt: int) -> None:
+    """Per-rank salt of the DROPOUT streams (fused output blocks, native attention).  Under batch sharding every rank
+    must draw the same eps (same seed) but should NOT apply the same dropout mask to its own rows: `parallel.
+    broadcast_seed` sets the salt to the rank, which changes the masks and leaves the weight samples alone."""
+    _global["dropout_salt"] = int(salt)
+
+
+def dropout_seed() -> int:
+    """Seed of the counter-based dropout masks: the eps seed mixed with the per-rank salt."""
+    return (seed() + 0x9E3779B97F4A7C15 * _global["dropout_salt"]) & 0xFFFFFFFFFFFFFFFF
 
 
 def get_mc_samples() -> int:
@@ -250,7 +262,8 @@ def rng_state(model: torch.nn.Module) -> dict:
     into the reference and of reference checkpoints into this package.  Reads the device counters (one sync)."""
     from .nn.parameters.gaussian import Gaussian
 
-    out = {"version": 1, "seed": seed(), "gaussians": {}, "dropout_sites": {}, "presample_runs": None,
+    out = {"version": 1, "seed": seed(), "dropout_salt": _global["dropout_salt"], "gaussians": {}, "dropout_sites": {},
+           "presample_runs": None,
            "device_steps": {int(i): int(t.item()) for i, t in _device_step.items()}}
     for name, mod in model.named_modules():
         if isinstance(mod, Gaussian):
@@ -271,6 +284,7 @@ def load_rng_state(model: torch.nn.Module, state: dict) -> None:
     if state.get("version") != 1:
         raise ValueError(f"unknown rng_state version {state.get('version')!r}")
     manual_seed(int(state["seed"]))
+    set_dropout_salt(int(state.get("dropout_salt", 0)))
     mods = dict(model.named_modules())
     for name, g in state["gaussians"].items():
         mod = mods.get(name)

@@ -350,3 +350,35 @@ def test_reference_checkpoint_loads_strictly_and_back(kw):
     back.load_state_dict(ours.state_dict(), strict=True)
     for k, v in back.state_dict().items():
         assert torch.equal(v, ref_sd[k]), k
+
+
+def test_rng_state_round_trip_restores_stream_ids_and_counters():
+    """bf.rng_state / bf.load_rng_state (reproducible resume): seed, dropout salt, per-tensor stream ids / steps and the
+    fused blocks' call counters survive a round trip into freshly built objects; pure host logic, no kernels."""
+    import copy
+    import bayeformers_b200 as bf
+    import bayeformers_b200.nn as bnn
+    from bayeformers_b200 import runtime
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    bf.manual_seed(4711)
+    a = bf.to_bayesian(net, delta=0.05)
+    gs = [m for m in a.modules() if isinstance(m, bnn.Gaussian)]
+    for k, g in enumerate(gs):
+        g.step = 10 + k
+    runtime.set_dropout_salt(3)
+    state = copy.deepcopy(bf.rng_state(a))
+    assert state["seed"] == 4711 and state["dropout_salt"] == 3 and len(state["gaussians"]) == len(gs)
+    bf.manual_seed(1)
+    runtime.set_dropout_salt(0)
+    b = bf.to_bayesian(net, delta=0.05)  # fresh stream ids
+    gb = [m for m in b.modules() if isinstance(m, bnn.Gaussian)]
+    assert [g.tensor_id for g in gb] != [g.tensor_id for g in gs]
+    bf.load_rng_state(b, state)
+    assert runtime.seed() == 4711 and runtime.dropout_seed() != runtime.seed()
+    assert [(g.tensor_id, g.step) for g in gb] == [(g.tensor_id, g.step) for g in gs]
+    runtime.set_dropout_salt(0)
+    assert runtime.dropout_seed() == runtime.seed()
+    with pytest.raises(KeyError):
+        bf.load_rng_state(torch.nn.Sequential(torch.nn.Linear(2, 2)), state)
