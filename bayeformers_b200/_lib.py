@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libbayeformers_b200.so")
 ABI_VERSION = 2
 BF_F32, BF_BF16 = 0, 1
 BF_PRIOR_MIXTURE, BF_PRIOR_GAUSSIAN, BF_PRIOR_NONE = 0, 1, 2
-BF_OPT_GEMM_2CTA, BF_OPT_WGRAD_2CTA, BF_OPT_RESLN_BWD_STAGED, BF_OPT_SK_PREFETCH = 0, 1, 2, 3
+BF_OPT_GEMM_2CTA, BF_OPT_WGRAD_2CTA, BF_OPT_RESLN_BWD_STAGED, BF_OPT_SK_PREFETCH, BF_OPT_ATTN_TC = 0, 1, 2, 3, 4
 
 class BfTensorDesc(ctypes.Structure):
     """`bf_tensor_desc` of include/bayeformers_b200.h (multi-tensor sample+KL)."""
@@ -111,10 +111,10 @@ SIGNATURES = {
     "bf_dropout_mask": (c_int32, [c_void_p, c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p]),
     "bf_attention_supported": (c_int32, [c_int64, c_int64]),
     "bf_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,
-                                   c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]),
-    "bf_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                   c_int64, c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bf_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int64, c_int64, c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     "bf_attention_dropout_mask": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint32,
                                             c_void_p]),
 }

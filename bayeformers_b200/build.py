@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libbayeformers_b200.so")
-SOURCES = ["bf_api.cu", "bf_sample_kl.cu", "bf_gemm_simt.cu", "bf_gemm_tc.cu", "bf_gemm_tc2.cu", "bf_gemm_act.cu", "bf_wgrad_tc.cu", "bf_linear.cu", "bf_layernorm.cu", "bf_optim.cu", "bf_resln.cu", "bf_embedding.cu", "bf_attention.cu"]
+SOURCES = ["bf_api.cu", "bf_sample_kl.cu", "bf_gemm_simt.cu", "bf_gemm_tc.cu", "bf_gemm_tc2.cu", "bf_gemm_act.cu", "bf_wgrad_tc.cu", "bf_linear.cu", "bf_layernorm.cu", "bf_optim.cu", "bf_resln.cu", "bf_embedding.cu", "bf_attention.cu", "bf_attention_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -31,8 +31,11 @@ namespace attn {
 constexpr int TMAX = 128, D = 64, kThreads = 256;  // 8 warps x 16 query rows (phase B of the backward: x 16 keys)
 constexpr int TILE_BYTES = TMAX * D * 2;      // one [128, 64] bf16 tile: 16 KiB
 constexpr int SQ_BYTES = TMAX * TMAX * 2;     // one [128, 128] bf16 tile: 32 KiB
-constexpr int FWD_SMEM = 3 * TILE_BYTES;                    // q, k, v
-constexpr int BWD_SMEM = 4 * TILE_BYTES + 2 * SQ_BYTES;     // q, k, v, dO, P_d, dS
+constexpr int kBwdThreads = 512;              // backward: 16 warps = 8 row groups x 2 key halves
+constexpr int FWD_BUF = 3 * TILE_BYTES;       // q, k, v of one pair
+constexpr int FWD_SMEM = 2 * FWD_BUF;         // double buffered: 96 KiB, two blocks per SM
+constexpr int BWD_BUF = 4 * TILE_BYTES;       // q, k, v, dO of one pair
+constexpr int BWD_SMEM = 2 * BWD_BUF + 2 * SQ_BYTES + 2 * TMAX * 4;  // + P_d, dS, partial D: 193 KiB
 
 struct Params {
     const __nv_bfloat16 *q, *k, *v, *o, *dout;
@@ -70,7 +73,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // byte offset of element (row, col) in a [rows][64] bf16 tile (128 B rows, 16 B chunks XOR-swizzled by row % 8)
 __device__ __forceinline__ uint32_t off64(int row, int col) {
@@ -84,7 +89,7 @@ __device__ __forceinline__ uint32_t off128(int row, int col) {
 
 // [T, 64] rows of one (batch, head) from global memory into a swizzled tile; rows >= T are zero-filled
 __device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* base, int64_t st, int T) {
-    for (int i = threadIdx.x; i < TMAX * 8; i += kThreads) {
+    for (int i = threadIdx.x; i < TMAX * 8; i += blockDim.x) {
         const int r = i >> 3, ch = i & 7;
         uint8_t* dst = tile + r * 128 + (((ch ^ r) & 7) << 4);
         if (r < T) cp_async16(smem_u32(dst), base + (int64_t)r * st + ch * 8);
@@ -92,12 +97,14 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* ba
     }
 }
 
-// keep bits of the 32 values a thread holds of query row `row` (tiles j = 0..15, e = 0..1 -> bit 2*j + e)
-__device__ __forceinline__ uint32_t keep_bits(const Params& p, uint32_t row, int c, uint32_t step) {
+// keep bits of the values a thread holds of query row `row` in key tiles 4 * m0 .. 4 * (m0 + NM) - 1
+// (local tile jl, element e -> bit 2 * jl + e); one Philox call covers 4 tiles
+template <int NM>
+__device__ __forceinline__ uint32_t keep_bits(const Params& p, uint32_t row, int c, uint32_t step, int m0) {
     uint32_t bits = 0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const uint4 r = bf_philox4x32_10(row, (uint32_t)(c + 4 * m), 0x40000000u | p.site, step, p.k0, p.k1);
+    for (int m = 0; m < NM; ++m) {
+        const uint4 r = bf_philox4x32_10(row, (uint32_t)(c + 4 * (m0 + m)), 0x40000000u | p.site, step, p.k0, p.k1);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -109,50 +116,85 @@ __device__ __forceinline__ uint32_t keep_bits(const Params& p, uint32_t row, int
     return bits;
 }
 
-// S = q_w k^T for the 16 query rows of this warp: s[j] = accumulator of key tile j (keys 8j .. 8j+7)
-__device__ __forceinline__ void scores(float (&s)[16][4], const uint8_t* sA, const uint8_t* sB, int row0, int lane) {
+// S = A_w B^T for the 16 rows of this warp and 16 * NJP rows of B starting at key0: s[j] = accumulator of the
+// 8 columns key0 + 8j .. key0 + 8j + 7.  A, B are [rows][64] tiles.
+template <int NJP>
+__device__ __forceinline__ void scores(float (&s)[2 * NJP][4], const uint8_t* sA, const uint8_t* sB, int row0, int key0,
+                                       int lane) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+    for (int j = 0; j < 2 * NJP; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         uint32_t a[4];
         ldsm_x4(a, a_base + off64(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 16 + (lane >> 4) * 8));
 #pragma unroll
-        for (int jp = 0; jp < 8; ++jp) {
+        for (int jp = 0; jp < NJP; ++jp) {
             uint32_t b[4];
-            ldsm_x4(b, b_base + off64(jp * 16 + (lane & 7) + (lane >> 4) * 8, kk * 16 + ((lane >> 3) & 1) * 8));
+            ldsm_x4(b, b_base + off64(key0 + jp * 16 + (lane & 7) + (lane >> 4) * 8, kk * 16 + ((lane >> 3) & 1) * 8));
             mma16816(s[2 * jp], a, b[0], b[1]);
             mma16816(s[2 * jp + 1], a, b[2], b[3]);
         }
     }
 }
 
+// the 16 x 64 accumulator tile of a warp (o[j]: columns 8j + 2c, +1 of rows g and g + 8) -> its own 16 rows of a
+// [rows][64] staging tile -> 128 B rows of global memory, 16 B per lane
+__device__ __forceinline__ void store_rows64(uint8_t* stage, int row0, const float (&o)[8][4], float r0, float r1,
+                                             __nv_bfloat16* gbase, int64_t g_st, int lane) {
+    const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t*>(stage + off64(row0 + g, 8 * j + 2 * c)) = pack_bf16(o[j][0] * r0, o[j][1] * r0);
+        *reinterpret_cast<uint32_t*>(stage + off64(row0 + g + 8, 8 * j + 2 * c)) = pack_bf16(o[j][2] * r1, o[j][3] * r1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + 4 * i + (lane >> 3), ch = lane & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + off64(r, 8 * ch));
+        *reinterpret_cast<uint4*>(gbase + (int64_t)r * g_st + 8 * ch) = val;
+    }
+}
+
 // ------------------------------------------------------------------ forward
+// Two (sequence, head) pairs are in flight per block: the q / k / v tiles of the next pair arrive (cp.async) while the
+// current one is computed.  FULL: T == 128, no tile-range predicates.
+template <bool FULL>
 __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* const sQ = smem;
-    uint8_t* const sK = smem + TILE_BYTES;
-    uint8_t* const sV = smem + 2 * TILE_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
-    const int T = p.T;
-    for (int pair = blockIdx.x; pair < p.B * p.H; pair += gridDim.x) {
+    const int T = FULL ? TMAX : p.T;
+    const int total = p.B * p.H;
+    auto issue = [&](int pair, int buf) {
         const int b = pair / p.H, h = pair - b * p.H;
-        load_tile(sQ, p.q + b * p.q_sb + h * p.q_sh, p.q_st, T);
-        load_tile(sK, p.k + b * p.k_sb + h * p.k_sh, p.k_st, T);
-        load_tile(sV, p.v + b * p.v_sb + h * p.v_sh, p.v_st, T);
-        cp_async_wait_all();
+        uint8_t* const base = smem + buf * FWD_BUF;
+        load_tile(base, p.q + b * p.q_sb + h * p.q_sh, p.q_st, T);
+        load_tile(base + TILE_BYTES, p.k + b * p.k_sb + h * p.k_sh, p.k_st, T);
+        load_tile(base + 2 * TILE_BYTES, p.v + b * p.v_sb + h * p.v_sh, p.v_st, T);
+    };
+    if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+    cp_async_commit();
+    int it = 0;
+    for (int pair = blockIdx.x; pair < total; pair += gridDim.x, ++it) {
+        const int b = pair / p.H, h = pair - b * p.H;
+        if (pair + (int)gridDim.x < total) issue(pair + gridDim.x, (it + 1) & 1);
+        cp_async_commit();
+        cp_async_wait_group<1>();
         __syncthreads();
+        uint8_t* const sQ = smem + (it & 1) * FWD_BUF;
+        const uint8_t* const sK = sQ + TILE_BYTES;
+        const uint8_t* const sV = sQ + 2 * TILE_BYTES;
         const int row0 = warp * 16;
-        if (row0 < T) {
+        if (FULL || row0 < T) {
             float s[16][4];
-            scores(s, sQ, sK, row0, lane);
+            scores<8>(s, sQ, sK, row0, 0, lane);
             // ---- softmax of rows (row0 + g) and (row0 + g + 8); a row lives in the 4 lanes of a quad
             float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (8 * j < T) {  // T % 16 == 0: a tile is either wholly inside or wholly outside
+                if (FULL || 8 * j < T) {  // T % 16 == 0: a tile is either wholly inside or wholly outside
                     mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
                     mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
                 }
@@ -166,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const Params
             const float off0 = mx[0] * p.scale_log2e, off1 = mx[1] * p.scale_log2e;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const bool in = 8 * j < T;
+                const bool in = FULL || 8 * j < T;
                 s[j][0] = in ? bf_ex2_approx(fmaf(s[j][0], p.scale_log2e, -off0)) : 0.0f;
                 s[j][1] = in ? bf_ex2_approx(fmaf(s[j][1], p.scale_log2e, -off0)) : 0.0f;
                 s[j][2] = in ? bf_ex2_approx(fmaf(s[j][2], p.scale_log2e, -off1)) : 0.0f;
@@ -186,7 +228,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const Params
             }
             // ---- dropout on the (unnormalised) probabilities; 1 / sum is applied to the output rows
             if (p.thresh != 0u) {
-                const uint32_t kb0 = keep_bits(p, (uint32_t)grow, c, step), kb1 = keep_bits(p, (uint32_t)(grow + 8), c, step);
+                const uint32_t kb0 = keep_bits<4>(p, (uint32_t)grow, c, step, 0);
+                const uint32_t kb1 = keep_bits<4>(p, (uint32_t)(grow + 8), c, step, 0);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     s[j][0] = ((kb0 >> (2 * j)) & 1u) ? s[j][0] * p.inv_keep : 0.0f;
@@ -213,198 +256,189 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const Params
                     mma16816(o[2 * np + 1], a, vb[2], vb[3]);
                 }
             }
-            const float r0 = bf_rcp_approx(sum[0]), r1 = bf_rcp_approx(sum[1]);
-            // out[b][t][h][:]  (each quad writes 16 contiguous bytes per tile)
-            __nv_bfloat16* const orow = p.out + (((int64_t)b * T + row0 + g) * p.H + h) * D + 2 * c;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                *reinterpret_cast<uint32_t*>(orow + 8 * j) = pack_bf16(o[j][0] * r0, o[j][1] * r0);
-                *reinterpret_cast<uint32_t*>(orow + (int64_t)8 * p.H * D + 8 * j) = pack_bf16(o[j][2] * r1, o[j][3] * r1);
-            }
+            // out[b][t][h][:] through the warp's own (now dead) q rows: whole 128 B rows per store
+            store_rows64(sQ, row0, o, bf_rcp_approx(sum[0]), bf_rcp_approx(sum[1]),
+                         p.out + ((int64_t)b * T * p.H + h) * D, (int64_t)p.H * D, lane);
         }
-        __syncthreads();  // the next pair's loads overwrite the tiles
+        __syncthreads();  // the loads issued by the next iteration overwrite this buffer's partner... and then this one
     }
+    cp_async_wait_group<0>();
 }
 
 // ------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(kThreads, 1) attention_bwd_kernel(const Params p) {
+// 16 warps: warp w owns query rows 16 * (w % 8) and, in phase A, the key half w / 8 -- so a thread holds 32 scores,
+// not 64, and four warps per scheduler hide each other's latencies.  The q / k / v / dO tiles of the next pair arrive
+// while this one is computed.
+//   phase A : S, P (from the stored log-sum-exp), keep mask, dP = dO v^T for (16 rows) x (64 keys);
+//             partial D_i = sum_k P_d[i][k] dP_d[i][k] (== rowsum(dO o O), so O is never read) -> shared memory;
+//             P_d -> sP.                       barrier
+//             dS = P o (dP_d - D) * scale -> sS.   barrier
+//   phase B : warps 0..7: dv (their 16 keys) = P_d^T dO;  warps 8..15: dk (their 16 keys) = dS^T q;
+//             every warp: dq (its 16 rows, d half w / 8) = dS k.
+template <bool FULL>
+__global__ void __launch_bounds__(kBwdThreads, 1) attention_bwd_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* const sQ = smem;
-    uint8_t* const sK = smem + TILE_BYTES;
-    uint8_t* const sV = smem + 2 * TILE_BYTES;
-    uint8_t* const sO = smem + 3 * TILE_BYTES;  // dO
-    uint8_t* const sP = smem + 4 * TILE_BYTES;  // P_d [q][key]
-    uint8_t* const sS = sP + SQ_BYTES;          // dS  [q][key]
+    uint8_t* const sP = smem + 2 * BWD_BUF;  // P_d [q][key]
+    uint8_t* const sS = sP + SQ_BYTES;       // dS  [q][key]
+    float* const sD = reinterpret_cast<float*>(sS + SQ_BYTES);  // [2][128] partial D of the two key halves
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int rw = warp & 7, kh = warp >> 3, row0 = rw * 16, key0 = 64 * kh;
     const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
-    const int T = p.T;
-    for (int pair = blockIdx.x; pair < p.B * p.H; pair += gridDim.x) {
+    const int T = FULL ? TMAX : p.T;
+    const int total = p.B * p.H;
+    const int64_t o_st = (int64_t)p.H * D;
+    auto issue = [&](int pair, int buf) {
+        const int b = pair / p.H, h = pair - b * p.H;
+        uint8_t* const base = smem + buf * BWD_BUF;
+        load_tile(base, p.q + b * p.q_sb + h * p.q_sh, p.q_st, T);
+        load_tile(base + TILE_BYTES, p.k + b * p.k_sb + h * p.k_sh, p.k_st, T);
+        load_tile(base + 2 * TILE_BYTES, p.v + b * p.v_sb + h * p.v_sh, p.v_st, T);
+        load_tile(base + 3 * TILE_BYTES, p.dout + ((int64_t)b * T * p.H + h) * D, o_st, T);
+    };
+    if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+    cp_async_commit();
+    const float ik = p.thresh != 0u ? p.inv_keep : 1.0f;
+    int it = 0;
+    for (int pair = blockIdx.x; pair < total; pair += gridDim.x, ++it) {
         const int b = pair / p.H, h = pair - b * p.H;
         const int64_t o_base = ((int64_t)b * T * p.H + h) * D;  // [b][0][h][0] of the [B, T, H, 64] tensors
-        const int64_t o_st = (int64_t)p.H * D;
-        load_tile(sQ, p.q + b * p.q_sb + h * p.q_sh, p.q_st, T);
-        load_tile(sK, p.k + b * p.k_sb + h * p.k_sh, p.k_st, T);
-        load_tile(sV, p.v + b * p.v_sb + h * p.v_sh, p.v_st, T);
-        load_tile(sO, p.dout + o_base, o_st, T);
-        const int row0 = warp * 16;
-        // ---- D_i = sum_d dO[i][d] * O[i][d] for the rows of this warp (2 lanes per row), while the tiles arrive
-        float dsum = 0.0f;
-        {
-            const int r = row0 + (lane >> 1);
-            if (r < T) {
-                const __nv_bfloat16* po = p.o + o_base + (int64_t)r * o_st + (lane & 1) * 32;
-                const __nv_bfloat16* pg = p.dout + o_base + (int64_t)r * o_st + (lane & 1) * 32;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(po) + i), d = __ldg(reinterpret_cast<const uint4*>(pg) + i);
-                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        dsum = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(dw[e] << 16), dsum);
-                        dsum = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(dw[e] & 0xffff0000u), dsum);
-                    }
-                }
-            }
-            dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-        }
-        // rows (row0 + g) and (row0 + g + 8) of this thread: lanes 2g, 2g+1 hold row g; lanes 2g+16, 2g+17 row g+8
-        const float D0 = __shfl_sync(0xffffffffu, dsum, 2 * g), D1 = __shfl_sync(0xffffffffu, dsum, 2 * g + 16);
+        if (pair + (int)gridDim.x < total) issue(pair + gridDim.x, (it + 1) & 1);
+        cp_async_commit();
+        const bool rows_in = FULL || row0 < T;
         const int64_t grow = ((int64_t)b * p.H + h) * T + row0 + g;
         float lse0 = 0.0f, lse1 = 0.0f;
-        if (row0 < T) lse0 = __ldg(p.lse + grow), lse1 = __ldg(p.lse + grow + 8);
-        cp_async_wait_all();
+        if (rows_in) lse0 = __ldg(p.lse + grow), lse1 = __ldg(p.lse + grow + 8);
+        cp_async_wait_group<1>();
         __syncthreads();
+        const uint8_t* const sQ = smem + (it & 1) * BWD_BUF;
+        const uint8_t* const sK = sQ + TILE_BYTES;
+        const uint8_t* const sV = sQ + 2 * TILE_BYTES;
+        const uint8_t* const sO = sQ + 3 * TILE_BYTES;  // dO
 
-        // =============== phase A: the 16 query rows of this warp ===============
-        {
-            float s[16][4];
-            uint32_t pa[8][4];  // P_d as bf16 A fragments (also what goes to sP)
-            if (row0 < T) {
-                scores(s, sQ, sK, row0, lane);
-                uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu;
-                if (p.thresh != 0u) kb0 = keep_bits(p, (uint32_t)grow, c, step), kb1 = keep_bits(p, (uint32_t)(grow + 8), c, step);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {  // true probabilities P
-                    const bool in = 8 * j < T;
-                    s[j][0] = in ? bf_ex2_approx(fmaf(s[j][0], p.scale_log2e, -lse0)) : 0.0f;
-                    s[j][1] = in ? bf_ex2_approx(fmaf(s[j][1], p.scale_log2e, -lse0)) : 0.0f;
-                    s[j][2] = in ? bf_ex2_approx(fmaf(s[j][2], p.scale_log2e, -lse1)) : 0.0f;
-                    s[j][3] = in ? bf_ex2_approx(fmaf(s[j][3], p.scale_log2e, -lse1)) : 0.0f;
-                }
-                const float ik = p.thresh != 0u ? p.inv_keep : 1.0f;
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    const int j0 = 2 * kc, j1 = 2 * kc + 1;
-                    pa[kc][0] = pack_bf16(((kb0 >> (2 * j0)) & 1u) ? s[j0][0] * ik : 0.0f, ((kb0 >> (2 * j0 + 1)) & 1u) ? s[j0][1] * ik : 0.0f);
-                    pa[kc][1] = pack_bf16(((kb1 >> (2 * j0)) & 1u) ? s[j0][2] * ik : 0.0f, ((kb1 >> (2 * j0 + 1)) & 1u) ? s[j0][3] * ik : 0.0f);
-                    pa[kc][2] = pack_bf16(((kb0 >> (2 * j1)) & 1u) ? s[j1][0] * ik : 0.0f, ((kb0 >> (2 * j1 + 1)) & 1u) ? s[j1][1] * ik : 0.0f);
-                    pa[kc][3] = pack_bf16(((kb1 >> (2 * j1)) & 1u) ? s[j1][2] * ik : 0.0f, ((kb1 >> (2 * j1 + 1)) & 1u) ? s[j1][3] * ik : 0.0f);
-                }
-                // dP_d = dO_w v^T (same shape of product as the scores: A = dO rows, B = v as [key][d])
-                float dp[16][4];
-                scores(dp, sO, sV, row0, lane);
-                // dS = P o (keep ? dP_d / (1-p) : 0  -  D) * scale, kept as bf16 A fragments in s's place
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float d0 = ((kb0 >> (2 * j)) & 1u) ? dp[j][0] * ik : 0.0f, d1 = ((kb0 >> (2 * j + 1)) & 1u) ? dp[j][1] * ik : 0.0f;
-                    const float d2 = ((kb1 >> (2 * j)) & 1u) ? dp[j][2] * ik : 0.0f, d3 = ((kb1 >> (2 * j + 1)) & 1u) ? dp[j][3] * ik : 0.0f;
-                    s[j][0] = s[j][0] * (d0 - D0) * p.scale;
-                    s[j][1] = s[j][1] * (d1 - D0) * p.scale;
-                    s[j][2] = s[j][2] * (d2 - D1) * p.scale;
-                    s[j][3] = s[j][3] * (d3 - D1) * p.scale;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) pa[kc][0] = pa[kc][1] = pa[kc][2] = pa[kc][3] = 0u;
+        // =============== phase A: 16 query rows x 64 keys per warp ===============
+        float s[8][4], dp[8][4];
+        uint32_t kb0 = 0xffffffffu, kb1 = 0xffffffffu;
+        if (rows_in) {
+            scores<4>(s, sQ, sK, row0, key0, lane);
+            if (p.thresh != 0u) {
+                kb0 = keep_bits<2>(p, (uint32_t)grow, c, step, 2 * kh);
+                kb1 = keep_bits<2>(p, (uint32_t)(grow + 8), c, step, 2 * kh);
             }
-            // stage P_d and dS as [q][key] bf16 for the transposed products of phase B
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g, 16 * kc + 2 * c)) = pa[kc][0];
-                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g + 8, 16 * kc + 2 * c)) = pa[kc][1];
-                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g, 16 * kc + 8 + 2 * c)) = pa[kc][2];
-                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g + 8, 16 * kc + 8 + 2 * c)) = pa[kc][3];
+            for (int j = 0; j < 8; ++j) {  // true probabilities P
+                const bool in = FULL || key0 + 8 * j < T;
+                s[j][0] = in ? bf_ex2_approx(fmaf(s[j][0], p.scale_log2e, -lse0)) : 0.0f;
+                s[j][1] = in ? bf_ex2_approx(fmaf(s[j][1], p.scale_log2e, -lse0)) : 0.0f;
+                s[j][2] = in ? bf_ex2_approx(fmaf(s[j][2], p.scale_log2e, -lse1)) : 0.0f;
+                s[j][3] = in ? bf_ex2_approx(fmaf(s[j][3], p.scale_log2e, -lse1)) : 0.0f;
             }
-            uint32_t da[8][4];
+            // dP_d = dO_w v^T (same shape of product as the scores: A = dO rows, B = v as [key][d])
+            scores<4>(dp, sO, sV, row0, key0, lane);
+            float part0 = 0.0f, part1 = 0.0f;
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                da[kc][0] = pack_bf16(s[2 * kc][0], s[2 * kc][1]);
-                da[kc][1] = pack_bf16(s[2 * kc][2], s[2 * kc][3]);
-                da[kc][2] = pack_bf16(s[2 * kc + 1][0], s[2 * kc + 1][1]);
-                da[kc][3] = pack_bf16(s[2 * kc + 1][2], s[2 * kc + 1][3]);
-                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g, 16 * kc + 2 * c)) = da[kc][0];
-                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g + 8, 16 * kc + 2 * c)) = da[kc][1];
-                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g, 16 * kc + 8 + 2 * c)) = da[kc][2];
-                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g + 8, 16 * kc + 8 + 2 * c)) = da[kc][3];
+            for (int j = 0; j < 8; ++j) {
+                // dp <- keep ? dP_d / (1 - p) : 0 (the gradient w.r.t. the undropped probability)
+                dp[j][0] = ((kb0 >> (2 * j)) & 1u) ? dp[j][0] * ik : 0.0f;
+                dp[j][1] = ((kb0 >> (2 * j + 1)) & 1u) ? dp[j][1] * ik : 0.0f;
+                dp[j][2] = ((kb1 >> (2 * j)) & 1u) ? dp[j][2] * ik : 0.0f;
+                dp[j][3] = ((kb1 >> (2 * j + 1)) & 1u) ? dp[j][3] * ik : 0.0f;
+                part0 = fmaf(s[j][0], dp[j][0], fmaf(s[j][1], dp[j][1], part0));
+                part1 = fmaf(s[j][2], dp[j][2], fmaf(s[j][3], dp[j][3], part1));
             }
-            if (row0 < T) {
-                // dq_w = dS_w k  (B = k as [key][d] read transposed)
-                float dq[8][4];
+            part0 += __shfl_xor_sync(0xffffffffu, part0, 1);
+            part0 += __shfl_xor_sync(0xffffffffu, part0, 2);
+            part1 += __shfl_xor_sync(0xffffffffu, part1, 1);
+            part1 += __shfl_xor_sync(0xffffffffu, part1, 2);
+            if (c == 0) sD[kh * TMAX + row0 + g] = part0, sD[kh * TMAX + row0 + g + 8] = part1;
+            // P_d as bf16 -> sP[q][key]
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
-                const uint32_t k_base = smem_u32(sK);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-#pragma unroll
-                    for (int np = 0; np < 4; ++np) {
-                        uint32_t kb[4];
-                        ldsm_x4_t(kb, k_base + off64(kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
-                        mma16816(dq[2 * np], da[kc], kb[0], kb[1]);
-                        mma16816(dq[2 * np + 1], da[kc], kb[2], kb[3]);
-                    }
-                }
-                __nv_bfloat16* const qrow = p.dq + o_base + (int64_t)(row0 + g) * o_st + 2 * c;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    *reinterpret_cast<uint32_t*>(qrow + 8 * j) = pack_bf16(dq[j][0], dq[j][1]);
-                    *reinterpret_cast<uint32_t*>(qrow + 8 * o_st + 8 * j) = pack_bf16(dq[j][2], dq[j][3]);
-                }
+            for (int kc = 0; kc < 4; ++kc) {
+                const int j0 = 2 * kc, j1 = 2 * kc + 1, col = key0 + 16 * kc + 2 * c;
+                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g, col)) =
+                    pack_bf16(((kb0 >> (2 * j0)) & 1u) ? s[j0][0] * ik : 0.0f, ((kb0 >> (2 * j0 + 1)) & 1u) ? s[j0][1] * ik : 0.0f);
+                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g + 8, col)) =
+                    pack_bf16(((kb1 >> (2 * j0)) & 1u) ? s[j0][2] * ik : 0.0f, ((kb1 >> (2 * j0 + 1)) & 1u) ? s[j0][3] * ik : 0.0f);
+                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g, col + 8)) =
+                    pack_bf16(((kb0 >> (2 * j1)) & 1u) ? s[j1][0] * ik : 0.0f, ((kb0 >> (2 * j1 + 1)) & 1u) ? s[j1][1] * ik : 0.0f);
+                *reinterpret_cast<uint32_t*>(sP + off128(row0 + g + 8, col + 8)) =
+                    pack_bf16(((kb1 >> (2 * j1)) & 1u) ? s[j1][2] * ik : 0.0f, ((kb1 >> (2 * j1 + 1)) & 1u) ? s[j1][3] * ik : 0.0f);
             }
         }
-        __syncthreads();
-
-        // =============== phase B: the 16 keys of this warp: dv = P_d^T dO, dk = dS^T q ===============
-        if (row0 < T) {
-            const int key0 = row0;
-            float dv[8][4], dk[8][4];
+        __syncthreads();  // both halves of D are there
+        if (rows_in) {
+            // D_i = sum_k P[i][k] * (keep ? dP_d / (1-p) : 0) = sum_k P_d[i][k] dP_d[i][k]
+            const float D0 = sD[row0 + g] + sD[TMAX + row0 + g], D1 = sD[row0 + g + 8] + sD[TMAX + row0 + g + 8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.0f;
-            const uint32_t p_base = smem_u32(sP), s_base = smem_u32(sS), o_smem = smem_u32(sO), q_smem = smem_u32(sQ);
+            for (int kc = 0; kc < 4; ++kc) {
+                const int j0 = 2 * kc, j1 = 2 * kc + 1, col = key0 + 16 * kc + 2 * c;
+                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g, col)) =
+                    pack_bf16(s[j0][0] * (dp[j0][0] - D0) * p.scale, s[j0][1] * (dp[j0][1] - D0) * p.scale);
+                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g + 8, col)) =
+                    pack_bf16(s[j0][2] * (dp[j0][2] - D1) * p.scale, s[j0][3] * (dp[j0][3] - D1) * p.scale);
+                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g, col + 8)) =
+                    pack_bf16(s[j1][0] * (dp[j1][0] - D0) * p.scale, s[j1][1] * (dp[j1][1] - D0) * p.scale);
+                *reinterpret_cast<uint32_t*>(sS + off128(row0 + g + 8, col + 8)) =
+                    pack_bf16(s[j1][2] * (dp[j1][2] - D1) * p.scale, s[j1][3] * (dp[j1][3] - D1) * p.scale);
+            }
+        }
+        __syncthreads();  // P_d and dS complete
+
+        // =============== phase B ===============
+        if (rows_in) {
+            // ---- dv (warps 0..7) or dk (warps 8..15) of the 16 keys row0 .. row0 + 15: A = transposed 16 x 16 blocks of
+            //      sP / sS, B = dO / q as [query][d]
+            float acc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+            const uint32_t a_base = smem_u32(kh == 0 ? sP : sS), b_base = smem_u32(kh == 0 ? sO : sQ);
             const int mi = lane >> 3;
 #pragma unroll
             for (int qc = 0; qc < 8; ++qc) {
-                if (16 * qc >= T) break;
-                // A fragments = transposed 16(keys) x 16(queries) blocks of the [q][key] tiles
-                const int qr = qc * 16 + (lane & 7) + (mi >> 1) * 8, kcol = key0 + (mi & 1) * 8;
-                uint32_t ap[4], as[4];
-                ldsm_x4_t(ap, p_base + off128(qr, kcol));
-                ldsm_x4_t(as, s_base + off128(qr, kcol));
+                if (!FULL && 16 * qc >= T) break;
+                uint32_t a[4];
+                ldsm_x4_t(a, a_base + off128(qc * 16 + (lane & 7) + (mi >> 1) * 8, row0 + (mi & 1) * 8));
 #pragma unroll
                 for (int np = 0; np < 4; ++np) {
-                    uint32_t ob[4], qb[4];
-                    const uint32_t o = off64(qc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8);
-                    ldsm_x4_t(ob, o_smem + o);
-                    ldsm_x4_t(qb, q_smem + o);
-                    mma16816(dv[2 * np], ap, ob[0], ob[1]);
-                    mma16816(dv[2 * np + 1], ap, ob[2], ob[3]);
-                    mma16816(dk[2 * np], as, qb[0], qb[1]);
-                    mma16816(dk[2 * np + 1], as, qb[2], qb[3]);
+                    uint32_t bb[4];
+                    ldsm_x4_t(bb, b_base + off64(qc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
+                    mma16816(acc[2 * np], a, bb[0], bb[1]);
+                    mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
                 }
             }
-            __nv_bfloat16* const vrow = p.dv + o_base + (int64_t)(key0 + g) * o_st + 2 * c;
-            __nv_bfloat16* const krow = p.dk + o_base + (int64_t)(key0 + g) * o_st + 2 * c;
+            __nv_bfloat16* const orow = (kh == 0 ? p.dv : p.dk) + o_base + (int64_t)(row0 + g) * o_st + 2 * c;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                *reinterpret_cast<uint32_t*>(vrow + 8 * j) = pack_bf16(dv[j][0], dv[j][1]);
-                *reinterpret_cast<uint32_t*>(vrow + 8 * o_st + 8 * j) = pack_bf16(dv[j][2], dv[j][3]);
-                *reinterpret_cast<uint32_t*>(krow + 8 * j) = pack_bf16(dk[j][0], dk[j][1]);
-                *reinterpret_cast<uint32_t*>(krow + 8 * o_st + 8 * j) = pack_bf16(dk[j][2], dk[j][3]);
+                *reinterpret_cast<uint32_t*>(orow + 8 * j) = pack_bf16(acc[j][0], acc[j][1]);
+                *reinterpret_cast<uint32_t*>(orow + 8 * o_st + 8 * j) = pack_bf16(acc[j][2], acc[j][3]);
+            }
+            // ---- dq of the 16 rows, columns 32 * kh .. +31: A = sS rows, B = k as [key][d] read transposed
+            float dq[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
+            const uint32_t s_base = smem_u32(sS), k_base = smem_u32(sK);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                if (!FULL && 16 * kc >= T) break;
+                uint32_t a[4];
+                ldsm_x4(a, s_base + off128(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, kc * 16 + (lane >> 4) * 8));
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    uint32_t kb[4];
+                    ldsm_x4_t(kb, k_base + off64(kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, (2 * kh + np) * 16 + (lane >> 4) * 8));
+                    mma16816(dq[2 * np], a, kb[0], kb[1]);
+                    mma16816(dq[2 * np + 1], a, kb[2], kb[3]);
+                }
+            }
+            __nv_bfloat16* const qrow = p.dq + o_base + (int64_t)(row0 + g) * o_st + 32 * kh + 2 * c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<uint32_t*>(qrow + 8 * j) = pack_bf16(dq[j][0], dq[j][1]);
+                *reinterpret_cast<uint32_t*>(qrow + 8 * o_st + 8 * j) = pack_bf16(dq[j][2], dq[j][3]);
             }
         }
-        __syncthreads();  // the next pair's loads overwrite the tiles
+        __syncthreads();  // sP / sS / sD and this tile buffer are free again
     }
+    cp_async_wait_group<0>();
 }
 
 __global__ void __launch_bounds__(256) attention_mask_kernel(uint8_t* out, const Params p) {
@@ -450,18 +484,29 @@ static int fill_common(Params& p, int64_t B, int64_t H, int64_t T, float scale, 
     BF_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "bad dropout probability");                                      \
     BF_CHECK_ARG(B * H * T < (int64_t)1 << 32, "too many rows for the mask counter")
 
+// bf_attention_tc.cu
+int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64_t* strides, int64_t B, int64_t H, float scale,
+                        float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* out, float* lse, uint32_t* keep,
+                        cudaStream_t stream);
+int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides, const float* lse,
+                        const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
+                        uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream);
+
 extern "C" int bf_attention_supported(int64_t T, int64_t head_dim) {
     return (head_dim == attn::D && T >= 16 && T <= attn::TMAX && T % 16 == 0) ? 1 : 0;
 }
 
 extern "C" int bf_attention_fwd(const void* q, const void* k, const void* v, const int64_t* strides, int64_t B, int64_t H,
                                 int64_t T, float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site,
-                                void* out, float* lse, void* stream) {
+                                void* out, float* lse, uint32_t* keep, void* stream) {
     BF_CHECK_ARG(q && k && v && strides && out && lse, "null pointer");
     BF_ATTN_CHECK();
     for (int i = 0; i < 9; ++i) BF_CHECK_ARG(strides[i] % 8 == 0, "strides must be multiples of 8 elements (16 B)");
     BF_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                    reinterpret_cast<uintptr_t>(out)) & 15u) == 0, "q, k, v, out must be 16 B aligned");
+    if (T == attn::TMAX && bf_option(BF_OPT_ATTN_TC) && (keep || p_drop == 0.0f))
+        return bf_attention_tc_fwd(q, k, v, strides, B, H, scale, p_drop, seed, step, site, out, lse, keep,
+                                   reinterpret_cast<cudaStream_t>(stream));
     attn::Params p{};
     p.q = (const __nv_bfloat16*)q, p.k = (const __nv_bfloat16*)k, p.v = (const __nv_bfloat16*)v;
     p.out = (__nv_bfloat16*)out, p.lse = lse;
@@ -469,24 +514,27 @@ extern "C" int bf_attention_fwd(const void* q, const void* k, const void* v, con
     p.k_sb = strides[3], p.k_sh = strides[4], p.k_st = strides[5];
     p.v_sb = strides[6], p.v_sh = strides[7], p.v_st = strides[8];
     attn::fill_common(p, B, H, T, scale, p_drop, seed, step, site);
-    BF_CUDA_OK(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::FWD_SMEM));
+    auto* const kernel = T == attn::TMAX ? attn::attention_fwd_kernel<true> : attn::attention_fwd_kernel<false>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::FWD_SMEM));
     const int64_t pairs = B * H, cap = (int64_t)bf_num_sms() * 2;
-    attn::attention_fwd_kernel<<<(int)(pairs < cap ? pairs : cap), attn::kThreads, attn::FWD_SMEM,
-                                 reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    kernel<<<(int)(pairs < cap ? pairs : cap), attn::kThreads, attn::FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     BF_LAUNCH_OK();
     return 0;
 }
 
 extern "C" int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
-                                const void* out, const float* lse, int64_t B, int64_t H, int64_t T, float scale,
-                                float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk, void* dv,
-                                void* stream) {
-    BF_CHECK_ARG(dout && q && k && v && strides && out && lse && dq && dk && dv, "null pointer");
+                                const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T,
+                                float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk,
+                                void* dv, void* stream) {
+    BF_CHECK_ARG(dout && q && k && v && strides && lse && dq && dk && dv, "null pointer");
     BF_ATTN_CHECK();
     for (int i = 0; i < 9; ++i) BF_CHECK_ARG(strides[i] % 8 == 0, "strides must be multiples of 8 elements (16 B)");
     BF_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
-                   reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq) |
-                   reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 15u) == 0, "buffers must be 16 B aligned");
+                   reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                   reinterpret_cast<uintptr_t>(dv)) & 15u) == 0, "buffers must be 16 B aligned");
+    if (T == attn::TMAX && bf_option(BF_OPT_ATTN_TC) && (keep || p_drop == 0.0f))
+        return bf_attention_tc_bwd(dout, q, k, v, strides, lse, keep, B, H, scale, p_drop, seed, step, site, dq, dk, dv,
+                                   reinterpret_cast<cudaStream_t>(stream));
     attn::Params p{};
     p.q = (const __nv_bfloat16*)q, p.k = (const __nv_bfloat16*)k, p.v = (const __nv_bfloat16*)v;
     p.o = (const __nv_bfloat16*)out, p.dout = (const __nv_bfloat16*)dout, p.lse = const_cast<float*>(lse);
@@ -495,10 +543,10 @@ extern "C" int bf_attention_bwd(const void* dout, const void* q, const void* k, 
     p.k_sb = strides[3], p.k_sh = strides[4], p.k_st = strides[5];
     p.v_sb = strides[6], p.v_sh = strides[7], p.v_st = strides[8];
     attn::fill_common(p, B, H, T, scale, p_drop, seed, step, site);
-    BF_CUDA_OK(cudaFuncSetAttribute(attn::attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::BWD_SMEM));
+    auto* const kernel = T == attn::TMAX ? attn::attention_bwd_kernel<true> : attn::attention_bwd_kernel<false>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::BWD_SMEM));
     const int64_t pairs = B * H, cap = (int64_t)bf_num_sms();
-    attn::attention_bwd_kernel<<<(int)(pairs < cap ? pairs : cap), attn::kThreads, attn::BWD_SMEM,
-                                 reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    kernel<<<(int)(pairs < cap ? pairs : cap), attn::kBwdThreads, attn::BWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     BF_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,522 @@
+// tcgen05 version of the short-sequence attention (T == 128, head width 64): the five products of a (sequence, head)
+// pair are whole-tile tensor-core MMAs on TMA-loaded shared-memory operands with TMEM accumulators, so the CUDA cores
+// only do what is left -- the softmax, the dropout mask and the packing -- on ONE row per thread.  bf_attention.cu
+// (mma.sync on ldmatrix fragments) stays for the other lengths; both produce the same keep mask.
+//
+// One block per SM, 10 warps:
+//   warps 0..7  row workers: thread (w, lane) owns row 32 * (w % 4) + lane of every accumulator (its TMEM lane) and the
+//               column half w / 4 -- 64 scores, or 32 output columns
+//   warp 8      TMA producer (one thread): q, k, v (and dO) tiles of the NEXT pair while this one is computed
+//   warp 9      MMA issuer (one thread)
+//
+// forward, per pair:   S = q k^T  (128x128x64, TMEM)        -> rows: max / exp2 / sum (two halves exchanged through
+//                      shared memory), Philox keep bits (stored: 16 B per row, the backward does not regenerate them),
+//                      P_d as bf16 -> shared memory          -> O = P_d v (128x64x128)   -> rows: * 1/((1-p) sum) ->
+//                      staged tile -> one TMA store.         S is double buffered: S(i+1) runs under the softmax of i.
+// backward, per pair:  S = q k^T, dP = dO v^T                -> rows: P = exp2(S c - lse), D = sum_k P_d dP_d (== dO.O:
+//                      O is never read), P_d and dS as bf16 -> shared memory [q][key], which the tensor core reads
+//                      K-major for dq = dS k and MN-major (transposed) for dv = P_d^T dO and dk = dS^T q
+//                      -> rows: three staged tiles -> three TMA stores.
+// Every output element is written once; nothing is accumulated across blocks (deterministic).
+#include "bf_tc.cuh"
+
+namespace attn_tc {
+using namespace tc;
+
+constexpr int TT = 128, DD = 64;
+constexpr int TILE = TT * DD * 2;      // one [128][64] bf16 tile, 128 B rows, 128B-swizzled: 16 KiB
+constexpr int kRowThreads = 256;       // 8 row-worker warps
+constexpr int kThreads = 320;          // + producer warp + MMA warp
+constexpr int FWD_BUF = 3 * TILE;      // q, k, v
+constexpr int BWD_BUF = 4 * TILE;      // q, k, v, dO
+constexpr int XCH_BYTES = 2 * 2 * TT * 4;  // two exchanged row statistics x two column halves
+constexpr int BAR_BYTES = 256;
+constexpr int FWD_SMEM = 1024 + 2 * FWD_BUF + 2 * TILE + TILE + XCH_BYTES + BAR_BYTES;  // + P_d (2 sub-tiles) + O staging
+constexpr int BWD_SMEM = 1024 + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;         // + P_d, dS (2 sub-tiles each)
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Params {
+    float* lse;       // [B, heads, 128] base-2 log-sum-exp of the scaled scores
+    uint32_t* keep;   // [B, heads, 128, 4] keep bits of the 128 keys of a row (bit k % 32 of word k / 32), or null
+    int H, total;     // heads, B * heads
+    float scale, scale_log2e, inv_keep;
+    uint32_t thresh, k0, k1, step, site;
+    const uint32_t* step_ptr;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+// 16 B chunk `chunk` of row `row` in a swizzled [128][64] bf16 tile
+__device__ __forceinline__ uint32_t chunk_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+// MN-major operand: rows = reduction index (128 B each, 8-row groups 1024 B apart), 64-wide atoms one tile apart
+__device__ __forceinline__ uint64_t mn_desc(uint32_t tile, int k) { return make_smem_desc(tile + k * 2048, TILE, 1024); }
+// K-major operand with a 128-deep reduction: reduction atoms (64 elements) one tile apart
+__device__ __forceinline__ uint64_t k_desc128(uint32_t tile, int k) { return operand_desc<false>(tile + (k >> 2) * TILE, k & 3); }
+
+// keep bits of the 64 keys [64 ch, 64 ch + 64) of query row `row` (bit k % 32 of word (k / 32) % 2): the mask
+// bf_attention.cu defines -- Philox call (row, (k % 8) / 2 + 4 * (k / 32)), word (k / 8) % 4, half k % 2
+__device__ __forceinline__ void keep_words(const Params& p, uint32_t row, int ch, uint32_t step, uint32_t& w0, uint32_t& w1) {
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+            const uint4 r = bf_philox4x32_10(row, (uint32_t)(cq + 4 * (2 * ch + mm)), 0x40000000u | p.site, step, p.k0, p.k1);
+            const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                w[mm] |= (uint32_t)((v[t] & 0xffffu) >= p.thresh) << (8 * t + 2 * cq);
+                w[mm] |= (uint32_t)((v[t] >> 16) >= p.thresh) << (8 * t + 2 * cq + 1);
+            }
+        }
+    }
+    w0 = w[0], w1 = w[1];
+}
+
+struct Smem {
+    uint32_t base;   // 1024 B aligned shared-window address
+    uint8_t* gen;    // the same place as a generic pointer
+};
+__device__ __forceinline__ Smem aligned_smem(uint8_t* raw) {
+    const uint32_t a = smem_u32(raw), b = (a + 1023u) & ~1023u;
+    return {b, raw + (b - a)};
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kThreads, 1)
+    fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+               const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const Smem sm = aligned_smem(smem_raw);
+    const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * FWD_BUF, s_out = s_p + 2 * TILE;
+    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * FWD_BUF + 3 * TILE);  // [kind][half][row]
+    const uint32_t bars = s_out + TILE + XCH_BYTES;
+    auto full = [&](int b) { return bars + 8u * b; };
+    auto empty = [&](int b) { return bars + 8u * (2 + b); };
+    auto s_ready = [&](int b) { return bars + 8u * (4 + b); };
+    auto s_free = [&](int b) { return bars + 8u * (6 + b); };
+    const uint32_t p_ready = bars + 64, o_ready = bars + 72, o_free = bars + 80, tmem_slot = bars + 96;
+    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * FWD_BUF + 3 * TILE + XCH_BYTES + 96);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == kRowThreads) {
+        tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v), tma_prefetch_desc(&map_o);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(full(b), 1), mbar_init(empty(b), 1), mbar_init(s_ready(b), 1), mbar_init(s_free(b), kRowThreads);
+        }
+        mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1), mbar_init(o_free, kRowThreads);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+    const int n_mine = p.total > (int)blockIdx.x ? (p.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
+                mbar_wait(empty(b), ((i >> 1) & 1) ^ 1u);
+                mbar_expect_tx(full(b), 3 * TILE);
+                const uint32_t dst = s_tiles + b * FWD_BUF;
+                tma_load_4d(dst, &map_q, full(b), 0, 0, h, bb);
+                tma_load_4d(dst + TILE, &map_k, full(b), 0, 0, h, bb);
+                tma_load_4d(dst + 2 * TILE, &map_v, full(b), 0, 0, h, bb);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(false, false, TT, TT), idesc_o = make_idesc(false, true, TT, DD);
+            auto issue_s = [&](int i) {  // S(i) = q k^T into TMEM buffer i % 2
+                const int b = i & 1;
+                mbar_wait(full(b), (i >> 1) & 1);
+                mbar_wait(s_free(b), ((i >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t q = s_tiles + b * FWD_BUF, k = q + TILE;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + b * TT, operand_desc<false>(q, kk), operand_desc<false>(k, kk), idesc_s, kk > 0);
+                umma_commit(s_ready(b));
+            };
+            if (n_mine > 0) issue_s(0);
+            for (int i = 0; i < n_mine; ++i) {
+                if (i + 1 < n_mine) issue_s(i + 1);  // runs under the softmax of pair i
+                mbar_wait(p_ready, i & 1);
+                mbar_wait(o_free, (i & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t v = s_tiles + (i & 1) * FWD_BUF + 2 * TILE;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)  // O = P_d v: reduction over the 128 keys
+                    umma_bf16(tmem + 2 * TT, k_desc128(s_p, kk), mn_desc(v, kk), idesc_o, kk > 0);
+                umma_commit(o_ready);
+                umma_commit(empty(i & 1));  // q, k, v of this pair are no longer read
+            }
+        }
+    } else {
+        const int q = 32 * (warp & 3) + lane, ch = warp >> 2;
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
+        for (int i = 0; i < n_mine; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
+            const uint32_t grow = (uint32_t)pair * TT + q;
+            uint32_t ra[32], rb[32];
+            mbar_wait(s_ready(b), (i >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + b * TT + 64 * ch, ra);
+            tmem_ld_32x32(lane_addr + b * TT + 64 * ch + 32, rb);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free(b));
+            float s[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(ra[j]), s[32 + j] = __uint_as_float(rb[j]);
+            float mx = s[0];
+#pragma unroll
+            for (int j = 1; j < 64; ++j) mx = fmaxf(mx, s[j]);
+            xch[ch * TT + q] = mx;
+            if (threadIdx.x == 0) tma_store_wait_read<0>();  // the staged output of the previous pair has left
+            named_bar_sync<1, kRowThreads>();
+            const float off = fmaxf(xch[q], xch[TT + q]) * p.scale_log2e;
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                s[j] = bf_ex2_approx(fmaf(s[j], p.scale_log2e, -off));
+                sum += s[j];
+            }
+            xch[2 * TT + ch * TT + q] = sum;
+            named_bar_sync<2, kRowThreads>();
+            const float total = xch[2 * TT + q] + xch[3 * TT + q];
+            if (ch == 0) p.lse[grow] = off + bf_lg2_approx(total);
+            if (p.thresh != 0u) {
+                uint32_t w0, w1;
+                keep_words(p, grow, ch, step, w0, w1);
+                if (p.keep) *reinterpret_cast<uint2*>(p.keep + (size_t)grow * 4 + 2 * ch) = make_uint2(w0, w1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (!((w0 >> j) & 1u)) s[j] = 0.0f;
+                    if (!((w1 >> j) & 1u)) s[32 + j] = 0.0f;
+                }
+            }
+            // P_d (still without 1 / ((1-p) sum): applied to the output row) -> row q of key sub-tile ch
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8)
+                sts128(s_p + ch * TILE + chunk_off(q, c8), pack_bf16(s[8 * c8], s[8 * c8 + 1]), pack_bf16(s[8 * c8 + 2], s[8 * c8 + 3]),
+                       pack_bf16(s[8 * c8 + 4], s[8 * c8 + 5]), pack_bf16(s[8 * c8 + 6], s[8 * c8 + 7]));
+            fence_proxy_async();
+            mbar_arrive(p_ready);
+            // ---- output row q, columns 32 ch .. +31
+            mbar_wait(o_ready, i & 1);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + 2 * TT + 32 * ch, ra);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_free);
+            const float r = p.inv_keep * bf_rcp_approx(total);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(ra[8 * c4 + e]) * r;
+                sts128(s_out + chunk_off(q, 4 * ch + c4), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                       pack_bf16(o[6], o[7]));
+            }
+            fence_proxy_async();
+            named_bar_sync<3, kRowThreads>();
+            if (threadIdx.x == 0) {
+                tma_store_4d(&map_o, s_out, 0, 0, h, bb);
+                tma_store_commit();
+            }
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(kThreads, 1)
+    bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+               const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
+               const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const Smem sm = aligned_smem(smem_raw);
+    const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * BWD_BUF, s_s = s_p + 2 * TILE;
+    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * BWD_BUF + 4 * TILE);  // [half][row]
+    const uint32_t bars = s_s + 2 * TILE + XCH_BYTES;
+    auto full = [&](int b) { return bars + 8u * b; };
+    auto empty = [&](int b) { return bars + 8u * (2 + b); };
+    const uint32_t s_ready = bars + 32, s_free = bars + 40, p_ready = bars + 48, o_ready = bars + 56, o_free = bars + 64,
+                   tmem_slot = bars + 96;
+    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + 96);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == kRowThreads) {
+        tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v), tma_prefetch_desc(&map_do);
+        tma_prefetch_desc(&map_dq), tma_prefetch_desc(&map_dk), tma_prefetch_desc(&map_dv);
+        for (int b = 0; b < 2; ++b) mbar_init(full(b), 1), mbar_init(empty(b), 1);
+        mbar_init(s_ready, 1), mbar_init(s_free, kRowThreads), mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1);
+        mbar_init(o_free, kRowThreads);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+    const int n_mine = p.total > (int)blockIdx.x ? (p.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // TMEM columns: S 0..127, dP 128..255, dv 256..319, dk 320..383, dq 384..447
+    constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
+                mbar_wait(empty(b), ((i >> 1) & 1) ^ 1u);
+                mbar_expect_tx(full(b), 4 * TILE);
+                const uint32_t dst = s_tiles + b * BWD_BUF;
+                tma_load_4d(dst, &map_q, full(b), 0, 0, h, bb);
+                tma_load_4d(dst + TILE, &map_k, full(b), 0, 0, h, bb);
+                tma_load_4d(dst + 2 * TILE, &map_v, full(b), 0, 0, h, bb);
+                tma_load_4d(dst + 3 * TILE, &map_do, full(b), 0, 0, h, bb);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(false, false, TT, TT);   // S, dP: both operands K-major
+            constexpr uint32_t idesc_t = make_idesc(true, true, TT, DD);     // dv, dk: transposed A, B = [q][d]
+            constexpr uint32_t idesc_q = make_idesc(false, true, TT, DD);    // dq: A = dS [q][key], B = k [key][d]
+            for (int i = 0; i < n_mine; ++i) {
+                const int b = i & 1;
+                const uint32_t q = s_tiles + b * BWD_BUF, k = q + TILE, v = q + 2 * TILE, dO = q + 3 * TILE;
+                mbar_wait(full(b), (i >> 1) & 1);
+                mbar_wait(s_free, (i & 1) ^ 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + C_S, operand_desc<false>(q, kk), operand_desc<false>(k, kk), idesc_s, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + C_DP, operand_desc<false>(dO, kk), operand_desc<false>(v, kk), idesc_s, kk > 0);
+                umma_commit(s_ready);
+                mbar_wait(p_ready, i & 1);
+                mbar_wait(o_free, (i & 1) ^ 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)  // dv[key][d] = sum_q P_d[q][key] dO[q][d]
+                    umma_bf16(tmem + C_DV, mn_desc(s_p, kk), mn_desc(dO, kk), idesc_t, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)  // dk[key][d] = sum_q dS[q][key] q[q][d]
+                    umma_bf16(tmem + C_DK, mn_desc(s_s, kk), mn_desc(q, kk), idesc_t, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)  // dq[q][d] = sum_key dS[q][key] k[key][d]
+                    umma_bf16(tmem + C_DQ, k_desc128(s_s, kk), mn_desc(k, kk), idesc_q, kk > 0);
+                umma_commit(o_ready);
+                umma_commit(empty(b));
+            }
+        }
+    } else {
+        const int q = 32 * (warp & 3) + lane, ch = warp >> 2;
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+        const float ik = p.thresh != 0u ? p.inv_keep : 1.0f;
+        for (int i = 0; i < n_mine; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+            const uint32_t grow = (uint32_t)pair * TT + q;
+            const float lse = __ldg(p.lse + grow);
+            uint2 kw = make_uint2(0xffffffffu, 0xffffffffu);
+            if (p.thresh != 0u) kw = __ldg(reinterpret_cast<const uint2*>(p.keep + (size_t)grow * 4 + 2 * ch));
+            uint32_t ra[32], rb[32], rc[32], rd[32];
+            mbar_wait(s_ready, i & 1);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + C_S + 64 * ch, ra);
+            tmem_ld_32x32(lane_addr + C_S + 64 * ch + 32, rb);
+            tmem_ld_32x32(lane_addr + C_DP + 64 * ch, rc);
+            tmem_ld_32x32(lane_addr + C_DP + 64 * ch + 32, rd);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            // P (true probabilities) in ra / rb, t = keep ? dP_d : 0 in rc / rd; partial D over this half of the keys
+            float part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p0 = bf_ex2_approx(fmaf(__uint_as_float(ra[j]), p.scale_log2e, -lse));
+                const float p1 = bf_ex2_approx(fmaf(__uint_as_float(rb[j]), p.scale_log2e, -lse));
+                const float t0 = ((kw.x >> j) & 1u) ? __uint_as_float(rc[j]) : 0.0f;
+                const float t1 = ((kw.y >> j) & 1u) ? __uint_as_float(rd[j]) : 0.0f;
+                part = fmaf(p0, t0, fmaf(p1, t1, part));
+                ra[j] = __float_as_uint(p0), rb[j] = __float_as_uint(p1);
+                rc[j] = __float_as_uint(t0), rd[j] = __float_as_uint(t1);
+            }
+            xch[ch * TT + q] = part * ik;
+            if (threadIdx.x == 0) tma_store_wait_read<0>();  // the staged gradients of the previous pair have left
+            named_bar_sync<1, kRowThreads>();
+            const float Dq = xch[q] + xch[TT + q];  // = sum_k P_d dP_d = rowsum(dO o O)
+            // P_d = keep ? P / (1-p) : 0 and dS = P (t / (1-p) - D) scale -> row q of key sub-tile ch
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t(&pr)[32] = half ? rb : ra;
+                const uint32_t(&tr)[32] = half ? rd : rc;
+                const uint32_t kbits = half ? kw.y : kw.x;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint32_t pd[4], ds[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j0 = 8 * c4 + 2 * e, j1 = j0 + 1;
+                        const float pa = __uint_as_float(pr[j0]), pb = __uint_as_float(pr[j1]);
+                        pd[e] = pack_bf16(((kbits >> j0) & 1u) ? pa * ik : 0.0f, ((kbits >> j1) & 1u) ? pb * ik : 0.0f);
+                        ds[e] = pack_bf16(pa * p.scale * fmaf(__uint_as_float(tr[j0]), ik, -Dq),
+                                          pb * p.scale * fmaf(__uint_as_float(tr[j1]), ik, -Dq));
+                    }
+                    const uint32_t o = ch * TILE + chunk_off(q, 4 * half + c4);
+                    sts128(s_p + o, pd[0], pd[1], pd[2], pd[3]);
+                    sts128(s_s + o, ds[0], ds[1], ds[2], ds[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(p_ready);
+            // ---- gradients: row q (dq) / key q (dv, dk), columns 32 ch .. +31, staged where P_d / dS were
+            mbar_wait(o_ready, i & 1);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + C_DV + 32 * ch, ra);
+            tmem_ld_32x32(lane_addr + C_DK + 32 * ch, rb);
+            tmem_ld_32x32(lane_addr + C_DQ + 32 * ch, rc);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_free);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const uint32_t o = chunk_off(q, 4 * ch + c4);
+                auto pk = [&](const uint32_t(&r)[32], int e) {
+                    return pack_bf16(__uint_as_float(r[8 * c4 + 2 * e]), __uint_as_float(r[8 * c4 + 2 * e + 1]));
+                };
+                sts128(s_p + o, pk(ra, 0), pk(ra, 1), pk(ra, 2), pk(ra, 3));
+                sts128(s_p + TILE + o, pk(rb, 0), pk(rb, 1), pk(rb, 2), pk(rb, 3));
+                sts128(s_s + o, pk(rc, 0), pk(rc, 1), pk(rc, 2), pk(rc, 3));
+            }
+            fence_proxy_async();
+            named_bar_sync<2, kRowThreads>();
+            if (threadIdx.x == 0) {
+                tma_store_4d(&map_dv, s_p, 0, 0, h, bb);
+                tma_store_4d(&map_dk, s_p + TILE, 0, 0, h, bb);
+                tma_store_4d(&map_dq, s_s, 0, 0, h, bb);
+                tma_store_commit();
+            }
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+// [B][128][heads][64]-indexed view (any batch / head / token strides, unit inner stride) as a 4-D tensor map:
+// box = one (sequence, head) tile of 128 rows x 128 B, 128B swizzle
+static int encode_pair_map(CUtensorMap* m, const void* base, int64_t B, int64_t H, int64_t sb, int64_t sh, int64_t st) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        bf_set_error("cuTensorMapEncodeTiled entry point not available");
+        return BF_ERR_DRIVER;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)DD, (cuuint64_t)TT, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)st * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)DD, (cuuint32_t)TT, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        bf_set_error("cuTensorMapEncodeTiled (attention tile) failed with CUresult " + std::to_string((int)r));
+        return BF_ERR_DRIVER;
+    }
+    return 0;
+}
+
+static void fill(Params& p, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site,
+                 float* lse, uint32_t* keep) {
+    p.lse = lse, p.keep = keep;
+    p.H = (int)H, p.total = (int)(B * H);
+    p.scale = scale, p.scale_log2e = scale * 1.4426950408889634f;
+    p.thresh = 0u, p.inv_keep = 1.0f;
+    if (p_drop > 0.0f) {
+        uint32_t t = (uint32_t)lrintf(p_drop * 65536.0f);
+        if (t > 65535u) t = 65535u;
+        p.thresh = t;
+        p.inv_keep = 65536.0f / (65536.0f - (float)t);
+    }
+    p.k0 = (uint32_t)(seed & 0xffffffffu), p.k1 = (uint32_t)(seed >> 32), p.step = step, p.site = site;
+    p.step_ptr = bf_step_counter();
+}
+
+}  // namespace attn_tc
+
+// called by bf_attention_fwd / bf_attention_bwd (bf_attention.cu) after their argument checks, for T == 128
+int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64_t* strides, int64_t B, int64_t H, float scale,
+                        float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* out, float* lse, uint32_t* keep,
+                        cudaStream_t stream) {
+    using namespace attn_tc;
+    CUtensorMap mq, mk, mv, mo;
+    int rc;
+    if ((rc = encode_pair_map(&mq, q, B, H, strides[0], strides[1], strides[2]))) return rc;
+    if ((rc = encode_pair_map(&mk, k, B, H, strides[3], strides[4], strides[5]))) return rc;
+    if ((rc = encode_pair_map(&mv, v, B, H, strides[6], strides[7], strides[8]))) return rc;
+    if ((rc = encode_pair_map(&mo, out, B, H, (int64_t)TT * H * DD, DD, H * DD))) return rc;
+    Params p{};
+    fill(p, B, H, scale, p_drop, seed, step, site, lse, keep);
+    BF_CUDA_OK(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
+    fwd_kernel<<<grid, kThreads, FWD_SMEM, stream>>>(mq, mk, mv, mo, p);
+    BF_LAUNCH_OK();
+    return 0;
+}
+
+int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides, const float* lse,
+                        const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
+                        uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream) {
+    using namespace attn_tc;
+    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
+    const int64_t osb = (int64_t)TT * H * DD, osh = DD, ost = H * DD;
+    int rc;
+    if ((rc = encode_pair_map(&mq, q, B, H, strides[0], strides[1], strides[2]))) return rc;
+    if ((rc = encode_pair_map(&mk, k, B, H, strides[3], strides[4], strides[5]))) return rc;
+    if ((rc = encode_pair_map(&mv, v, B, H, strides[6], strides[7], strides[8]))) return rc;
+    if ((rc = encode_pair_map(&mdo, dout, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdq, dq, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdk, dk, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdv, dv, B, H, osb, osh, ost))) return rc;
+    Params p{};
+    fill(p, B, H, scale, p_drop, seed, step, site, const_cast<float*>(lse), const_cast<uint32_t*>(keep));
+    BF_CUDA_OK(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
+    bwd_kernel<<<grid, kThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    BF_LAUNCH_OK();
+    return 0;
+}

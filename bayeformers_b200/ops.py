@@ -879,13 +879,15 @@ class AttentionFn(torch.autograd.Function):
         strides = torch.tensor([t.stride(i) for t in (qc, kc, vc) for i in (0, 1, 2)], dtype=torch.int64)
         out = torch.empty((B, T, H, Dh), dtype=torch.bfloat16, device=dev)
         lse = torch.empty((B, H, T), dtype=torch.float32, device=dev)
+        # T == 128 (tcgen05 kernels): the keep bits of the dropout mask go to backward instead of being regenerated
+        keep = torch.empty((B, H, T, 4), dtype=torch.int32, device=dev) if (T == 128 and drop.p > 0.0) else None
         flops = 4.0 * B * H * T * T * Dh
         rc = _timed("attention_fwd", flops, dev, lambda: lib.bf_attention_fwd(
             _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), B, H, T, float(scale), float(drop.p), drop.seed,
-            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(out), _ptr(lse), _stream(dev)))
+            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(out), _ptr(lse), _ptr(keep), _stream(dev)))
         _lib.check(rc, "bf_attention_fwd")
         stats["launches"] += 1
-        ctx.save_for_backward(qc, kc, vc, out, lse)
+        ctx.save_for_backward(qc, kc, vc, lse, keep)
         ctx.meta = (float(scale), drop, strides)
         return out
 
@@ -893,7 +895,7 @@ class AttentionFn(torch.autograd.Function):
     @_guarded
     def backward(ctx, gout):
         lib = _lib.load()
-        qc, kc, vc, out, lse = ctx.saved_tensors
+        qc, kc, vc, lse, keep = ctx.saved_tensors
         scale, drop, strides = ctx.meta
         dev = qc.device
         B, H, T, Dh = qc.shape
@@ -902,8 +904,8 @@ class AttentionFn(torch.autograd.Function):
         dk, dv = torch.empty_like(dq), torch.empty_like(dq)
         flops = 10.0 * B * H * T * T * Dh
         rc = _timed("attention_bwd", flops, dev, lambda: lib.bf_attention_bwd(
-            _ptr(g), _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), _ptr(out), _ptr(lse), B, H, T, scale, float(drop.p),
-            drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dq), _ptr(dk), _ptr(dv), _stream(dev)))
+            _ptr(g), _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), None, _ptr(lse), _ptr(keep), B, H, T, scale,
+            float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dq), _ptr(dk), _ptr(dv), _stream(dev)))
         _lib.check(rc, "bf_attention_bwd")
         stats["launches"] += 1
         # [B, T, H, D] buffers seen as [B, H, T, D]: the layout the inputs came in (views of [B, T, H*D] rows), so the

@@ -69,7 +69,8 @@ int bf_set_step_counter(const uint32_t* device_counter);
 #define BF_OPT_WGRAD_2CTA 1        /* fused wgrad: same values */
 #define BF_OPT_RESLN_BWD_STAGED 2  /* 1 (default): shared-memory-staged resln backward, 0: register prefetch */
 #define BF_OPT_SK_PREFETCH 3       /* multi-tensor sample+KL prefetch: 0 none, 1 L1 (default), 2 L2 */
-#define BF_OPT_COUNT 4
+#define BF_OPT_ATTN_TC 4          /* T == 128 attention: 1 (default) tcgen05 kernels, 0 the mma.sync kernels */
+#define BF_OPT_COUNT 5
 int bf_set_option(int32_t option, int32_t value);
 int bf_get_option(int32_t option);
 
@@ -374,17 +375,24 @@ int bf_dropout_mask(uint8_t* out, int64_t n, float p_drop, uint64_t seed, uint32
  *           outputs, no transposed copies
  * out, dout, dq, dk, dv   bf16 [B, T, H, 64] densely packed
  * lse       fp32 [B, H, T]: base-2 log-sum-exp of the scaled scores, written by fwd, read by bwd
+ * keep      optional uint32 [B, H, T, 4] (only used when T == 128): the 128 keep bits of every query row (bit k % 32
+ *           of word k / 32), written by fwd and read by bwd so that the tcgen05 backward does not regenerate the
+ *           mask.  Null: the mma.sync kernels run (they regenerate it), whatever BF_OPT_ATTN_TC says, unless
+ *           p_drop == 0.
+ * out       (bwd) the forward output; unused since round 2 (D = rowsum(dO o O) is formed from P and dP), may be null
  * The dropout keep mask is a pure function of (seed, site, step [+ device step counter], b, h, q, k)
- * (Philox4x32-10; see bf_attention.cu) and is regenerated in backward; bf_attention_dropout_mask
+ * (Philox4x32-10; see bf_attention.cu), the same for both kernel families; bf_attention_dropout_mask
  * writes it as bytes [B, H, T, T] (tests).  Deterministic: every output element is written once.
+ * T == 128 runs on the tensor cores' tcgen05 path (bf_attention_tc.cu: TMA-loaded tiles, TMEM accumulators, one row
+ * per thread for the softmax); other lengths use mma.sync on ldmatrix fragments (bf_attention.cu).
  * ------------------------------------------------------------------------- */
 int bf_attention_supported(int64_t T, int64_t head_dim);
 int bf_attention_fwd(const void* q, const void* k, const void* v, const int64_t* strides, int64_t B, int64_t H, int64_t T,
                      float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* out, float* lse,
-                     void* stream);
+                     uint32_t* keep, void* stream);
 int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
-                     const void* out, const float* lse, int64_t B, int64_t H, int64_t T, float scale, float p_drop,
-                     uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk, void* dv, void* stream);
+                     const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T, float scale,
+                     float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk, void* dv, void* stream);
 int bf_attention_dropout_mask(uint8_t* out, int64_t B, int64_t H, int64_t T, float p_drop, uint64_t seed, uint32_t step,
                               uint32_t site, void* stream);
 

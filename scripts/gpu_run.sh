@@ -20,6 +20,9 @@ for stage in "$@"; do
         timeout -k 10 900 python bench.py --config $c --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "$c rc $?"; cut -c1-600 gpurun_out/bench_$c.json; tail -2 gpurun_out/bench_$c.err
       done ;;
     launches) timeout -k 10 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 --warmup 1 --graph 0 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "rc $?"; tail -2 gpurun_out/ncu_launch.log | cut -c1-200; python scripts/launch_summary.py gpurun_out/launches.csv > gpurun_out/launches.md; head -30 gpurun_out/launches.md ;;
+    attn)
+      timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "attention" 2>&1 | tail -8
+      timeout -k 10 300 python scripts/bench_attention.py 2>&1 | tail -3 | tee gpurun_out/bench_attention.json ;;
     ab_links)
       for v in 0 1 0 1; do
         timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --gelu-links $v > gpurun_out/bench_links$v.json 2> gpurun_out/bench_links$v.err; echo "links=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_links$v.json | head -2

@@ -1349,8 +1349,10 @@ def test_attention_dropout_masks_are_independent_across_sites_and_steps():
 
 
 def test_accelerate_host_native_attention_matches_sdpa():
-    """accelerate_host_(attention=True) on a HuggingFace BERT: eval-mode logits and gradients agree with the torch SDPA
-    path to bf16 rounding, the native kernels really ran, and a masked batch falls back to SDPA."""
+    """accelerate_host_(attention=True) on a HuggingFace BERT: eval-mode logits agree with the torch SDPA path to bf16
+    rounding; the rho gradients of every layer are no further from an all-fp32 run of the same model than the bf16 SDPA
+    path's are (the key projections' gradients nearly cancel, so two bf16 paths differ by more from each other than
+    either does from fp32); the native kernels really ran, and a masked batch falls back to SDPA."""
     import copy
     from transformers import BertConfig, BertForSequenceClassification
     torch.manual_seed(2)
@@ -1358,19 +1360,22 @@ def test_accelerate_host_native_attention_matches_sdpa():
                      intermediate_size=512, max_position_embeddings=128, num_labels=2)
     base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True, gemm_dtype="bf16")
     fast = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, attention=True)
-    base, fast = base.eval().to(DEV), fast.eval().to(DEV)
+    truth = copy.deepcopy(base)  # fp32 everywhere: FFMA contractions, fp32 host model
+    for l in truth.bayesian_children:
+        l.gemm_dtype = torch.float32
+    base, fast, truth = base.eval().to(DEV), fast.eval().to(DEV), truth.eval().to(DEV)
     for m in (base, fast):
         bf.cast_frequentist_(m, torch.bfloat16)
     S, B, Tn = 2, 3, 128
     ids = torch.randint(0, 100, (B, Tn), generator=torch.Generator().manual_seed(1)).to(DEV)
     gen = torch.Generator().manual_seed(5)
-    for la, lb in zip(base.bayesian_children, fast.bayesian_children):
+    for la, lb, lc in zip(base.bayesian_children, fast.bayesian_children, truth.bayesian_children):
         ew = [torch.randn(la.weight.mu.shape, generator=gen) for _ in range(S)]
         eb = [torch.randn(la.bias.mu.shape, generator=gen) for _ in range(S)]
-        la.weight.normal, lb.weight.normal = FixedEps(ew), FixedEps([e.clone() for e in ew])
-        la.bias.normal, lb.bias.normal = FixedEps(eb), FixedEps([e.clone() for e in eb])
+        for l in (la, lb, lc):
+            l.weight.normal, l.bias.normal = FixedEps([e.clone() for e in ew]), FixedEps([e.clone() for e in eb])
     outs = []
-    for m in (base, fast):
+    for m in (base, fast, truth):
         ops.enable_kernel_timing(True)
         try:
             with bf.mc_samples(S):
@@ -1383,8 +1388,12 @@ def test_accelerate_host_native_attention_matches_sdpa():
         assert ({"attention_fwd", "attention_bwd"} <= ran) == (m is fast)
         outs.append((logits.detach().float(), [l.weight.rho.grad.clone() for l in m.bayesian_children]))
     assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < 2e-2
-    for ga, gb in zip(outs[0][1], outs[1][1]):  # two bf16 attention implementations against each other
-        assert rel_err(gb.cpu().numpy(), ga.cpu().numpy()) < 1e-1
+    e_sdpa = [rel_err(g.cpu().numpy(), t.cpu().numpy()) for g, t in zip(outs[0][1], outs[2][1])]
+    e_native = [rel_err(g.cpu().numpy(), t.cpu().numpy()) for g, t in zip(outs[1][1], outs[2][1])]
+    print(f"[native attention vs SDPA] logits {rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()):.2e}; rho "
+          f"grads against fp32: bf16 SDPA max {max(e_sdpa):.2e}, native max {max(e_native):.2e}")
+    for a, b in zip(e_native, e_sdpa):
+        assert a < max(2.0 * b, 2e-2), (e_native, e_sdpa)
     # an attention mask is outside the kernels' case: transformers' own SDPA function takes it
     mask = torch.ones(B, Tn, dtype=torch.long, device=DEV)
     mask[:, 100:] = 0
