@@ -3,39 +3,52 @@
 // only do what is left -- the softmax, the dropout mask and the packing -- on ONE row per thread.  bf_attention.cu
 // (mma.sync on ldmatrix fragments) stays for the other lengths; both produce the same keep mask.
 //
-// One block per SM, 10 warps:
-//   warps 0..7  row workers: thread (w, lane) owns row 32 * (w % 4) + lane of every accumulator (its TMEM lane) and the
-//               column half w / 4 -- 64 scores, or 32 output columns
-//   warp 8      TMA producer (one thread): q, k, v (and dO) tiles of the NEXT pair while this one is computed
-//   warp 9      MMA issuer (one thread)
+// One block per SM, 18 warps:
+//   warps 0..15 row workers: thread (w, lane) owns row 32 * (w % 4) + lane of every accumulator (its TMEM lane) and the
+//               column quarter w / 4 -- 32 scores, or 16 output columns
+//   warp 16     TMA producer (one thread): q, k, v (and dO) tiles of the NEXT pair while this one is computed
+//   warp 17     MMA issuer (one thread)
+// Outputs leave straight from registers: a thread holds 16 consecutive bf16 of an output row = one 32 B sector
+// (st.global.v8), so there is no staging tile, no store fence and no wait for a bulk store.
 //
-// forward, per pair:   S = q k^T  (128x128x64, TMEM)        -> rows: max / exp2 / sum (two halves exchanged through
+// forward, per pair:   S = q k^T  (128x128x64, TMEM)        -> rows: max / exp2 / sum (four quarters exchanged through
 //                      shared memory), Philox keep bits (stored: 16 B per row, the backward does not regenerate them),
 //                      P_d as bf16 -> shared memory          -> O = P_d v (128x64x128)   -> rows: * 1/((1-p) sum) ->
-//                      staged tile -> one TMA store.         S is double buffered: S(i+1) runs under the softmax of i.
+//                      global memory.  S, P_d and O are double buffered: S(i+1) and O(i-1) run under the softmax of i.
 // backward, per pair:  S = q k^T, dP = dO v^T                -> rows: P = exp2(S c - lse), D = sum_k P_d dP_d (== dO.O:
 //                      O is never read), P_d and dS as bf16 -> shared memory [q][key], which the tensor core reads
 //                      K-major for dq = dS k and MN-major (transposed) for dv = P_d^T dO and dk = dS^T q
-//                      -> rows: three staged tiles -> three TMA stores.
+//                      -> rows -> global memory.  The first pass of pair i+1 runs under the dv / dk / dq MMAs of pair i.
 // Every output element is written once; nothing is accumulated across blocks (deterministic).
 #include "bf_tc.cuh"
 
 namespace attn_tc {
 using namespace tc;
 
+// phase timeline of block 0 (scripts/attn_trace.cu builds this file with -DBF_ATTN_TRACE); compiled out otherwise
+#ifdef BF_ATTN_TRACE
+__device__ unsigned long long g_trace[2 * 16 * 16];
+#define BF_STAMP(who, slot) \
+    do { if (blockIdx.x == 0 && i < 16) g_trace[((who) * 16 + i) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define BF_STAMP(who, slot) do { } while (0)
+#endif
+
 constexpr int TT = 128, DD = 64;
 constexpr int TILE = TT * DD * 2;      // one [128][64] bf16 tile, 128 B rows, 128B-swizzled: 16 KiB
-constexpr int kRowThreads = 256;       // 8 row-worker warps
-constexpr int kThreads = 320;          // + producer warp + MMA warp
+constexpr int kRowWarps = 16;
+constexpr int kRowThreads = kRowWarps * 32;   // 512 row workers
+constexpr int kThreads = kRowThreads + 64;    // + producer warp (16) + MMA warp (17)
 constexpr int FWD_BUF = 3 * TILE;      // q, k, v
 constexpr int BWD_BUF = 4 * TILE;      // q, k, v, dO
-constexpr int XCH_BYTES = 2 * 2 * TT * 4;  // two exchanged row statistics x two column halves
+constexpr int XCH_BYTES = 2 * 4 * TT * 4;  // two exchanged row statistics x four column quarters
 constexpr int BAR_BYTES = 256;
-constexpr int FWD_SMEM = 1024 + 2 * FWD_BUF + 2 * TILE + TILE + XCH_BYTES + BAR_BYTES;  // + P_d (2 sub-tiles) + O staging
+constexpr int FWD_SMEM = 1024 + 2 * FWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;  // + 2 x P_d (2 sub-tiles)
 constexpr int BWD_SMEM = 1024 + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;         // + P_d, dS (2 sub-tiles each)
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Params {
+    __nv_bfloat16 *out, *dq, *dk, *dv;  // [B, 128, heads, 64]: written row quarter by row quarter (32 B per thread)
     float* lse;       // [B, heads, 128] base-2 log-sum-exp of the scaled scores
     uint32_t* keep;   // [B, heads, 128, 4] keep bits of the 128 keys of a row (bit k % 32 of word k / 32), or null
     int H, total;     // heads, B * heads
@@ -50,9 +63,20 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+// 32 lanes x 16 consecutive 32-bit columns (see tmem_ld_32x32)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 B (16 bf16 = one output row quarter, one full sector) straight from registers
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -69,24 +93,21 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t tile, int k) { return make_
 // K-major operand with a 128-deep reduction: reduction atoms (64 elements) one tile apart
 __device__ __forceinline__ uint64_t k_desc128(uint32_t tile, int k) { return operand_desc<false>(tile + (k >> 2) * TILE, k & 3); }
 
-// keep bits of the 64 keys [64 ch, 64 ch + 64) of query row `row` (bit k % 32 of word (k / 32) % 2): the mask
-// bf_attention.cu defines -- Philox call (row, (k % 8) / 2 + 4 * (k / 32)), word (k / 8) % 4, half k % 2
-__device__ __forceinline__ void keep_words(const Params& p, uint32_t row, int ch, uint32_t step, uint32_t& w0, uint32_t& w1) {
-    uint32_t w[2] = {0u, 0u};
+// keep bits of the 32 keys [32 cq, 32 cq + 32) of query row `row` (bit k % 32): the mask bf_attention.cu defines --
+// Philox call (row, (k % 8) / 2 + 4 * (k / 32)), word (k / 8) % 4, half k % 2
+__device__ __forceinline__ uint32_t keep_word(const Params& p, uint32_t row, int cq, uint32_t step) {
+    uint32_t w = 0u;
 #pragma unroll
-    for (int mm = 0; mm < 2; ++mm) {
+    for (int c = 0; c < 4; ++c) {
+        const uint4 r = bf_philox4x32_10(row, (uint32_t)(c + 4 * cq), 0x40000000u | p.site, step, p.k0, p.k1);
+        const uint32_t v[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int cq = 0; cq < 4; ++cq) {
-            const uint4 r = bf_philox4x32_10(row, (uint32_t)(cq + 4 * (2 * ch + mm)), 0x40000000u | p.site, step, p.k0, p.k1);
-            const uint32_t v[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                w[mm] |= (uint32_t)((v[t] & 0xffffu) >= p.thresh) << (8 * t + 2 * cq);
-                w[mm] |= (uint32_t)((v[t] >> 16) >= p.thresh) << (8 * t + 2 * cq + 1);
-            }
+        for (int t = 0; t < 4; ++t) {
+            w |= (uint32_t)((v[t] & 0xffffu) >= p.thresh) << (8 * t + 2 * c);
+            w |= (uint32_t)((v[t] >> 16) >= p.thresh) << (8 * t + 2 * c + 1);
         }
     }
-    w0 = w[0], w1 = w[1];
+    return w;
 }
 
 struct Smem {
@@ -98,41 +119,50 @@ __device__ __forceinline__ Smem aligned_smem(uint8_t* raw) {
     return {b, raw + (b - a)};
 }
 
+// Row workers: thread (w, lane) owns row 32 * (w % 4) + lane (its TMEM lane) and the column quarter w / 4:
+// 32 scores, or 16 output columns.
+
 // ------------------------------------------------------------------ forward
+// S, P_d and O are double buffered, so per pair the row workers only ever wait for S: while they do the softmax of
+// pair i the tensor core runs O(i-1) = P_d v and S(i+1) = q k^T; the output rows of pair i-1 are drained after the
+// softmax of pair i.
 __global__ void __launch_bounds__(kThreads, 1)
     fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = aligned_smem(smem_raw);
-    const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * FWD_BUF, s_out = s_p + 2 * TILE;
-    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * FWD_BUF + 3 * TILE);  // [kind][half][row]
-    const uint32_t bars = s_out + TILE + XCH_BYTES;
+    const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * FWD_BUF;
+    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * FWD_BUF + 4 * TILE);  // [kind][quarter][row]
+    const uint32_t bars = s_p + 4 * TILE + XCH_BYTES;
     auto full = [&](int b) { return bars + 8u * b; };
     auto empty = [&](int b) { return bars + 8u * (2 + b); };
     auto s_ready = [&](int b) { return bars + 8u * (4 + b); };
     auto s_free = [&](int b) { return bars + 8u * (6 + b); };
-    const uint32_t p_ready = bars + 64, o_ready = bars + 72, o_free = bars + 80, tmem_slot = bars + 96;
-    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * FWD_BUF + 3 * TILE + XCH_BYTES + 96);
+    auto p_ready = [&](int b) { return bars + 8u * (8 + b); };
+    auto o_ready = [&](int b) { return bars + 8u * (10 + b); };
+    auto o_free = [&](int b) { return bars + 8u * (12 + b); };
+    const uint32_t tmem_slot = bars + 128;
+    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * FWD_BUF + 4 * TILE + XCH_BYTES + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == kRowThreads) {
-        tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v), tma_prefetch_desc(&map_o);
+        tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v);
         for (int b = 0; b < 2; ++b) {
             mbar_init(full(b), 1), mbar_init(empty(b), 1), mbar_init(s_ready(b), 1), mbar_init(s_free(b), kRowThreads);
+            mbar_init(p_ready(b), kRowThreads), mbar_init(o_ready(b), 1), mbar_init(o_free(b), kRowThreads);
         }
-        mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1), mbar_init(o_free, kRowThreads);
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == kRowWarps + 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
     const int n_mine = p.total > (int)blockIdx.x ? (p.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    constexpr uint32_t C_O = 2 * TT;  // TMEM columns: S buffers at 0 and 128, O buffers at 256 and 320
 
-    if (warp == 8) {
+    if (warp == kRowWarps) {
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
                 const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
@@ -144,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tma_load_4d(dst + 2 * TILE, &map_v, full(b), 0, 0, h, bb);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kRowWarps + 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc(false, false, TT, TT), idesc_o = make_idesc(false, true, TT, DD);
             auto issue_s = [&](int i) {  // S(i) = q k^T into TMEM buffer i % 2
@@ -160,131 +190,126 @@ __global__ void __launch_bounds__(kThreads, 1)
             };
             if (n_mine > 0) issue_s(0);
             for (int i = 0; i < n_mine; ++i) {
+                const int b = i & 1;
                 if (i + 1 < n_mine) issue_s(i + 1);  // runs under the softmax of pair i
-                mbar_wait(p_ready, i & 1);
-                mbar_wait(o_free, (i & 1) ^ 1u);
+                mbar_wait(p_ready(b), (i >> 1) & 1);
+                mbar_wait(o_free(b), ((i >> 1) & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t v = s_tiles + (i & 1) * FWD_BUF + 2 * TILE;
+                const uint32_t v = s_tiles + b * FWD_BUF + 2 * TILE;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)  // O = P_d v: reduction over the 128 keys
-                    umma_bf16(tmem + 2 * TT, k_desc128(s_p, kk), mn_desc(v, kk), idesc_o, kk > 0);
-                umma_commit(o_ready);
-                umma_commit(empty(i & 1));  // q, k, v of this pair are no longer read
+                    umma_bf16(tmem + C_O + b * DD, k_desc128(s_p + b * 2 * TILE, kk), mn_desc(v, kk), idesc_o, kk > 0);
+                umma_commit(o_ready(b));
+                umma_commit(empty(b));  // q, k, v of this pair are no longer read
             }
         }
     } else {
-        const int q = 32 * (warp & 3) + lane, ch = warp >> 2;
+        const int q = 32 * (warp & 3) + lane, cq = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
-        for (int i = 0; i < n_mine; ++i) {
-            const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
-            const uint32_t grow = (uint32_t)pair * TT + q;
-            uint32_t ra[32], rb[32];
-            mbar_wait(s_ready(b), (i >> 1) & 1);
-            tc_fence_after();
-            tmem_ld_32x32(lane_addr + b * TT + 64 * ch, ra);
-            tmem_ld_32x32(lane_addr + b * TT + 64 * ch + 32, rb);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_free(b));
-            float s[64];
+        float r_prev = 0.0f;
+        for (int i = 0; i <= n_mine; ++i) {
+            float r_cur = 0.0f;
+            if (i < n_mine) {
+                const int pair = blockIdx.x + i * gridDim.x, b = i & 1;
+                const uint32_t grow = (uint32_t)pair * TT + q;
+                uint32_t ra[32];
+                mbar_wait(s_ready(b), (i >> 1) & 1);
+                tc_fence_after();
+                tmem_ld_32x32(lane_addr + b * TT + 32 * cq, ra);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(s_free(b));
+                float s[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(ra[j]), s[32 + j] = __uint_as_float(rb[j]);
-            float mx = s[0];
+                for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(ra[j]);
+                float mx = s[0];
 #pragma unroll
-            for (int j = 1; j < 64; ++j) mx = fmaxf(mx, s[j]);
-            xch[ch * TT + q] = mx;
-            if (threadIdx.x == 0) tma_store_wait_read<0>();  // the staged output of the previous pair has left
-            named_bar_sync<1, kRowThreads>();
-            const float off = fmaxf(xch[q], xch[TT + q]) * p.scale_log2e;
-            float sum = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                s[j] = bf_ex2_approx(fmaf(s[j], p.scale_log2e, -off));
-                sum += s[j];
-            }
-            xch[2 * TT + ch * TT + q] = sum;
-            named_bar_sync<2, kRowThreads>();
-            const float total = xch[2 * TT + q] + xch[3 * TT + q];
-            if (ch == 0) p.lse[grow] = off + bf_lg2_approx(total);
-            if (p.thresh != 0u) {
-                uint32_t w0, w1;
-                keep_words(p, grow, ch, step, w0, w1);
-                if (p.keep) *reinterpret_cast<uint2*>(p.keep + (size_t)grow * 4 + 2 * ch) = make_uint2(w0, w1);
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
+                xch[cq * TT + q] = mx;
+                named_bar_sync<1, kRowThreads>();
+                const float off = fmaxf(fmaxf(xch[q], xch[TT + q]), fmaxf(xch[2 * TT + q], xch[3 * TT + q])) * p.scale_log2e;
+                float sum = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (!((w0 >> j) & 1u)) s[j] = 0.0f;
-                    if (!((w1 >> j) & 1u)) s[32 + j] = 0.0f;
+                    s[j] = bf_ex2_approx(fmaf(s[j], p.scale_log2e, -off));
+                    sum += s[j];
                 }
-            }
-            // P_d (still without 1 / ((1-p) sum): applied to the output row) -> row q of key sub-tile ch
+                xch[4 * TT + cq * TT + q] = sum;
+                named_bar_sync<2, kRowThreads>();
+                const float total = (xch[4 * TT + q] + xch[5 * TT + q]) + (xch[6 * TT + q] + xch[7 * TT + q]);
+                if (cq == 0) p.lse[grow] = off + bf_lg2_approx(total);
+                r_cur = p.inv_keep * bf_rcp_approx(total);
+                if (p.thresh != 0u) {
+                    const uint32_t w = keep_word(p, grow, cq, step);
+                    if (p.keep) p.keep[(size_t)grow * 4 + cq] = w;
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-                sts128(s_p + ch * TILE + chunk_off(q, c8), pack_bf16(s[8 * c8], s[8 * c8 + 1]), pack_bf16(s[8 * c8 + 2], s[8 * c8 + 3]),
-                       pack_bf16(s[8 * c8 + 4], s[8 * c8 + 5]), pack_bf16(s[8 * c8 + 6], s[8 * c8 + 7]));
-            fence_proxy_async();
-            mbar_arrive(p_ready);
-            // ---- output row q, columns 32 ch .. +31
-            mbar_wait(o_ready, i & 1);
-            tc_fence_after();
-            tmem_ld_32x32(lane_addr + 2 * TT + 32 * ch, ra);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(o_free);
-            const float r = p.inv_keep * bf_rcp_approx(total);
+                    for (int j = 0; j < 32; ++j)
+                        if (!(w & (1u << j))) s[j] = 0.0f;
+                }
+                // P_d (still without 1 / ((1-p) sum): applied to the output row) -> row q of key sub-tile cq / 2
+                const uint32_t dst = s_p + (b * 2 + (cq >> 1)) * TILE;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float o[8];
+                for (int c = 0; c < 4; ++c)
+                    sts128(dst + chunk_off(q, 4 * (cq & 1) + c), pack_bf16(s[8 * c], s[8 * c + 1]), pack_bf16(s[8 * c + 2], s[8 * c + 3]),
+                           pack_bf16(s[8 * c + 4], s[8 * c + 5]), pack_bf16(s[8 * c + 6], s[8 * c + 7]));
+                fence_proxy_async();
+                mbar_arrive(p_ready(b));
+            }
+            if (i > 0) {  // output row q of pair i-1, columns 16 cq .. +15
+                const int j = i - 1, pb = j & 1, pair = blockIdx.x + j * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+                uint32_t ro[16];
+                mbar_wait(o_ready(pb), (j >> 1) & 1);
+                tc_fence_after();
+                tmem_ld_32x16(lane_addr + C_O + pb * DD + 16 * cq, ro);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(o_free(pb));
+                uint32_t o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(ra[8 * c4 + e]) * r;
-                sts128(s_out + chunk_off(q, 4 * ch + c4), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                       pack_bf16(o[6], o[7]));
+                for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(ro[2 * e]) * r_prev, __uint_as_float(ro[2 * e + 1]) * r_prev);
+                stg256(p.out + (((size_t)bb * TT + q) * p.H + h) * DD + 16 * cq, o);
             }
-            fence_proxy_async();
-            named_bar_sync<3, kRowThreads>();
-            if (threadIdx.x == 0) {
-                tma_store_4d(&map_o, s_out, 0, 0, h, bb);
-                tma_store_commit();
-            }
+            r_prev = r_cur;
         }
-        if (threadIdx.x == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kRowWarps + 1) {
         tc_fence_after();
         tmem_dealloc(tmem, TMEM_COLS);
     }
 }
 
 // ------------------------------------------------------------------ backward
+// Software pipelined over pairs: the first pass of pair i+1 (P, t = keep ? dP_d : 0 and the partial D) runs while the
+// tensor core computes dv, dk, dq of pair i, whose rows are drained afterwards; the second pass (P_d, dS -> shared
+// memory) runs while S and dP of the next pair are formed.  lse and the keep words are fetched one pair ahead.
 __global__ void __launch_bounds__(kThreads, 1)
     bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
-               const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
-               const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ Params p) {
+               const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = aligned_smem(smem_raw);
     const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * BWD_BUF, s_s = s_p + 2 * TILE;
-    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * BWD_BUF + 4 * TILE);  // [half][row]
+    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * BWD_BUF + 4 * TILE);  // [pair parity][quarter][row]
     const uint32_t bars = s_s + 2 * TILE + XCH_BYTES;
     auto full = [&](int b) { return bars + 8u * b; };
     auto empty = [&](int b) { return bars + 8u * (2 + b); };
     const uint32_t s_ready = bars + 32, s_free = bars + 40, p_ready = bars + 48, o_ready = bars + 56, o_free = bars + 64,
-                   tmem_slot = bars + 96;
-    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + 96);
+                   tmem_slot = bars + 128;
+    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == kRowThreads) {
         tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v), tma_prefetch_desc(&map_do);
-        tma_prefetch_desc(&map_dq), tma_prefetch_desc(&map_dk), tma_prefetch_desc(&map_dv);
         for (int b = 0; b < 2; ++b) mbar_init(full(b), 1), mbar_init(empty(b), 1);
         mbar_init(s_ready, 1), mbar_init(s_free, kRowThreads), mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1);
         mbar_init(o_free, kRowThreads);
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == kRowWarps + 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -293,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // TMEM columns: S 0..127, dP 128..255, dv 256..319, dk 320..383, dq 384..447
     constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
 
-    if (warp == 8) {
+    if (warp == kRowWarps) {
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
                 const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
@@ -306,12 +331,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tma_load_4d(dst + 3 * TILE, &map_do, full(b), 0, 0, h, bb);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kRowWarps + 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc(false, false, TT, TT);   // S, dP: both operands K-major
             constexpr uint32_t idesc_t = make_idesc(true, true, TT, DD);     // dv, dk: transposed A, B = [q][d]
             constexpr uint32_t idesc_q = make_idesc(false, true, TT, DD);    // dq: A = dS [q][key], B = k [key][d]
-            for (int i = 0; i < n_mine; ++i) {
+            auto issue_sdp = [&](int i) {
                 const int b = i & 1;
                 const uint32_t q = s_tiles + b * BWD_BUF, k = q + TILE, v = q + 2 * TILE, dO = q + 3 * TILE;
                 mbar_wait(full(b), (i >> 1) & 1);
@@ -324,8 +349,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16(tmem + C_DP, operand_desc<false>(dO, kk), operand_desc<false>(v, kk), idesc_s, kk > 0);
                 umma_commit(s_ready);
+            };
+            if (n_mine > 0) issue_sdp(0);
+            for (int i = 0; i < n_mine; ++i) {
+                const int b = i & 1;
+                const uint32_t q = s_tiles + b * BWD_BUF, k = q + TILE, dO = q + 3 * TILE;
+                if (i + 1 < n_mine) issue_sdp(i + 1);  // as soon as the row workers have taken S, dP of pair i
+                BF_STAMP(1, 3);
                 mbar_wait(p_ready, i & 1);
+                BF_STAMP(1, 4);
                 mbar_wait(o_free, (i & 1) ^ 1u);
+                BF_STAMP(1, 5);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)  // dv[key][d] = sum_q P_d[q][key] dO[q][d]
@@ -338,101 +372,100 @@ __global__ void __launch_bounds__(kThreads, 1)
                     umma_bf16(tmem + C_DQ, k_desc128(s_s, kk), mn_desc(k, kk), idesc_q, kk > 0);
                 umma_commit(o_ready);
                 umma_commit(empty(b));
+                BF_STAMP(1, 6);
             }
         }
     } else {
-        const int q = 32 * (warp & 3) + lane, ch = warp >> 2;
+        const int q = 32 * (warp & 3) + lane, cq = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const float ik = p.thresh != 0u ? p.inv_keep : 1.0f;
-        for (int i = 0; i < n_mine; ++i) {
-            const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
-            const uint32_t grow = (uint32_t)pair * TT + q;
-            const float lse = __ldg(p.lse + grow);
-            uint2 kw = make_uint2(0xffffffffu, 0xffffffffu);
-            if (p.thresh != 0u) kw = __ldg(reinterpret_cast<const uint2*>(p.keep + (size_t)grow * 4 + 2 * ch));
-            uint32_t ra[32], rb[32], rc[32], rd[32];
+        uint32_t rp[32], rt[32];  // P (true probabilities) and t = keep ? dP_d : 0 of the pair in flight
+        float part = 0.0f, lse_n = 0.0f;
+        uint32_t kw = 0xffffffffu, kw_n = 0xffffffffu;
+        auto fetch = [&](int i) {  // lse and keep word of pair i (used one pass later)
+            if (i < n_mine) {
+                const uint32_t grow = (uint32_t)(blockIdx.x + i * gridDim.x) * TT + q;
+                lse_n = __ldg(p.lse + grow);
+                if (p.thresh != 0u) kw_n = __ldg(p.keep + (size_t)grow * 4 + cq);
+            }
+        };
+        auto pass1 = [&](int i) {  // S, dP of pair i -> P, t, partial D over this quarter of the keys
+            const float lse = lse_n;
+            kw = kw_n;
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
-            tmem_ld_32x32(lane_addr + C_S + 64 * ch, ra);
-            tmem_ld_32x32(lane_addr + C_S + 64 * ch + 32, rb);
-            tmem_ld_32x32(lane_addr + C_DP + 64 * ch, rc);
-            tmem_ld_32x32(lane_addr + C_DP + 64 * ch + 32, rd);
+            tmem_ld_32x32(lane_addr + C_S + 32 * cq, rp);
+            tmem_ld_32x32(lane_addr + C_DP + 32 * cq, rt);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_free);
-            // P (true probabilities) in ra / rb, t = keep ? dP_d : 0 in rc / rd; partial D over this half of the keys
-            float part = 0.0f;
+            fetch(i + 1);
+            part = 0.0f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float p0 = bf_ex2_approx(fmaf(__uint_as_float(ra[j]), p.scale_log2e, -lse));
-                const float p1 = bf_ex2_approx(fmaf(__uint_as_float(rb[j]), p.scale_log2e, -lse));
-                const float t0 = ((kw.x >> j) & 1u) ? __uint_as_float(rc[j]) : 0.0f;
-                const float t1 = ((kw.y >> j) & 1u) ? __uint_as_float(rd[j]) : 0.0f;
-                part = fmaf(p0, t0, fmaf(p1, t1, part));
-                ra[j] = __float_as_uint(p0), rb[j] = __float_as_uint(p1);
-                rc[j] = __float_as_uint(t0), rd[j] = __float_as_uint(t1);
+                const float pj = bf_ex2_approx(fmaf(__uint_as_float(rp[j]), p.scale_log2e, -lse));
+                const float tj = (kw & (1u << j)) ? __uint_as_float(rt[j]) : 0.0f;
+                part = fmaf(pj, tj, part);
+                rp[j] = __float_as_uint(pj), rt[j] = __float_as_uint(tj);
             }
-            xch[ch * TT + q] = part * ik;
-            if (threadIdx.x == 0) tma_store_wait_read<0>();  // the staged gradients of the previous pair have left
+        };
+        fetch(0);
+        if (n_mine > 0) pass1(0);
+        for (int i = 0; i < n_mine; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+            if (threadIdx.x == 0) BF_STAMP(0, 0);
+            float* const xi = xch + (i & 1) * 4 * TT;  // by parity: this barrier is the only one of the pair
+            xi[cq * TT + q] = part * ik;
             named_bar_sync<1, kRowThreads>();
-            const float Dq = xch[q] + xch[TT + q];  // = sum_k P_d dP_d = rowsum(dO o O)
-            // P_d = keep ? P / (1-p) : 0 and dS = P (t / (1-p) - D) scale -> row q of key sub-tile ch
+            if (threadIdx.x == 0) BF_STAMP(0, 1);
+            const float Dq = (xi[q] + xi[TT + q]) + (xi[2 * TT + q] + xi[3 * TT + q]);  // = rowsum(dO o O)
+            // P_d = keep ? P / (1-p) : 0 and dS = P (t / (1-p) - D) scale -> row q of key sub-tile cq / 2
+            {
+                const uint32_t o0 = (cq >> 1) * TILE;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t(&pr)[32] = half ? rb : ra;
-                const uint32_t(&tr)[32] = half ? rd : rc;
-                const uint32_t kbits = half ? kw.y : kw.x;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t pd[4], ds[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int j0 = 8 * c4 + 2 * e, j1 = j0 + 1;
-                        const float pa = __uint_as_float(pr[j0]), pb = __uint_as_float(pr[j1]);
-                        pd[e] = pack_bf16(((kbits >> j0) & 1u) ? pa * ik : 0.0f, ((kbits >> j1) & 1u) ? pb * ik : 0.0f);
-                        ds[e] = pack_bf16(pa * p.scale * fmaf(__uint_as_float(tr[j0]), ik, -Dq),
-                                          pb * p.scale * fmaf(__uint_as_float(tr[j1]), ik, -Dq));
+                        const int j0 = 8 * c + 2 * e, j1 = j0 + 1;
+                        const float pa = __uint_as_float(rp[j0]), pb = __uint_as_float(rp[j1]);
+                        pd[e] = pack_bf16((kw & (1u << j0)) ? pa * ik : 0.0f, (kw & (1u << j1)) ? pb * ik : 0.0f);
+                        ds[e] = pack_bf16(pa * p.scale * fmaf(__uint_as_float(rt[j0]), ik, -Dq),
+                                          pb * p.scale * fmaf(__uint_as_float(rt[j1]), ik, -Dq));
                     }
-                    const uint32_t o = ch * TILE + chunk_off(q, 4 * half + c4);
+                    const uint32_t o = o0 + chunk_off(q, 4 * (cq & 1) + c);
                     sts128(s_p + o, pd[0], pd[1], pd[2], pd[3]);
                     sts128(s_s + o, ds[0], ds[1], ds[2], ds[3]);
                 }
             }
             fence_proxy_async();
             mbar_arrive(p_ready);
-            // ---- gradients: row q (dq) / key q (dv, dk), columns 32 ch .. +31, staged where P_d / dS were
+            if (threadIdx.x == 0) BF_STAMP(0, 2);
+            if (i + 1 < n_mine) pass1(i + 1);  // under the dv / dk / dq MMAs of pair i
+            if (threadIdx.x == 0) BF_STAMP(0, 3);
+            // ---- gradients: row q (dq) / key q (dv, dk), columns 16 cq .. +15; one at a time (P, t of the next pair
+            //      are live in registers)
             mbar_wait(o_ready, i & 1);
+            if (threadIdx.x == 0) BF_STAMP(0, 4);
             tc_fence_after();
-            tmem_ld_32x32(lane_addr + C_DV + 32 * ch, ra);
-            tmem_ld_32x32(lane_addr + C_DK + 32 * ch, rb);
-            tmem_ld_32x32(lane_addr + C_DQ + 32 * ch, rc);
-            tmem_ld_wait();
+            const size_t orow = (((size_t)bb * TT + q) * p.H + h) * DD + 16 * cq;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                uint32_t ro[16], o[8];
+                tmem_ld_32x16(lane_addr + (g == 0 ? C_DV : g == 1 ? C_DK : C_DQ) + 16 * cq, ro);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(ro[2 * e]), __uint_as_float(ro[2 * e + 1]));
+                stg256((g == 0 ? p.dv : g == 1 ? p.dk : p.dq) + orow, o);
+            }
             tc_fence_before();
             mbar_arrive(o_free);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const uint32_t o = chunk_off(q, 4 * ch + c4);
-                auto pk = [&](const uint32_t(&r)[32], int e) {
-                    return pack_bf16(__uint_as_float(r[8 * c4 + 2 * e]), __uint_as_float(r[8 * c4 + 2 * e + 1]));
-                };
-                sts128(s_p + o, pk(ra, 0), pk(ra, 1), pk(ra, 2), pk(ra, 3));
-                sts128(s_p + TILE + o, pk(rb, 0), pk(rb, 1), pk(rb, 2), pk(rb, 3));
-                sts128(s_s + o, pk(rc, 0), pk(rc, 1), pk(rc, 2), pk(rc, 3));
-            }
-            fence_proxy_async();
-            named_bar_sync<2, kRowThreads>();
-            if (threadIdx.x == 0) {
-                tma_store_4d(&map_dv, s_p, 0, 0, h, bb);
-                tma_store_4d(&map_dk, s_p + TILE, 0, 0, h, bb);
-                tma_store_4d(&map_dq, s_s, 0, 0, h, bb);
-                tma_store_commit();
-            }
+            if (threadIdx.x == 0) BF_STAMP(0, 5);
         }
-        if (threadIdx.x == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kRowWarps + 1) {
         tc_fence_after();
         tmem_dealloc(tmem, TMEM_COLS);
     }
@@ -483,17 +516,17 @@ int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64
                         float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* out, float* lse, uint32_t* keep,
                         cudaStream_t stream) {
     using namespace attn_tc;
-    CUtensorMap mq, mk, mv, mo;
+    CUtensorMap mq, mk, mv;
     int rc;
     if ((rc = encode_pair_map(&mq, q, B, H, strides[0], strides[1], strides[2]))) return rc;
     if ((rc = encode_pair_map(&mk, k, B, H, strides[3], strides[4], strides[5]))) return rc;
     if ((rc = encode_pair_map(&mv, v, B, H, strides[6], strides[7], strides[8]))) return rc;
-    if ((rc = encode_pair_map(&mo, out, B, H, (int64_t)TT * H * DD, DD, H * DD))) return rc;
     Params p{};
     fill(p, B, H, scale, p_drop, seed, step, site, lse, keep);
+    p.out = (__nv_bfloat16*)out;
     BF_CUDA_OK(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
-    fwd_kernel<<<grid, kThreads, FWD_SMEM, stream>>>(mq, mk, mv, mo, p);
+    fwd_kernel<<<grid, kThreads, FWD_SMEM, stream>>>(mq, mk, mv, p);
     BF_LAUNCH_OK();
     return 0;
 }
@@ -502,21 +535,19 @@ int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const vo
                         const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
                         uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream) {
     using namespace attn_tc;
-    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
+    CUtensorMap mq, mk, mv, mdo;
     const int64_t osb = (int64_t)TT * H * DD, osh = DD, ost = H * DD;
     int rc;
     if ((rc = encode_pair_map(&mq, q, B, H, strides[0], strides[1], strides[2]))) return rc;
     if ((rc = encode_pair_map(&mk, k, B, H, strides[3], strides[4], strides[5]))) return rc;
     if ((rc = encode_pair_map(&mv, v, B, H, strides[6], strides[7], strides[8]))) return rc;
     if ((rc = encode_pair_map(&mdo, dout, B, H, osb, osh, ost))) return rc;
-    if ((rc = encode_pair_map(&mdq, dq, B, H, osb, osh, ost))) return rc;
-    if ((rc = encode_pair_map(&mdk, dk, B, H, osb, osh, ost))) return rc;
-    if ((rc = encode_pair_map(&mdv, dv, B, H, osb, osh, ost))) return rc;
     Params p{};
     fill(p, B, H, scale, p_drop, seed, step, site, const_cast<float*>(lse), const_cast<uint32_t*>(keep));
+    p.dq = (__nv_bfloat16*)dq, p.dk = (__nv_bfloat16*)dk, p.dv = (__nv_bfloat16*)dv;
     BF_CUDA_OK(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
-    bwd_kernel<<<grid, kThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
+    bwd_kernel<<<grid, kThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, p);
     BF_LAUNCH_OK();
     return 0;
 }

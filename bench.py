@@ -79,9 +79,10 @@ def parse():
     ap.add_argument("--host-ln", type=int, default=1)
     ap.add_argument("--fuse-residual", type=int, default=1)
     ap.add_argument("--grad-sinks", type=int, default=1)
-    ap.add_argument("--attention", type=int, default=0,
-                    help="1: route the host model's short-sequence attention (T <= 128) through the native kernels "
-                         "(correct, but at 110 TFLOP/s still behind cuDNN's fused attention: off by default)")
+    ap.add_argument("--attention", type=int, default=1,
+                    help="1 (default): the host model's short-sequence attention (T <= 128) runs on the native kernels "
+                         "(tcgen05 at T = 128: 1.2 ms per BERT-base layer fwd+bwd against 2.2 ms of cuDNN's fused "
+                         "attention); 0: torch SDPA")
     ap.add_argument("--sigma-cache", type=int, default=1,
                     help="ClipAdamW writes softplus(updated rho) next to its update; the sampling kernel reads it")
     ap.add_argument("--gelu-links", type=int, default=1,
@@ -375,7 +376,7 @@ def workload_config(args, world):
             "host_layernorm": ("native kernels (bf_layernorm_*)" if args.host_ln else "torch") if bert else "n/a",
             "output_blocks": ("dropout + residual + LayerNorm fused (bf_resln_*, Philox mask, bias grad handed to the Linear)"
                               if args.fuse_residual else "torch dropout + add, separate LayerNorm") if bert else "n/a",
-            "attention": ("native whole-sequence kernels (bf_attention_*, Philox dropout mask) for T <= 128, else torch SDPA"
+            "attention": ("native whole-sequence kernels (bf_attention_*: tcgen05 at T = 128, Philox dropout mask) for T <= 128, else torch SDPA"
                           if args.attention else "torch SDPA (cuDNN)") if bert else "n/a",
             "shared_input_grads": ("accumulated in place by the dgrad kernels (TMA reduce-add)"
                                    if (args.grad_sinks and args.fuse_residual) else "autograd add passes") if bert else "n/a",
