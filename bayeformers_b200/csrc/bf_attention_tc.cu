@@ -39,11 +39,13 @@ constexpr int TILE = TT * DD * 2;      // one [128][64] bf16 tile, 128 B rows, 1
 constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;   // 512 row workers
 constexpr int kThreads = kRowThreads + 64;    // + producer warp (16) + MMA warp (17)
+constexpr int kBwdThreads = kThreads + 32;    // backward: + store warp (18)
 constexpr int FWD_BUF = 3 * TILE;      // q, k, v
 constexpr int BWD_BUF = 4 * TILE;      // q, k, v, dO
 constexpr int XCH_BYTES = 2 * 4 * TT * 4;  // two exchanged row statistics x four column quarters
 constexpr int BAR_BYTES = 256;
-constexpr int FWD_SMEM = 1024 + 2 * FWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;  // + 2 x P_d (2 sub-tiles)
+constexpr int kFwdStages = 3;          // q, k, v tile buffers in flight (the kernel is bound by bytes in flight per SM)
+constexpr int FWD_SMEM = 1024 + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;  // + 2 x P_d (2 sub-tiles)
 constexpr int BWD_SMEM = 1024 + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;         // + P_d, dS (2 sub-tiles each)
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -62,6 +64,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 // 32 lanes x 16 consecutive 32-bit columns (see tmem_ld_32x32)
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -131,24 +138,25 @@ __global__ void __launch_bounds__(kThreads, 1)
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = aligned_smem(smem_raw);
-    const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * FWD_BUF;
-    float* const xch = reinterpret_cast<float*>(sm.gen + 2 * FWD_BUF + 4 * TILE);  // [kind][quarter][row]
+    const uint32_t s_tiles = sm.base, s_p = sm.base + kFwdStages * FWD_BUF;
+    float* const xch = reinterpret_cast<float*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE);  // [kind][quarter][row]
     const uint32_t bars = s_p + 4 * TILE + XCH_BYTES;
-    auto full = [&](int b) { return bars + 8u * b; };
-    auto empty = [&](int b) { return bars + 8u * (2 + b); };
-    auto s_ready = [&](int b) { return bars + 8u * (4 + b); };
-    auto s_free = [&](int b) { return bars + 8u * (6 + b); };
-    auto p_ready = [&](int b) { return bars + 8u * (8 + b); };
-    auto o_ready = [&](int b) { return bars + 8u * (10 + b); };
-    auto o_free = [&](int b) { return bars + 8u * (12 + b); };
+    auto full = [&](int st) { return bars + 8u * st; };                 // q, k, v tiles: kFwdStages deep
+    auto empty = [&](int st) { return bars + 8u * (kFwdStages + st); };
+    auto s_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + b); };  // S, P_d, O: double buffered (b = i % 2)
+    auto s_free = [&](int b) { return bars + 8u * (2 * kFwdStages + 2 + b); };
+    auto p_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + 4 + b); };
+    auto o_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + 6 + b); };
+    auto o_free = [&](int b) { return bars + 8u * (2 * kFwdStages + 8 + b); };
     const uint32_t tmem_slot = bars + 128;
-    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * FWD_BUF + 4 * TILE + XCH_BYTES + 128);
+    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == kRowThreads) {
         tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v);
+        for (int st = 0; st < kFwdStages; ++st) mbar_init(full(st), 1), mbar_init(empty(st), 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(full(b), 1), mbar_init(empty(b), 1), mbar_init(s_ready(b), 1), mbar_init(s_free(b), kRowThreads);
+            mbar_init(s_ready(b), 1), mbar_init(s_free(b), kRowThreads);
             mbar_init(p_ready(b), kRowThreads), mbar_init(o_ready(b), 1), mbar_init(o_free(b), kRowThreads);
         }
         fence_barrier_init();
@@ -165,24 +173,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == kRowWarps) {
         if (lane == 0) {
             for (int i = 0; i < n_mine; ++i) {
-                const int pair = blockIdx.x + i * gridDim.x, b = i & 1, bb = pair / p.H, h = pair - bb * p.H;
-                mbar_wait(empty(b), ((i >> 1) & 1) ^ 1u);
-                mbar_expect_tx(full(b), 3 * TILE);
-                const uint32_t dst = s_tiles + b * FWD_BUF;
-                tma_load_4d(dst, &map_q, full(b), 0, 0, h, bb);
-                tma_load_4d(dst + TILE, &map_k, full(b), 0, 0, h, bb);
-                tma_load_4d(dst + 2 * TILE, &map_v, full(b), 0, 0, h, bb);
+                const int pair = blockIdx.x + i * gridDim.x, st = i % kFwdStages, bb = pair / p.H, h = pair - bb * p.H;
+                mbar_wait(empty(st), ((i / kFwdStages) & 1) ^ 1u);
+                mbar_expect_tx(full(st), 3 * TILE);
+                const uint32_t dst = s_tiles + st * FWD_BUF;
+                tma_load_4d(dst, &map_q, full(st), 0, 0, h, bb);
+                tma_load_4d(dst + TILE, &map_k, full(st), 0, 0, h, bb);
+                tma_load_4d(dst + 2 * TILE, &map_v, full(st), 0, 0, h, bb);
             }
         }
     } else if (warp == kRowWarps + 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc(false, false, TT, TT), idesc_o = make_idesc(false, true, TT, DD);
             auto issue_s = [&](int i) {  // S(i) = q k^T into TMEM buffer i % 2
-                const int b = i & 1;
-                mbar_wait(full(b), (i >> 1) & 1);
+                const int b = i & 1, st = i % kFwdStages;
+                mbar_wait(full(st), (i / kFwdStages) & 1);
                 mbar_wait(s_free(b), ((i >> 1) & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t q = s_tiles + b * FWD_BUF, k = q + TILE;
+                const uint32_t q = s_tiles + st * FWD_BUF, k = q + TILE;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16(tmem + b * TT, operand_desc<false>(q, kk), operand_desc<false>(k, kk), idesc_s, kk > 0);
@@ -195,12 +203,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(p_ready(b), (i >> 1) & 1);
                 mbar_wait(o_free(b), ((i >> 1) & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t v = s_tiles + b * FWD_BUF + 2 * TILE;
+                const uint32_t v = s_tiles + (i % kFwdStages) * FWD_BUF + 2 * TILE;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)  // O = P_d v: reduction over the 128 keys
                     umma_bf16(tmem + C_O + b * DD, k_desc128(s_p + b * 2 * TILE, kk), mn_desc(v, kk), idesc_o, kk > 0);
                 umma_commit(o_ready(b));
-                umma_commit(empty(b));  // q, k, v of this pair are no longer read
+                umma_commit(empty(i % kFwdStages));  // q, k, v of this pair are no longer read
             }
         }
     } else {
@@ -208,70 +216,77 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
         float r_prev = 0.0f;
-        for (int i = 0; i <= n_mine; ++i) {
-            float r_cur = 0.0f;
-            if (i < n_mine) {
-                const int pair = blockIdx.x + i * gridDim.x, b = i & 1;
-                const uint32_t grow = (uint32_t)pair * TT + q;
-                uint32_t ra[32];
-                mbar_wait(s_ready(b), (i >> 1) & 1);
-                tc_fence_after();
-                tmem_ld_32x32(lane_addr + b * TT + 32 * cq, ra);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(s_free(b));
-                float s[32];
+        // output row q of pair j, columns 16 cq .. +15: straight from TMEM to global memory
+        auto drain = [&](int j, float r) {
+            const int pb = j & 1, pair = blockIdx.x + j * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+            uint32_t ro[16], o[8];
+            mbar_wait(o_ready(pb), (j >> 1) & 1);
+            tc_fence_after();
+            tmem_ld_32x16(lane_addr + C_O + pb * DD + 16 * cq, ro);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(o_free(pb));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(ra[j]);
-                float mx = s[0];
+            for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(ro[2 * e]) * r, __uint_as_float(ro[2 * e + 1]) * r);
+            stg256(p.out + (((size_t)bb * TT + q) * p.H + h) * DD + 16 * cq, o);
+        };
+        for (int i = 0; i < n_mine; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x, b = i & 1;
+            const uint32_t grow = (uint32_t)pair * TT + q;
+            uint32_t ra[32];
+            if (threadIdx.x == 0) BF_STAMP(0, 0);
+            mbar_wait(s_ready(b), (i >> 1) & 1);
+            if (threadIdx.x == 0) BF_STAMP(0, 1);
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + b * TT + 32 * cq, ra);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free(b));
+            float s[32];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
-                xch[cq * TT + q] = mx;
-                named_bar_sync<1, kRowThreads>();
-                const float off = fmaxf(fmaxf(xch[q], xch[TT + q]), fmaxf(xch[2 * TT + q], xch[3 * TT + q])) * p.scale_log2e;
-                float sum = 0.0f;
+            for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(ra[j]);
+            float mx = s[0];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    s[j] = bf_ex2_approx(fmaf(s[j], p.scale_log2e, -off));
-                    sum += s[j];
-                }
-                xch[4 * TT + cq * TT + q] = sum;
-                named_bar_sync<2, kRowThreads>();
-                const float total = (xch[4 * TT + q] + xch[5 * TT + q]) + (xch[6 * TT + q] + xch[7 * TT + q]);
-                if (cq == 0) p.lse[grow] = off + bf_lg2_approx(total);
-                r_cur = p.inv_keep * bf_rcp_approx(total);
-                if (p.thresh != 0u) {
-                    const uint32_t w = keep_word(p, grow, cq, step);
-                    if (p.keep) p.keep[(size_t)grow * 4 + cq] = w;
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
+            xch[cq * TT + q] = mx;
+            if (threadIdx.x == 0) BF_STAMP(0, 2);
+            named_bar_sync<1, kRowThreads>();
+            if (threadIdx.x == 0) BF_STAMP(0, 3);
+            if (threadIdx.x == 0) BF_STAMP(0, 4);
+            const float off = fmaxf(fmaxf(xch[q], xch[TT + q]), fmaxf(xch[2 * TT + q], xch[3 * TT + q])) * p.scale_log2e;
+            float sum = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (!(w & (1u << j))) s[j] = 0.0f;
-                }
-                // P_d (still without 1 / ((1-p) sum): applied to the output row) -> row q of key sub-tile cq / 2
-                const uint32_t dst = s_p + (b * 2 + (cq >> 1)) * TILE;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    sts128(dst + chunk_off(q, 4 * (cq & 1) + c), pack_bf16(s[8 * c], s[8 * c + 1]), pack_bf16(s[8 * c + 2], s[8 * c + 3]),
-                           pack_bf16(s[8 * c + 4], s[8 * c + 5]), pack_bf16(s[8 * c + 6], s[8 * c + 7]));
-                fence_proxy_async();
-                mbar_arrive(p_ready(b));
+            for (int j = 0; j < 32; ++j) {
+                s[j] = bf_ex2_approx(fmaf(s[j], p.scale_log2e, -off));
+                sum += s[j];
             }
-            if (i > 0) {  // output row q of pair i-1, columns 16 cq .. +15
-                const int j = i - 1, pb = j & 1, pair = blockIdx.x + j * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
-                uint32_t ro[16];
-                mbar_wait(o_ready(pb), (j >> 1) & 1);
-                tc_fence_after();
-                tmem_ld_32x16(lane_addr + C_O + pb * DD + 16 * cq, ro);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(o_free(pb));
-                uint32_t o[8];
+            xch[4 * TT + cq * TT + q] = sum;
+            if (threadIdx.x == 0) BF_STAMP(0, 5);
+            named_bar_sync<2, kRowThreads>();
+            if (threadIdx.x == 0) BF_STAMP(0, 6);
+            const float total = (xch[4 * TT + q] + xch[5 * TT + q]) + (xch[6 * TT + q] + xch[7 * TT + q]);
+            if (cq == 0) p.lse[grow] = off + bf_lg2_approx(total);
+            const float r_cur = p.inv_keep * bf_rcp_approx(total);
+            if (p.thresh != 0u) {
+                const uint32_t w = keep_word(p, grow, cq, step);
+                if (p.keep) p.keep[(size_t)grow * 4 + cq] = w;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(ro[2 * e]) * r_prev, __uint_as_float(ro[2 * e + 1]) * r_prev);
-                stg256(p.out + (((size_t)bb * TT + q) * p.H + h) * DD + 16 * cq, o);
+                for (int j = 0; j < 32; ++j)
+                    if (!(w & (1u << j))) s[j] = 0.0f;
             }
+            // P_d (still without 1 / ((1-p) sum): applied to the output row) -> row q of key sub-tile cq / 2
+            const uint32_t dst = s_p + (b * 2 + (cq >> 1)) * TILE;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                sts128(dst + chunk_off(q, 4 * (cq & 1) + c), pack_bf16(s[8 * c], s[8 * c + 1]), pack_bf16(s[8 * c + 2], s[8 * c + 3]),
+                       pack_bf16(s[8 * c + 4], s[8 * c + 5]), pack_bf16(s[8 * c + 6], s[8 * c + 7]));
+            fence_proxy_async();
+            mbar_arrive(p_ready(b));
+            if (threadIdx.x == 0) BF_STAMP(0, 7);
+            if (i > 0) drain(i - 1, r_prev);  // O(i-1) finished under this pair's softmax
             r_prev = r_cur;
         }
+        if (n_mine > 0) drain(n_mine - 1, r_prev);
     }
     tc_fence_before();
     __syncthreads();
@@ -285,10 +300,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 // Software pipelined over pairs: the first pass of pair i+1 (P, t = keep ? dP_d : 0 and the partial D) runs while the
 // tensor core computes dv, dk, dq of pair i, whose rows are drained afterwards; the second pass (P_d, dS -> shared
 // memory) runs while S and dP of the next pair are formed.  lse and the keep words are fetched one pair ahead.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
     bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
+               const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = aligned_smem(smem_raw);
     const uint32_t s_tiles = sm.base, s_p = sm.base + 2 * BWD_BUF, s_s = s_p + 2 * TILE;
@@ -297,15 +313,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     auto full = [&](int b) { return bars + 8u * b; };
     auto empty = [&](int b) { return bars + 8u * (2 + b); };
     const uint32_t s_ready = bars + 32, s_free = bars + 40, p_ready = bars + 48, o_ready = bars + 56, o_free = bars + 64,
-                   tmem_slot = bars + 128;
+                   staged = bars + 72, stage_free = bars + 80, tmem_slot = bars + 128;
     volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == kRowThreads) {
         tma_prefetch_desc(&map_q), tma_prefetch_desc(&map_k), tma_prefetch_desc(&map_v), tma_prefetch_desc(&map_do);
+        tma_prefetch_desc(&map_dq), tma_prefetch_desc(&map_dk), tma_prefetch_desc(&map_dv);
         for (int b = 0; b < 2; ++b) mbar_init(full(b), 1), mbar_init(empty(b), 1);
         mbar_init(s_ready, 1), mbar_init(s_free, kRowThreads), mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1);
-        mbar_init(o_free, kRowThreads);
+        mbar_init(o_free, kRowThreads), mbar_init(staged, kRowThreads), mbar_init(stage_free, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -375,7 +392,22 @@ __global__ void __launch_bounds__(kThreads, 1)
                 BF_STAMP(1, 6);
             }
         }
-    } else {
+    } else if (warp == kRowWarps + 2) {
+        // ===================== store warp: the staged gradient tiles (where P_d / dS were) -> global memory =====================
+        if (lane == 0) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+                mbar_wait(staged, i & 1);
+                tma_store_4d(&map_dv, s_p, 0, 0, h, bb);
+                tma_store_4d(&map_dk, s_p + TILE, 0, 0, h, bb);
+                tma_store_4d(&map_dq, s_s, 0, 0, h, bb);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+                mbar_arrive(stage_free);  // P_d / dS of the next pair may be written
+            }
+            tma_store_wait_all();
+        }
+    } else if (warp < kRowWarps) {
         const int q = 32 * (warp & 3) + lane, cq = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const float ik = p.thresh != 0u ? p.inv_keep : 1.0f;
@@ -412,30 +444,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         fetch(0);
         if (n_mine > 0) pass1(0);
         for (int i = 0; i < n_mine; ++i) {
-            const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
             if (threadIdx.x == 0) BF_STAMP(0, 0);
             float* const xi = xch + (i & 1) * 4 * TT;  // by parity: this barrier is the only one of the pair
             xi[cq * TT + q] = part * ik;
             named_bar_sync<1, kRowThreads>();
             if (threadIdx.x == 0) BF_STAMP(0, 1);
             const float Dq = (xi[q] + xi[TT + q]) + (xi[2 * TT + q] + xi[3 * TT + q]);  // = rowsum(dO o O)
-            // P_d = keep ? P / (1-p) : 0 and dS = P (t / (1-p) - D) scale -> row q of key sub-tile cq / 2
+            // P_d = keep ? P / (1-p) : 0 and dS = P (t / (1-p) - D) scale, packed in place (rp <- P_d, rt <- dS) ...
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int j0 = 2 * e, j1 = j0 + 1;
+                const float pa = __uint_as_float(rp[j0]), pb = __uint_as_float(rp[j1]);
+                const uint32_t ds = pack_bf16(pa * p.scale * fmaf(__uint_as_float(rt[j0]), ik, -Dq),
+                                              pb * p.scale * fmaf(__uint_as_float(rt[j1]), ik, -Dq));
+                rp[e] = pack_bf16((kw & (1u << j0)) ? pa * ik : 0.0f, (kw & (1u << j1)) ? pb * ik : 0.0f);
+                rt[e] = ds;
+            }
+            // ... while the gradient tiles of the previous pair leave the shared memory they were staged in; then row q of
+            // key sub-tile cq / 2
+            mbar_wait(stage_free, (i & 1) ^ 1u);
             {
                 const uint32_t o0 = (cq >> 1) * TILE;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    uint32_t pd[4], ds[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j0 = 8 * c + 2 * e, j1 = j0 + 1;
-                        const float pa = __uint_as_float(rp[j0]), pb = __uint_as_float(rp[j1]);
-                        pd[e] = pack_bf16((kw & (1u << j0)) ? pa * ik : 0.0f, (kw & (1u << j1)) ? pb * ik : 0.0f);
-                        ds[e] = pack_bf16(pa * p.scale * fmaf(__uint_as_float(rt[j0]), ik, -Dq),
-                                          pb * p.scale * fmaf(__uint_as_float(rt[j1]), ik, -Dq));
-                    }
                     const uint32_t o = o0 + chunk_off(q, 4 * (cq & 1) + c);
-                    sts128(s_p + o, pd[0], pd[1], pd[2], pd[3]);
-                    sts128(s_s + o, ds[0], ds[1], ds[2], ds[3]);
+                    sts128(s_p + o, rp[4 * c], rp[4 * c + 1], rp[4 * c + 2], rp[4 * c + 3]);
+                    sts128(s_s + o, rt[4 * c], rt[4 * c + 1], rt[4 * c + 2], rt[4 * c + 3]);
                 }
             }
             fence_proxy_async();
@@ -443,23 +477,28 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (threadIdx.x == 0) BF_STAMP(0, 2);
             if (i + 1 < n_mine) pass1(i + 1);  // under the dv / dk / dq MMAs of pair i
             if (threadIdx.x == 0) BF_STAMP(0, 3);
-            // ---- gradients: row q (dq) / key q (dv, dk), columns 16 cq .. +15; one at a time (P, t of the next pair
-            //      are live in registers)
+            // ---- gradients: row q (dq) / key q (dv, dk), columns 16 cq .. +15, staged where P_d / dS were (their MMAs
+            //      are complete); one at a time: P, t of the next pair are live in registers
             mbar_wait(o_ready, i & 1);
             if (threadIdx.x == 0) BF_STAMP(0, 4);
             tc_fence_after();
-            const size_t orow = (((size_t)bb * TT + q) * p.H + h) * DD + 16 * cq;
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
-                uint32_t ro[16], o[8];
+                uint32_t ro[16];
                 tmem_ld_32x16(lane_addr + (g == 0 ? C_DV : g == 1 ? C_DK : C_DQ) + 16 * cq, ro);
                 tmem_ld_wait();
+                const uint32_t dst = g == 0 ? s_p : g == 1 ? s_p + TILE : s_s;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(ro[2 * e]), __uint_as_float(ro[2 * e + 1]));
-                stg256((g == 0 ? p.dv : g == 1 ? p.dk : p.dq) + orow, o);
+                for (int c = 0; c < 2; ++c)
+                    sts128(dst + chunk_off(q, 2 * cq + c), pack_bf16(__uint_as_float(ro[8 * c]), __uint_as_float(ro[8 * c + 1])),
+                           pack_bf16(__uint_as_float(ro[8 * c + 2]), __uint_as_float(ro[8 * c + 3])),
+                           pack_bf16(__uint_as_float(ro[8 * c + 4]), __uint_as_float(ro[8 * c + 5])),
+                           pack_bf16(__uint_as_float(ro[8 * c + 6]), __uint_as_float(ro[8 * c + 7])));
             }
             tc_fence_before();
             mbar_arrive(o_free);
+            fence_proxy_async();
+            mbar_arrive(staged);
             if (threadIdx.x == 0) BF_STAMP(0, 5);
         }
     }
@@ -535,19 +574,22 @@ int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const vo
                         const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
                         uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream) {
     using namespace attn_tc;
-    CUtensorMap mq, mk, mv, mdo;
+    CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
     const int64_t osb = (int64_t)TT * H * DD, osh = DD, ost = H * DD;
     int rc;
     if ((rc = encode_pair_map(&mq, q, B, H, strides[0], strides[1], strides[2]))) return rc;
     if ((rc = encode_pair_map(&mk, k, B, H, strides[3], strides[4], strides[5]))) return rc;
     if ((rc = encode_pair_map(&mv, v, B, H, strides[6], strides[7], strides[8]))) return rc;
     if ((rc = encode_pair_map(&mdo, dout, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdq, dq, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdk, dk, B, H, osb, osh, ost))) return rc;
+    if ((rc = encode_pair_map(&mdv, dv, B, H, osb, osh, ost))) return rc;
     Params p{};
     fill(p, B, H, scale, p_drop, seed, step, site, const_cast<float*>(lse), const_cast<uint32_t*>(keep));
     p.dq = (__nv_bfloat16*)dq, p.dk = (__nv_bfloat16*)dk, p.dv = (__nv_bfloat16*)dv;
     BF_CUDA_OK(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
-    bwd_kernel<<<grid, kThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, p);
+    bwd_kernel<<<grid, kBwdThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
     BF_LAUNCH_OK();
     return 0;
 }

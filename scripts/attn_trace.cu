@@ -5,6 +5,7 @@
 #include "../bayeformers_b200/csrc/bf_attention_tc.cu"
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 int main() {
@@ -28,8 +29,22 @@ int main() {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("cuda: %s\n", cudaGetErrorString(e)); return 1; }
     unsigned long long t[2 * 16 * 16];
+    if (getenv("TRACE_FWD")) {
+        cudaMemset(0, 0, 0);
+        bf_attention_tc_fwd(q, k, v, strides, B, H, 0.125f, 0.1f, 1, 2, 3, o, lse, keep, 0);
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(t, attn_tc::g_trace, sizeof(t));
+        const char* fn[] = {"top", "s_ready", "max", "bar1", "drained(prev)", "philox+exp", "bar2", "staged P"};
+        printf("forward, ALU thread 0 (cycles since the pair's top)\n");
+        for (int i = 1; i < 12; ++i) {
+            printf("pair %2d: top+%6llu", i, t[i * 16] - t[(i - 1) * 16]);
+            for (int s = 1; s < 8; ++s) printf(" %s %llu", fn[s], t[i * 16 + s] - t[i * 16]);
+            printf("\n");
+        }
+        return 0;
+    }
     cudaMemcpyFromSymbol(t, attn_tc::g_trace, sizeof(t));
-    const char* an[] = {"top", "bar1", "staged P,dS", "pass1(next)", "o_ready", "stored"};
+    const char* an[] = {"top", "bar1", "staged P,dS", "pass1(next)", "o_ready", "staged"};
     printf("ALU thread 0 (cycles since the pair's top; 'top' = since previous top)\n");
     for (int i = 1; i < 12; ++i) {
         printf("pair %2d:", i);
