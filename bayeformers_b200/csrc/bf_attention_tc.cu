@@ -8,6 +8,8 @@
 //               column quarter w / 4 -- 32 scores, or 16 output columns
 //   warp 16     TMA producer (one thread): q, k, v (and dO) tiles of the NEXT pair while this one is computed
 //   warp 17     MMA issuer (one thread)
+//   forward: warps 18..25 generate the Philox keep bits of the pairs ahead (they fill the issue slots the row workers
+//   leave idle; in the row workers the mask was 2/3 of all instructions); backward: warp 18 stores the gradient tiles
 // Outputs leave straight from registers: a thread holds 16 consecutive bf16 of an output row = one 32 B sector
 // (st.global.v8), so there is no staging tile, no store fence and no wait for a bulk store.
 //
@@ -40,12 +42,15 @@ constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;   // 512 row workers
 constexpr int kThreads = kRowThreads + 64;    // + producer warp (16) + MMA warp (17)
 constexpr int kBwdThreads = kThreads + 32;    // backward: + store warp (18)
+constexpr int kMaskThreads = 256;             // forward: + 8 mask warps (18..25), two threads per query row
+constexpr int kFwdThreads = kThreads + kMaskThreads;
+constexpr int KEEP_BYTES = 2 * TT * 16;       // forward: keep words of two pairs
 constexpr int FWD_BUF = 3 * TILE;      // q, k, v
 constexpr int BWD_BUF = 4 * TILE;      // q, k, v, dO
 constexpr int XCH_BYTES = 2 * 4 * TT * 4;  // two exchanged row statistics x four column quarters
 constexpr int BAR_BYTES = 256;
 constexpr int kFwdStages = 3;          // q, k, v tile buffers in flight (the kernel is bound by bytes in flight per SM)
-constexpr int FWD_SMEM = 1024 + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;  // + 2 x P_d (2 sub-tiles)
+constexpr int FWD_SMEM = 1024 + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + KEEP_BYTES + BAR_BYTES;  // + 2 x P_d (2 sub-tiles)
 constexpr int BWD_SMEM = 1024 + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES;         // + P_d, dS (2 sub-tiles each)
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -133,14 +138,15 @@ __device__ __forceinline__ Smem aligned_smem(uint8_t* raw) {
 // S, P_d and O are double buffered, so per pair the row workers only ever wait for S: while they do the softmax of
 // pair i the tensor core runs O(i-1) = P_d v and S(i+1) = q k^T; the output rows of pair i-1 are drained after the
 // softmax of pair i.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
     fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = aligned_smem(smem_raw);
     const uint32_t s_tiles = sm.base, s_p = sm.base + kFwdStages * FWD_BUF;
     float* const xch = reinterpret_cast<float*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE);  // [kind][quarter][row]
-    const uint32_t bars = s_p + 4 * TILE + XCH_BYTES;
+    uint4* const keep_s = reinterpret_cast<uint4*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES);  // [2][row]
+    const uint32_t bars = s_p + 4 * TILE + XCH_BYTES + KEEP_BYTES;
     auto full = [&](int st) { return bars + 8u * st; };                 // q, k, v tiles: kFwdStages deep
     auto empty = [&](int st) { return bars + 8u * (kFwdStages + st); };
     auto s_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + b); };  // S, P_d, O: double buffered (b = i % 2)
@@ -148,8 +154,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     auto p_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + 4 + b); };
     auto o_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + 6 + b); };
     auto o_free = [&](int b) { return bars + 8u * (2 * kFwdStages + 8 + b); };
-    const uint32_t tmem_slot = bars + 128;
-    volatile uint32_t* const tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + 128);
+    auto mask_ready = [&](int b) { return bars + 8u * (2 * kFwdStages + 10 + b); };
+    auto mask_free = [&](int b) { return bars + 8u * (2 * kFwdStages + 12 + b); };
+    const uint32_t tmem_slot = bars + 160;
+    volatile uint32_t* const tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(sm.gen + kFwdStages * FWD_BUF + 4 * TILE + XCH_BYTES + KEEP_BYTES + 160);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == kRowThreads) {
@@ -158,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int b = 0; b < 2; ++b) {
             mbar_init(s_ready(b), 1), mbar_init(s_free(b), kRowThreads);
             mbar_init(p_ready(b), kRowThreads), mbar_init(o_ready(b), 1), mbar_init(o_free(b), kRowThreads);
+            mbar_init(mask_ready(b), kMaskThreads), mbar_init(mask_free(b), kRowThreads);
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -211,10 +221,25 @@ __global__ void __launch_bounds__(kThreads, 1)
                 umma_commit(empty(i % kFwdStages));  // q, k, v of this pair are no longer read
             }
         }
+    } else if (warp >= kRowWarps + 2) {
+        // ===================== mask warps: the Philox keep bits of the pairs ahead, off the row workers' critical path
+        // (thread t: query row t / 2, key half t % 2: 8 calls -> two keep words (64 keys) -> shared + global memory)
+        if (p.thresh != 0u) {
+            const int t = threadIdx.x - (kRowThreads + 64), row = t >> 1, half = t & 1;
+            const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
+            for (int i = 0; i < n_mine; ++i) {
+                const int pair = blockIdx.x + i * gridDim.x, b = i & 1;
+                const uint32_t grow = (uint32_t)pair * TT + row;
+                const uint2 w = make_uint2(keep_word(p, grow, 2 * half, step), keep_word(p, grow, 2 * half + 1, step));
+                if (p.keep) *reinterpret_cast<uint2*>(p.keep + (size_t)grow * 4 + 2 * half) = w;
+                mbar_wait(mask_free(b), ((i >> 1) & 1) ^ 1u);
+                reinterpret_cast<uint2*>(keep_s + b * TT + row)[half] = w;
+                mbar_arrive(mask_ready(b));
+            }
+        }
     } else {
         const int q = 32 * (warp & 3) + lane, cq = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        const uint32_t step = p.step + (p.step_ptr ? __ldg(p.step_ptr) : 0u);
         float r_prev = 0.0f;
         // output row q of pair j, columns 16 cq .. +15: straight from TMEM to global memory
         auto drain = [&](int j, float r) {
@@ -268,8 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (cq == 0) p.lse[grow] = off + bf_lg2_approx(total);
             const float r_cur = p.inv_keep * bf_rcp_approx(total);
             if (p.thresh != 0u) {
-                const uint32_t w = keep_word(p, grow, cq, step);
-                if (p.keep) p.keep[(size_t)grow * 4 + cq] = w;
+                mbar_wait(mask_ready(b), (i >> 1) & 1);
+                const uint32_t w = reinterpret_cast<const uint32_t*>(keep_s + b * TT + q)[cq];
+                mbar_arrive(mask_free(b));
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (!(w & (1u << j))) s[j] = 0.0f;
@@ -565,7 +591,7 @@ int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64
     p.out = (__nv_bfloat16*)out;
     BF_CUDA_OK(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
-    fwd_kernel<<<grid, kThreads, FWD_SMEM, stream>>>(mq, mk, mv, p);
+    fwd_kernel<<<grid, kFwdThreads, FWD_SMEM, stream>>>(mq, mk, mv, p);
     BF_LAUNCH_OK();
     return 0;
 }

@@ -23,6 +23,15 @@ for stage in "$@"; do
     attn)
       timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "attention" 2>&1 | tail -8
       timeout -k 10 300 python scripts/bench_attention.py 2>&1 | tail -3 | tee gpurun_out/bench_attention.json ;;
+    gelu)
+      timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "gelu" 2>&1 | tail -4
+      timeout -k 10 300 python scripts/bench_gelu.py 2>&1 | tail -2 | tee gpurun_out/bench_gelu.json ;;
+    ncu_attn)
+      timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"fwd_kernel|bwd_kernel|attention_fwd|attention_bwd|sdpa|cudnn" -c 40 -f -o gpurun_out/prof_attn python scripts/profile_attention.py > gpurun_out/ncu_attn.log 2>&1; echo "rc $?"; tail -2 gpurun_out/ncu_attn.log
+      rm -f gpurun_out/r02_ncu_attention.md; python scripts/ncu_summary.py gpurun_out/prof_attn.ncu-rep gpurun_out/r02_ncu_attention.md; cut -c1-260 gpurun_out/r02_ncu_attention.md ;;
+    sanitize_attn)
+      timeout -k 10 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128 or attention_kernels and 150-2-128" > gpurun_out/sanitizer_attn_memcheck.log 2>&1; echo "memcheck rc $?"; tail -4 gpurun_out/sanitizer_attn_memcheck.log
+      timeout -k 10 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128" > gpurun_out/sanitizer_attn_racecheck.log 2>&1; echo "racecheck rc $?"; tail -4 gpurun_out/sanitizer_attn_racecheck.log ;;
     ab_links)
       for v in 0 1 0 1; do
         timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --gelu-links $v > gpurun_out/bench_links$v.json 2> gpurun_out/bench_links$v.err; echo "links=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_links$v.json | head -2
