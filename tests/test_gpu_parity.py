@@ -1334,6 +1334,46 @@ def test_attention_kernels_vs_float64(B, H, Tn, p):
     assert torch.equal(g1, bufs[0].grad)
 
 
+def test_attention_tcgen05_and_mma_sync_kernels_share_one_mask_and_agree():
+    """T = 128 has two kernel families (tcgen05: bf_attention_tc.cu, default; mma.sync: bf_attention.cu,
+    BF_OPT_ATTN_TC = 0).  The keep bits the tcgen05 forward stores for its backward are BIT-IDENTICAL to the mask
+    bf_attention_dropout_mask defines (the one the mma.sync kernels regenerate), both families read q / k / v in place
+    from a fused [B, T, 3 * H * 64] projection buffer (token stride 3 * H * 64), and their outputs and gradients agree to
+    bf16 rounding.  150 x 2 pairs > 148 blocks: the persistent loops wrap."""
+    lib = _lib.load()
+    B, H, Tn, Dh = 150, 2, 128, 64
+    gen = torch.Generator().manual_seed(77)
+    fused = (torch.randn(B, Tn, 3 * H * Dh, generator=gen) * 0.7).bfloat16().to(DEV).requires_grad_()
+    q, k, v = (fused[..., i * H * Dh:(i + 1) * H * Dh].view(B, Tn, H, Dh).transpose(1, 2) for i in range(3))
+    gout = torch.randn(B, Tn, H, Dh, generator=gen).bfloat16().to(DEV)
+    drop = ops.DropoutSpec(p=0.25, seed=0x1234567, site_id=9, step=11)
+    res = {}
+    try:
+        for tc in (1, 0):
+            lib.bf_set_option(_lib.BF_OPT_ATTN_TC, tc)
+            fused.grad = None
+            ops.enable_kernel_timing(True)
+            out = ops.AttentionFn.apply(q, k, v, Dh ** -0.5, drop)
+            saved = out.grad_fn.saved_tensors
+            out.backward(gout)
+            torch.cuda.synchronize()
+            ops.enable_kernel_timing(False)
+            res[tc] = (out.detach().float(), fused.grad.detach().float().clone(), saved[-1])
+    finally:
+        ops.enable_kernel_timing(False)
+        lib.bf_set_option(_lib.BF_OPT_ATTN_TC, 1)
+    # the stored keep words against the byte mask of the contract
+    keep_words = res[1][2]
+    assert keep_words is not None and keep_words.shape == (B, H, Tn, 4) and keep_words.dtype == torch.int32
+    bits = ((keep_words.view(B, H, Tn, 4, 1) >> torch.arange(32, device=DEV, dtype=torch.int32)) & 1).reshape(B, H, Tn, 128)
+    mask = ops.attention_dropout_mask(B, H, Tn, drop, DEV)
+    assert torch.equal(bits.to(torch.uint8), mask)
+    assert abs(float(mask.float().mean()) - 0.75) < 2e-3
+    # the two families against each other
+    assert rel_err(res[1][0].cpu().numpy(), res[0][0].cpu().numpy()) < 6e-3
+    assert rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 1.5e-2
+
+
 def test_attention_dropout_masks_are_independent_across_sites_and_steps():
     B, H, Tn = 4, 12, 128
     base = ops.DropoutSpec(p=0.1, seed=11, site_id=3, step=5)
