@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libbayeformers_b200.so")
 ABI_VERSION = 2
 BF_F32, BF_BF16 = 0, 1
 BF_PRIOR_MIXTURE, BF_PRIOR_GAUSSIAN, BF_PRIOR_NONE = 0, 1, 2
-BF_OPT_GEMM_2CTA, BF_OPT_WGRAD_2CTA, BF_OPT_RESLN_BWD_STAGED, BF_OPT_SK_PREFETCH, BF_OPT_ATTN_TC = 0, 1, 2, 3, 4
+BF_OPT_GEMM_2CTA, BF_OPT_WGRAD_2CTA, BF_OPT_RESLN_BWD_STAGED, BF_OPT_SK_PREFETCH, BF_OPT_ATTN_TC, BF_OPT_GELU_POLY = 0, 1, 2, 3, 4, 5
 
 class BfTensorDesc(ctypes.Structure):
     """`bf_tensor_desc` of include/bayeformers_b200.h (multi-tensor sample+KL)."""

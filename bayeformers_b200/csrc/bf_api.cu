@@ -23,7 +23,7 @@ namespace {
 // one counter per device (a process may drive several devices; the pointer is only valid on the device it lives on)
 const uint32_t* g_step_counter[64] = {nullptr};
 // tuning switches, set explicitly through bf_set_option (no environment reads inside the library)
-int32_t g_options[BF_OPT_COUNT] = {/*GEMM_2CTA*/ 1, /*WGRAD_2CTA*/ 1, /*RESLN_BWD_STAGED*/ 1, /*SK_PREFETCH*/ 1, /*ATTN_TC*/ 1};
+int32_t g_options[BF_OPT_COUNT] = {/*GEMM_2CTA*/ 1, /*WGRAD_2CTA*/ 1, /*RESLN_BWD_STAGED*/ 1, /*SK_PREFETCH*/ 1, /*ATTN_TC*/ 1, /*GELU_POLY*/ 1};
 }
 const uint32_t* bf_step_counter() {
     int dev = 0;

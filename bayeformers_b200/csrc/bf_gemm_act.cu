@@ -23,6 +23,15 @@
 namespace act {
 using namespace tc;
 
+// phase timeline of cluster 0's leader (scripts/gelu_trace.cu builds this file with -DBF_GELU_TRACE); compiled out otherwise
+#ifdef BF_GELU_TRACE
+__device__ unsigned long long g_gelu_trace[3 * 16 * 16];
+#define BF_GSTAMP(who, it, slot) \
+    do { if (blockIdx.x == 0 && (it) < 16) g_gelu_trace[((who) * 16 + (it)) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define BF_GSTAMP(who, it, slot) do { } while (0)
+#endif
+
 constexpr int BLOCK_M = 128, BLOCK_N = 256, LOAD_N = 128;
 constexpr int kStages = 5;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = LOAD_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -33,8 +42,9 @@ constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS;
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 2 * BLOCK_N;
 constexpr int OUT_BYTES = EPI_GROUPS * 2 * BOX_BYTES;  // (z, y) per group
-constexpr int BIAS_BYTES = BLOCK_N * 4;
-constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + OUT_BYTES + 256 + BIAS_BYTES;
+constexpr int HB_COLS = 32, HB_BYTES = BLOCK_M * HB_COLS * 2;  // half box of the epilogue staging: 64 B rows, 8 KiB
+static_assert(OUT_BYTES == EPI_GROUPS * 4 * HB_BYTES, "two (z, y) half-box sets per group");
+constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + OUT_BYTES + 256;
 
 struct Params {
     int64_t S, I, J, R;
@@ -89,6 +99,43 @@ __device__ __forceinline__ bf_f2 gelu_erf2(bf_f2 z2) {
     const bf_f2 erf2 = bf_pack2(copysignf(r0, x0), copysignf(r1, x1));
     return bf_mul2(z2, bf_fma2(erf2, bf_splat2(0.5f), bf_splat2(0.5f)));
 }
+// The two fused epilogues run under the board's power cap, where what a tile costs is the ENERGY of its instructions,
+// not their issue slots (halving the epilogue's stall cycles left the kernel time unchanged: the clock dropped instead).
+// So the epilogues use the cheapest evaluation that stays far inside bf16's rounding (2^-9 = 3.9e-3 relative): odd
+// polynomials in z on the clamped argument, FFMA2 only -- no MUFU, no |z| / copysign.
+//   Phi(z) - 1/2 = z Q(z^2),  |z| <= 4: degree 15, |abs err| <= 2.3e-5 in fp32 (least-maximum fit, Lawson iteration;
+//   scripts/fit_gelu_poly.py); beyond +-4 the clamped value is used: |Phi(z) - Phi(+-4)| <= 3.2e-5 (5.3e-5 in total).
+__device__ __forceinline__ bf_f2 gelu_poly2(bf_f2 z2) {
+    float z0, z1;
+    bf_unpack2(z2, z0, z1);
+    const bf_f2 c2 = bf_pack2(fminf(fmaxf(z0, -4.0f), 4.0f), fminf(fmaxf(z1, -4.0f), 4.0f));
+    const bf_f2 t2 = bf_mul2(c2, c2);
+    bf_f2 q2 = bf_fma2(bf_splat2(-1.5807585973e-09f), t2, bf_splat2(1.2170958112e-07f));
+    q2 = bf_fma2(q2, t2, bf_splat2(-4.1008329283e-06f));
+    q2 = bf_fma2(q2, t2, bf_splat2(8.0667023899e-05f));
+    q2 = bf_fma2(q2, t2, bf_splat2(-1.0482022168e-03f));
+    q2 = bf_fma2(q2, t2, bf_splat2(9.6648676795e-03f));
+    q2 = bf_fma2(q2, t2, bf_splat2(-6.6175370767e-02f));
+    q2 = bf_fma2(q2, t2, bf_splat2(3.9884750669e-01f));
+    return bf_mul2(z2, bf_fma2(c2, q2, bf_splat2(0.5f)));  // z Phi(z)
+}
+//   gelu'(z) - 1/2 = Phi(z) - 1/2 + z phi(z) = z R(z^2),  |z| <= 4: degree 17, |abs err| <= 9.1e-5 in fp32; beyond +-4
+//   the clamped value is used: |gelu'(z) - gelu'(+-4)| <= 5.4e-4 (gelu'(4) = 1.0005, gelu'(-4) = -0.0005).
+__device__ __forceinline__ bf_f2 gelu_grad_poly2(bf_f2 z2) {
+    float z0, z1;
+    bf_unpack2(z2, z0, z1);
+    const bf_f2 c2 = bf_pack2(fminf(fmaxf(z0, -4.0f), 4.0f), fminf(fmaxf(z1, -4.0f), 4.0f));
+    const bf_f2 t2 = bf_mul2(c2, c2);
+    bf_f2 r2 = bf_fma2(bf_splat2(9.795993143e-10f), t2, bf_splat2(-8.218767033e-08f));
+    r2 = bf_fma2(r2, t2, bf_splat2(3.028339970e-06f));
+    r2 = bf_fma2(r2, t2, bf_splat2(-6.495748858e-05f));
+    r2 = bf_fma2(r2, t2, bf_splat2(9.073261046e-04f));
+    r2 = bf_fma2(r2, t2, bf_splat2(-8.716319043e-03f));
+    r2 = bf_fma2(r2, t2, bf_splat2(5.845609926e-02f));
+    r2 = bf_fma2(r2, t2, bf_splat2(-2.648265343e-01f));
+    r2 = bf_fma2(r2, t2, bf_splat2(7.976095509e-01f));
+    return bf_fma2(c2, r2, bf_splat2(0.5f));
+}
 // d gelu / dz = Phi(z) + z * phi(z) on two values; phi shares its exponential with erf: exp(-z^2/2) = exp(-x^2), x = z/sqrt 2
 __device__ __forceinline__ bf_f2 gelu_erf_grad2(bf_f2 z2) {
     float x0, x1, d0, d1, q0, q1, r0, r1;
@@ -121,6 +168,7 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
     return u;
 }
 
+template <bool POLY>  // POLY: polynomial GELU (BF_OPT_GELU_POLY = 1, default), else the erf form
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     bayes_gemm2_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                             const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_y,
@@ -138,7 +186,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
     volatile uint32_t* const tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(out_gen + OUT_BYTES + 8 * (2 * kStages + 4));
-    float* const bias_gen = reinterpret_cast<float*>(out_gen + OUT_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -198,7 +245,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
+                BF_GSTAMP(0, iter, 0);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                BF_GSTAMP(0, iter, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int ks = 0; ks < p.k_steps; ++ks) {
@@ -214,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     if (++stage == kStages) stage = 0, phase ^= 1u;
                 }
                 umma_commit_2sm(tfull_bar(acc));
+                BF_GSTAMP(0, iter, 2);
             }
         }
     } else {
@@ -222,79 +272,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int grp = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const bool store_thread = ((warp - 2) & 3) == 0 && lane == 0;
-        const int et = threadIdx.x - 64;  // 0..255 over both groups
-        const uint32_t my_out = out_base + grp * 2 * BOX_BYTES;
-        uint8_t* const my_out_gen = out_gen + grp * 2 * BOX_BYTES;
-        int iter = 0;
+        // Staging: per group two sets of (z, y) HALF boxes [128 rows][32 columns] (64 B rows, 64B swizzle).  A half box
+        // is computed into one set while the TMA stores of the other set drain: the store thread only ever waits for a
+        // store issued a whole half box earlier (with one 64-column set per group the wait for the just-issued store
+        // was 20 % of the tile time), and one barrier per half box is enough.
+        const uint32_t grp_out = out_base + grp * 4 * HB_BYTES;
+        uint8_t* const grp_out_gen = out_gen + grp * 4 * HB_BYTES;
+        int iter = 0, n_hb = 0;
         for (int64_t L = cluster_id; L < n_items; L += n_clusters, ++iter) {
             const Item it = decode_item(p, L);
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int i0 = it.i_pair * (2 * BLOCK_M) + (int)rank * BLOCK_M, j0 = it.j_blk * BLOCK_N;
-            // stage this tile's 256 bias values once (all rows use the same ones)
-            named_bar_sync_dyn(3, EPI_WARPS * 32);  // both groups are done reading the previous tile's slice
-            {
-                const int64_t jc = (int64_t)j0 + et;
-                bias_gen[et] = jc < p.J ? __ldg(p.bias + (int64_t)it.s * p.J + jc) : 0.0f;
-            }
-            named_bar_sync_dyn(3, EPI_WARPS * 32);
+            if (store_thread) BF_GSTAMP(1 + grp, iter, 0);
             mbar_wait(tfull_bar(acc), acc_phase);
+            if (store_thread) BF_GSTAMP(1 + grp, iter, 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            int n_boxes = BOXES;
-            if ((int64_t)j0 + BLOCK_N > p.J) n_boxes = (int)((p.J - j0 + BOX_COLS - 1) / BOX_COLS);
-            int last_b = -1;
-            for (int b = grp; b < n_boxes; b += EPI_GROUPS) last_b = b;
-            if (last_b < 0) {
+            const int n_cols = (int64_t)j0 + BLOCK_N > p.J ? (int)(p.J - j0) : BLOCK_N;
+            // this group's half boxes: columns c0 = 64 b + 32 hh, b = grp, grp + 2; the last one releases the accumulator
+            int last_c0 = -1;
+            for (int k = 0; k < 4; ++k) {
+                const int c0 = (grp + 2 * (k >> 1)) * BOX_COLS + (k & 1) * HB_COLS;
+                if (c0 < n_cols) last_c0 = c0;
+            }
+            if (last_c0 < 0) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
             }
+            const float* const bias_row = p.bias + (int64_t)it.s * p.J + j0;
 #pragma unroll 1
-            for (int b = grp; b < n_boxes; b += EPI_GROUPS) {
-                uint32_t r[2][32];
-                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS), r[0]);
-                tmem_ld_32x32(t_acc + (uint32_t)(b * BOX_COLS + 32), r[1]);
-                if (store_thread) tma_store_wait_read<0>();  // this group's previous (z, y) stores have read smem
+            for (int k = 0; k < 4; ++k) {
+                const int c0 = (grp + 2 * (k >> 1)) * BOX_COLS + (k & 1) * HB_COLS;
+                if (c0 >= n_cols) continue;
+                uint32_t r[32];
+                tmem_ld_32x32(t_acc + (uint32_t)c0, r);
                 tmem_ld_wait();
-                if (b == last_b) {
+                if (store_thread) BF_GSTAMP(1 + grp, iter, 2 + 3 * k);
+                if (c0 == last_c0) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
                 }
-                named_bar_sync_dyn(1 + grp, 128);
-                uint8_t* const z_row = my_out_gen + row * 128;
-                uint8_t* const y_row = z_row + BOX_BYTES;
+                const int set = n_hb++ & 1;
+                uint8_t* const z_row = grp_out_gen + set * 2 * HB_BYTES + row * 64;
+                uint8_t* const y_row = z_row + HB_BYTES;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float4* bp = reinterpret_cast<const float4*>(bias_gen + b * BOX_COLS + h * 32);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {  // 8 columns = one 16-byte chunk of the bf16 row
-                        const float4 b0 = bp[2 * t], b1 = bp[2 * t + 1];
-                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        uint32_t zw[4], yw[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float z0, z1, y0, y1;
-                            bf_unpack2(bf_add2(bf_pack2(__uint_as_float(r[h][8 * t + 2 * e]), __uint_as_float(r[h][8 * t + 2 * e + 1])),
-                                               bf_pack2(bv[2 * e], bv[2 * e + 1])), z0, z1);
-                            const __nv_bfloat162 zb = __floats2bfloat162_rn(z0, z1);
-                            zw[e] = *reinterpret_cast<const uint32_t*>(&zb);
-                            // gelu of the bf16-ROUNDED pre-activation: backward recomputes gelu' from the stored z
-                            bf_unpack2(gelu_erf2(bf_pack2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u))), y0, y1);
-                            const __nv_bfloat162 yb = __floats2bfloat162_rn(y0, y1);
-                            yw[e] = *reinterpret_cast<const uint32_t*>(&yb);
-                        }
-                        const int ch = h * 4 + t;
-                        *reinterpret_cast<uint4*>(z_row + ((ch ^ (row & 7)) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
-                        *reinterpret_cast<uint4*>(y_row + ((ch ^ (row & 7)) << 4)) = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+                for (int t = 0; t < 4; ++t) {  // 8 columns = one 16-byte chunk of the bf16 row
+                    float bv[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                    if (c0 + 8 * t < n_cols) {  // N % 8 == 0: a chunk is wholly inside or wholly outside; same address in all lanes
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_row + c0 + 8 * t));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_row + c0 + 8 * t) + 1);
+                        bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w, bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
                     }
+                    uint32_t zw[4], yw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float z0, z1, y0, y1;
+                        bf_unpack2(bf_add2(bf_pack2(__uint_as_float(r[8 * t + 2 * e]), __uint_as_float(r[8 * t + 2 * e + 1])),
+                                           bf_pack2(bv[2 * e], bv[2 * e + 1])), z0, z1);
+                        const __nv_bfloat162 zb = __floats2bfloat162_rn(z0, z1);
+                        zw[e] = *reinterpret_cast<const uint32_t*>(&zb);
+                        // gelu of the bf16-ROUNDED pre-activation: backward recomputes gelu' from the stored z
+                        {
+                            const bf_f2 zr2 = bf_pack2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u));
+                            bf_unpack2(POLY ? gelu_poly2(zr2) : gelu_erf2(zr2), y0, y1);
+                        }
+                        const __nv_bfloat162 yb = __floats2bfloat162_rn(y0, y1);
+                        yw[e] = *reinterpret_cast<const uint32_t*>(&yb);
+                    }
+                    const int sw = (t ^ ((row >> 1) & 3)) << 4;  // 64B swizzle: 16 B chunk index ^ bits 7..8 of the offset
+                    *reinterpret_cast<uint4*>(z_row + sw) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+                    *reinterpret_cast<uint4*>(y_row + sw) = make_uint4(yw[0], yw[1], yw[2], yw[3]);
                 }
                 fence_proxy_async();
+                if (store_thread) BF_GSTAMP(1 + grp, iter, 3 + 3 * k);
+                if (store_thread) tma_store_wait_read<0>();  // the other set's stores (a half box ago) have read smem
+                if (store_thread) BF_GSTAMP(1 + grp, iter, 4 + 3 * k);
                 named_bar_sync_dyn(1 + grp, 128);
                 if (store_thread) {
-                    tma_store_3d(&map_z, my_out, j0 + b * BOX_COLS, i0, it.s);
-                    tma_store_3d(&map_y, my_out + BOX_BYTES, j0 + b * BOX_COLS, i0, it.s);
+                    const uint32_t st = grp_out + set * 2 * HB_BYTES;
+                    tma_store_3d(&map_z, st, j0 + c0, i0, it.s);
+                    tma_store_3d(&map_y, st + HB_BYTES, j0 + c0, i0, it.s);
                     tma_store_commit();
                 }
             }
@@ -329,6 +389,7 @@ constexpr int Z_BYTES = BOXES * BOX_BYTES;             // 4 boxes of the tile's 
 constexpr int OUT_BYTES = EPI_GROUPS * BOX_BYTES;      // one staging box per epilogue group
 constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + Z_BYTES + OUT_BYTES + 256;
 
+template <bool POLY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     bayes_gemm2_dgelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
@@ -519,7 +580,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             const bf_f2 g2 = bf_pack2(__uint_as_float(r[h][8 * t + 2 * e]), __uint_as_float(r[h][8 * t + 2 * e + 1]));
                             const bf_f2 z2 = bf_pack2(__uint_as_float(zw[e] << 16), __uint_as_float(zw[e] & 0xffff0000u));
                             float o0, o1;
-                            bf_unpack2(bf_mul2(g2, gelu_erf_grad2(z2)), o0, o1);
+                            bf_unpack2(bf_mul2(g2, POLY ? gelu_grad_poly2(z2) : gelu_erf_grad2(z2)), o0, o1);
                             const __nv_bfloat162 ob = __floats2bfloat162_rn(o0, o1);
                             ow[e] = *reinterpret_cast<const uint32_t*>(&ob);
                         }
@@ -663,17 +724,18 @@ extern "C" int bf_linear_fwd_gelu(const void* x, const void* w, const float* bia
     int rc;
     if ((rc = tc::encode_map(&ma, x, S, M, K, BLOCK_M))) return rc;
     if ((rc = tc::encode_map(&mb, w, S, N, K, LOAD_N))) return rc;
-    if ((rc = tc::encode_map(&mz, z, S, M, N, BLOCK_M))) return rc;
-    if ((rc = tc::encode_map(&my, y, S, M, N, BLOCK_M))) return rc;
+    if ((rc = tc::encode_map(&mz, z, S, M, N, BLOCK_M, false, HB_COLS))) return rc;  // 64 B half boxes, 64B swizzle
+    if ((rc = tc::encode_map(&my, y, S, M, N, BLOCK_M, false, HB_COLS))) return rc;
     Params p{};
     p.S = S, p.I = M, p.J = N, p.R = K;
     p.i_pairs = tc::cdiv(M, 2 * BLOCK_M), p.j_tiles = tc::cdiv(N, BLOCK_N), p.k_steps = tc::cdiv(K, tc::BLOCK_K);
     p.bias = bias;
-    BF_CUDA_OK(cudaFuncSetAttribute(bayes_gemm2_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    auto* const kernel = bf_option(BF_OPT_GELU_POLY) ? bayes_gemm2_gelu_kernel<true> : bayes_gemm2_gelu_kernel<false>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
     const int64_t pairs = bf_num_sms() / 2;
     const int grid = 2 * (int)(n_items < pairs ? n_items : pairs);
-    bayes_gemm2_gelu_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mz, my, p);
+    kernel<<<grid, kThreads, SMEM_BYTES, st>>>(ma, mb, mz, my, p);
     BF_LAUNCH_OK();
     return 0;
 }
@@ -730,12 +792,12 @@ extern "C" int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z
     act::Params p{};
     p.S = S, p.I = M, p.J = K, p.R = N;
     p.i_pairs = tc::cdiv(M, 2 * act::BLOCK_M), p.j_tiles = tc::cdiv(K, act::BLOCK_N), p.k_steps = tc::cdiv(N, tc::BLOCK_K);
-    BF_CUDA_OK(cudaFuncSetAttribute(dg::bayes_gemm2_dgelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    dg::SMEM_BYTES));
+    auto* const kernel = bf_option(BF_OPT_GELU_POLY) ? dg::bayes_gemm2_dgelu_kernel<true> : dg::bayes_gemm2_dgelu_kernel<false>;
+    BF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
     const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
     const int64_t pairs = bf_num_sms() / 2;
     const int grid = 2 * (int)(n_items < pairs ? n_items : pairs);
-    dg::bayes_gemm2_dgelu_kernel<<<grid, dg::kThreads, dg::SMEM_BYTES, st>>>(ma, mb, mz, mo, p);
+    kernel<<<grid, dg::kThreads, dg::SMEM_BYTES, st>>>(ma, mb, mz, mo, p);
     BF_LAUNCH_OK();
     return 0;
 }

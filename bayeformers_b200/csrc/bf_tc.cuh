@@ -245,9 +245,10 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // tensor [S][rows][cols] (cols contiguous) of bf16 or fp32; box = {128 B of columns, box_rows, 1},
-// 128B swizzle, zero fill on out-of-bounds loads, clipping on out-of-bounds stores
+// 128B swizzle, zero fill on out-of-bounds loads, clipping on out-of-bounds stores.
+// box_cols = 64 B worth of columns (32 bf16) selects half-width boxes with the 64B swizzle (epilogue staging in halves).
 inline int encode_map(CUtensorMap* m, const void* base, int64_t S, int64_t rows, int64_t cols, int box_rows,
-                      bool fp32 = false) {
+                      bool fp32 = false, int box_cols = 0) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         bf_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -256,11 +257,16 @@ inline int encode_map(CUtensorMap* m, const void* base, int64_t S, int64_t rows,
     const cuuint64_t esz = fp32 ? 4 : 2;
     const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)S};
     const cuuint64_t strides[2] = {(cuuint64_t)cols * esz, (cuuint64_t)rows * (cuuint64_t)cols * esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1};
+    const bool half = box_cols != 0 && (cuuint64_t)box_cols * esz == 64;
+    if (box_cols != 0 && !half) {
+        bf_set_error("encode_map: box_cols must be 0 (128 B rows) or 64 B worth of columns");
+        return BF_ERR_DRIVER;
+    }
+    const cuuint32_t box[3] = {(cuuint32_t)((half ? 64 : 128) / esz), (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         bf_set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));

@@ -83,6 +83,9 @@ def parse():
                     help="1 (default): the host model's short-sequence attention (T <= 128) runs on the native kernels "
                          "(tcgen05 at T = 128: 1.2 ms per BERT-base layer fwd+bwd against 2.2 ms of cuDNN's fused "
                          "attention); 0: torch SDPA")
+    ap.add_argument("--gelu-poly", type=int, default=1,
+                    help="1 (default): the fused GELU / GELU' epilogues evaluate odd polynomials (|err| <= 1e-4 / 6e-4, "
+                         "inside bf16 rounding); 0: the erf forms (bf_set_option(BF_OPT_GELU_POLY))")
     ap.add_argument("--sigma-cache", type=int, default=1,
                     help="ClipAdamW writes softplus(updated rho) next to its update; the sampling kernel reads it")
     ap.add_argument("--gelu-links", type=int, default=1,
@@ -399,6 +402,8 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     model, cfg = wl.build()
     bf.manual_seed(1234)
     bf.runtime.enable_gelu_links(bool(args.gelu_links))
+    from bayeformers_b200 import _lib as _bf_lib
+    _bf_lib.load().bf_set_option(_bf_lib.BF_OPT_GELU_POLY, int(args.gelu_poly))
     layers = bnn.TORCH2BAYE_ALL if args.config == "bert_large" else None
     bm = bf.to_bayesian(model, delta=0.05, freeze=(args.config != "mlp"), gemm_dtype=gemm, kl_grad=bool(args.kl_grad),
                         layers=layers)

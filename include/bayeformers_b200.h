@@ -70,7 +70,9 @@ int bf_set_step_counter(const uint32_t* device_counter);
 #define BF_OPT_RESLN_BWD_STAGED 2  /* 1 (default): shared-memory-staged resln backward, 0: register prefetch */
 #define BF_OPT_SK_PREFETCH 3       /* multi-tensor sample+KL prefetch: 0 none, 1 L1 (default), 2 L2 */
 #define BF_OPT_ATTN_TC 4          /* T == 128 attention: 1 (default) tcgen05 kernels, 0 the mma.sync kernels */
-#define BF_OPT_COUNT 5
+#define BF_OPT_GELU_POLY 5        /* fused GELU / GELU' epilogues: 1 (default) odd polynomials on FFMA2 (|err| <= 1e-4 /
+                                    6e-4, far inside bf16 rounding), 0 the erf forms (A&S 7.1.26 / 7.1.28) */
+#define BF_OPT_COUNT 6
 int bf_set_option(int32_t option, int32_t value);
 int bf_get_option(int32_t option);
 

@@ -39,6 +39,10 @@ def timed(fn, reps=10):
 
 
 out = {}
+lib.bf_set_option(_lib.BF_OPT_GELU_POLY, 0)
+out["fwd_gelu_erf_ms"] = timed(lambda: lib.bf_linear_fwd_gelu(x.data_ptr(), w_up.data_ptr(), bias.data_ptr(), z.data_ptr(), y.data_ptr(), S, M, F, H, st))
+out["dgrad_gelu_erf_ms"] = timed(lambda: lib.bf_linear_dgrad_gelu(gy.data_ptr(), w_dn.data_ptr(), z.data_ptr(), gz.data_ptr(), S, M, H, F, st))
+lib.bf_set_option(_lib.BF_OPT_GELU_POLY, 1)
 out["fwd_plain_ms"] = timed(lambda: lib.bf_linear_fwd(x.data_ptr(), w_up.data_ptr(), bias.data_ptr(), z.data_ptr(), S, M, F, H, BF_BF16, BF_BF16, st))
 out["fwd_gelu_ms"] = timed(lambda: lib.bf_linear_fwd_gelu(x.data_ptr(), w_up.data_ptr(), bias.data_ptr(), z.data_ptr(), y.data_ptr(), S, M, F, H, st))
 out["dgrad_plain_ms"] = timed(lambda: lib.bf_linear_dgrad(gy.data_ptr(), w_dn.data_ptr(), gz.data_ptr(), S, M, H, F, BF_BF16, BF_BF16, st))
