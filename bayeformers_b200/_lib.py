@@ -73,6 +73,9 @@ SIGNATURES = {
                                      c_int64, c_void_p]),
     "bf_linear_dgrad_gelu_supported": (c_int32, [c_int64, c_int64, c_int64, c_int64]),
     "bf_linear_dgrad_gelu": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "bf_linear_dgrad_gelu_bias_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_linear_dgrad_gelu_bias": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                            c_int64, c_int64, c_void_p]),
     "bf_gelu_bwd_bias_grad_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "bf_gelu_bwd_bias_grad": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                         c_void_p]),

@@ -50,6 +50,9 @@ struct Params {
     int64_t S, I, J, R;
     int i_pairs, j_tiles, k_steps;
     const float* bias;  // [S][J], required
+    // dgelu only: per-block partial column sums of the result, [gridDim.x][S][J] fp32 (null: not wanted).  Every block
+    // adds the column sums of ITS tiles, in its fixed tile order, to its own row; a second pass adds the rows in order.
+    float* col_partial;
 };
 struct Item {
     int s, i_pair, j_blk;
@@ -389,7 +392,7 @@ constexpr int Z_BYTES = BOXES * BOX_BYTES;             // 4 boxes of the tile's 
 constexpr int OUT_BYTES = EPI_GROUPS * BOX_BYTES;      // one staging box per epilogue group
 constexpr int SMEM_BYTES = 1024 + kStages * STAGE_BYTES + Z_BYTES + OUT_BYTES + 256;
 
-template <bool POLY>
+template <bool POLY, bool COLSUM>  // COLSUM: also emit the column sums of the result (the producer's bias gradient)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     bayes_gemm2_dgelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
@@ -595,6 +598,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     tma_store_3d(&map_out, my_out, j0 + b * BOX_COLS, i0, it.s);
                     tma_store_commit();
                 }
+                if (COLSUM) {
+                    // column sums of the staged (bf16-rounded) box: warp w of the group takes columns 16 w .. +15 (8 words
+                    // of a row), lane l word l % 8 of the rows r = l / 8 (mod 4); rows beyond M were computed from
+                    // zero-filled operands and z, so they hold zeros.  The next box's barrier comes after these reads.
+                    const int gw = (warp - 3) & 3, wd = lane & 7;
+                    const uint8_t* const base = out_gen + grp * BOX_BYTES + (wd & 3) * 4;  // word wd % 4 of 16 B chunk 2 gw + wd / 4
+                    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int r_ = 4 * rr + (lane >> 3);
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(base + r_ * 128 + (((gw * 2 + (wd >> 2)) ^ (r_ & 7)) << 4));
+                        s0 += __uint_as_float(v << 16);
+                        s1 += __uint_as_float(v & 0xffff0000u);
+                    }
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, 8), s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, 16), s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    const int64_t col = (int64_t)j0 + b * BOX_COLS + gw * 16 + wd * 2;
+                    if (lane < 8 && col < p.J) {  // J % 8 == 0: the pair is inside or outside together
+                        float2* const dst = reinterpret_cast<float2*>(p.col_partial + ((int64_t)blockIdx.x * p.S + it.s) * p.J + col);
+                        float2 a = *dst;
+                        a.x += s0, a.y += s1;
+                        *dst = a;
+                    }
+                }
             }
         }
         if (store_thread) tma_store_wait_all();
@@ -775,11 +802,35 @@ extern "C" int bf_linear_dgrad_gelu_supported(int64_t S, int64_t M, int64_t N, i
     return bf_linear_fwd_gelu_supported(S, M, K, N);
 }
 
-// gz[s] = (gy[s] . w[s]) o gelu'(z[s])   gy [S,M,N], w [S,N,K], z / gz [S,M,K], all bf16
-extern "C" int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z, void* gz, int64_t S, int64_t M,
-                                    int64_t N, int64_t K, void* stream) {
+namespace act {
+// dbias[i] = sum over the per-block rows of the partial column sums, in block order (deterministic)
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int64_t n, int blocks) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.0f;
+    for (int c = 0; c < blocks; ++c) acc += partial[(int64_t)c * n + i];
+    out[i] = acc;
+}
+static int dgelu_grid(int64_t S, int64_t M, int64_t K) {
+    const int64_t n_items = S * tc::cdiv(M, 2 * BLOCK_M) * tc::cdiv(K, BLOCK_N);
+    const int64_t pairs = bf_num_sms() / 2;
+    return 2 * (int)(n_items < pairs ? n_items : pairs);
+}
+}  // namespace act
+
+extern "C" int64_t bf_linear_dgrad_gelu_bias_workspace_bytes(int64_t S, int64_t M, int64_t K) {
+    S = S < 1 ? 1 : S, M = M < 1 ? 1 : M, K = K < 1 ? 1 : K;
+    return (int64_t)act::dgelu_grid(S, M, K) * S * K * 4;
+}
+
+// gz[s] = (gy[s] . w[s]) o gelu'(z[s])   gy [S,M,N], w [S,N,K], z / gz [S,M,K], all bf16;
+// dbias (optional, with its workspace): dbias[s][k] = sum_m gz[s][m][k], fp32 -- the bias gradient of the layer that made z
+extern "C" int bf_linear_dgrad_gelu_bias(const void* gy, const void* w, const void* z, void* gz, float* dbias, void* workspace,
+                                         int64_t S, int64_t M, int64_t N, int64_t K, void* stream) {
     namespace dg = act::dgelu;
     BF_CHECK_ARG(gy && w && z && gz, "null pointer");
+    BF_CHECK_ARG(!dbias || workspace, "the bias gradient needs its workspace (bf_linear_dgrad_gelu_bias_workspace_bytes)");
     BF_CHECK_ARG(S >= 1 && M >= 1 && N >= 1 && K >= 1, "S, M, N, K must be >= 1");
     BF_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "bf16 path needs K % 8 == 0 and N % 8 == 0");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -792,12 +843,26 @@ extern "C" int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z
     act::Params p{};
     p.S = S, p.I = M, p.J = K, p.R = N;
     p.i_pairs = tc::cdiv(M, 2 * act::BLOCK_M), p.j_tiles = tc::cdiv(K, act::BLOCK_N), p.k_steps = tc::cdiv(N, tc::BLOCK_K);
-    auto* const kernel = bf_option(BF_OPT_GELU_POLY) ? dg::bayes_gemm2_dgelu_kernel<true> : dg::bayes_gemm2_dgelu_kernel<false>;
+    const int grid = act::dgelu_grid(S, M, K);
+    if (dbias) {
+        p.col_partial = static_cast<float*>(workspace);
+        BF_CUDA_OK(cudaMemsetAsync(workspace, 0, (size_t)grid * S * K * 4, st));
+    }
+    const bool poly = bf_option(BF_OPT_GELU_POLY) != 0;
+    auto* const kernel = dbias ? (poly ? dg::bayes_gemm2_dgelu_kernel<true, true> : dg::bayes_gemm2_dgelu_kernel<false, true>)
+                               : (poly ? dg::bayes_gemm2_dgelu_kernel<true, false> : dg::bayes_gemm2_dgelu_kernel<false, false>);
     BF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
-    const int64_t n_items = p.S * p.i_pairs * p.j_tiles;
-    const int64_t pairs = bf_num_sms() / 2;
-    const int grid = 2 * (int)(n_items < pairs ? n_items : pairs);
     kernel<<<grid, dg::kThreads, dg::SMEM_BYTES, st>>>(ma, mb, mz, mo, p);
     BF_LAUNCH_OK();
+    if (dbias) {
+        const int64_t n = S * K;
+        act::colsum_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.col_partial, dbias, n, grid);
+        BF_LAUNCH_OK();
+    }
     return 0;
+}
+
+extern "C" int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z, void* gz, int64_t S, int64_t M,
+                                    int64_t N, int64_t K, void* stream) {
+    return bf_linear_dgrad_gelu_bias(gy, w, z, gz, nullptr, nullptr, S, M, N, K, stream);
 }

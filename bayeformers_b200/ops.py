@@ -606,9 +606,12 @@ class BayesLinear(torch.autograd.Function):
         if have_gy:
             gyc = gy.reshape(S, M, N).to(cdt).contiguous()
             if z is not None and fused_act and link_out is not None and link_out.done:
-                # the consumer's dgrad already multiplied by gelu'(z) (bf_linear_dgrad_gelu): gy IS the gradient of z;
-                # only the bias gradient's column sums are left (db is None -> bf_bias_grad below)
+                # the consumer's dgrad already multiplied by gelu'(z) (bf_linear_dgrad_gelu_bias): gy IS the gradient of
+                # z, and its column sums -- this layer's bias gradient -- came out of the same epilogue
                 link_out.done = False
+                if link_out.bias_grad is not None and tuple(link_out.bias_grad.shape) == (S, N):
+                    db = link_out.bias_grad
+                link_out.bias_grad = None
             elif z is not None and fused_act:
                 # gz = gy * gelu'(z) and the bias gradient's column sums in ONE pass over gy
                 gz = torch.empty_like(gyc)
@@ -635,12 +638,14 @@ class BayesLinear(torch.autograd.Function):
                 # x = gelu(z) of a fused layer: dx o gelu'(z) straight from the dgrad epilogue, handed on as "dx"
                 link = spec.gelu_in
                 gz_in = torch.empty((S, M, K), dtype=torch.bfloat16, device=dev)
-                rc = _timed("gemm_dgrad_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_dgrad_gelu(
-                    _ptr(gyc), _ptr(W), _ptr(link.z), _ptr(gz_in), S, M, N, K, st))
-                _lib.check(rc, "bf_linear_dgrad_gelu")
-                stats["launches"] += 1
+                db_in = torch.empty((S, K), dtype=torch.float32, device=dev)  # bias gradient of the layer that made z
+                cws = _workspace("dgrad_gelu_colsum", dev, lib.bf_linear_dgrad_gelu_bias_workspace_bytes(S, M, K))
+                rc = _timed("gemm_dgrad_tc", 2.0 * S * M * N * K, dev, lambda: lib.bf_linear_dgrad_gelu_bias(
+                    _ptr(gyc), _ptr(W), _ptr(link.z), _ptr(gz_in), _ptr(db_in), _ptr(cws), S, M, N, K, st))
+                _lib.check(rc, "bf_linear_dgrad_gelu_bias")
+                stats["launches"] += 2  # the contraction and the fixed-order reduction of its per-block column sums
                 g_x = gz_in.view(x_shape)
-                link.done, link.buffer, link.z = True, g_x, None
+                link.done, link.buffer, link.z, link.bias_grad = True, g_x, None, db_in
             elif ctx.needs_input_grad[0]:
                 dx_dtype = x_dtype if (use_tc and x_dtype in (torch.float32, torch.bfloat16)) else torch.float32
                 sink = spec.sink

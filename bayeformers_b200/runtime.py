@@ -119,10 +119,11 @@ class GeluLink:
     a; `done` tells the producer's backward that what arrives is already the gradient of z, so it skips its own GELU'
     pass.  Valid when a has no other consumer (HF BertIntermediate -> BertOutput): a tensor hook on a checks that the
     gradient autograd finally delivers is exactly the buffer the fused kernel wrote, and raises otherwise."""
-    __slots__ = ("z", "done", "buffer")
+    __slots__ = ("z", "done", "buffer", "bias_grad")
 
     def __init__(self, z: torch.Tensor) -> None:
         self.z, self.done, self.buffer = z, False, None
+        self.bias_grad = None  # [S, N] fp32 column sums of the gradient of z, when the consumer's dgrad kernel emitted them
 
     def check(self, grad: torch.Tensor) -> None:
         if self.done and (grad is None or self.buffer is None or grad.data_ptr() != self.buffer.data_ptr()):

@@ -242,6 +242,12 @@ int bf_linear_fwd_gelu(const void* x, const void* w, const float* bias, void* z,
 int bf_linear_dgrad_gelu_supported(int64_t S, int64_t M, int64_t N, int64_t K);
 int bf_linear_dgrad_gelu(const void* gy, const void* w, const void* z, void* gz, int64_t S, int64_t M, int64_t N,
                          int64_t K, void* stream);
+/* the same with the column sums of gz -- the bias gradient of the layer that produced z, dbias [S, K] fp32 -- taken from
+ * the staged result boxes in the epilogue (per-block partial rows in `workspace`, added in block order by a second small
+ * pass: deterministic), instead of a separate pass over gz.  dbias == NULL: plain bf_linear_dgrad_gelu. */
+int64_t bf_linear_dgrad_gelu_bias_workspace_bytes(int64_t S, int64_t M, int64_t K);
+int bf_linear_dgrad_gelu_bias(const void* gy, const void* w, const void* z, void* gz, float* dbias, void* workspace,
+                              int64_t S, int64_t M, int64_t N, int64_t K, void* stream);
 int64_t bf_gelu_bwd_bias_grad_workspace_bytes(int64_t S, int64_t M, int64_t N);
 int bf_gelu_bwd_bias_grad(const void* gy, const void* z, void* gz, float* db, int64_t S, int64_t M, int64_t N,
                           void* workspace, void* stream);

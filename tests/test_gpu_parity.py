@@ -1233,6 +1233,19 @@ def test_dgrad_gelu_kernel_vs_float64(S, M, N, K):
     dx = torch.empty(S, M, K, dtype=torch.bfloat16, device=DEV)
     _lib.check(lib.bf_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), S, M, N, K, BF_BF16, BF_BF16, st), "dgrad")
     assert rel_err(gz.float().cpu().numpy(), (dx.double() * dgelu).cpu().numpy()) < 6e-3
+    # the same launch with the column sums of gz from its epilogue (per-block partial rows + fixed-order reduction):
+    # identical gz, sums of the bf16-ROUNDED values it stored, bit-identical from run to run
+    gz2, db = torch.empty_like(gz), torch.full((S, K), float("nan"), device=DEV)
+    ws = torch.zeros(int(lib.bf_linear_dgrad_gelu_bias_workspace_bytes(S, M, K)), dtype=torch.uint8, device=DEV)
+    for rep in range(2):
+        _lib.check(lib.bf_linear_dgrad_gelu_bias(gy.data_ptr(), w.data_ptr(), z.data_ptr(), gz2.data_ptr(), db.data_ptr(),
+                                                 ws.data_ptr(), S, M, N, K, st), "dgrad_gelu_bias")
+        torch.cuda.synchronize()
+        if rep == 0:
+            db0 = db.clone()
+    assert torch.equal(gz2, gz) and torch.equal(db, db0)
+    want_db = gz.double().sum(1)
+    assert rel_err(db.cpu().numpy(), want_db.cpu().numpy()) < 1e-5
 
 
 def test_ffn_block_with_and_without_gelu_link():
@@ -1269,6 +1282,9 @@ def test_ffn_block_with_and_without_gelu_link():
             ran = ops.kernel_timing_summary()
             ops.enable_kernel_timing(False)
             assert ("gelu_bwd_bias_grad" in ran) == (not linked)
+            # linked: the up layer's bias gradient came out of the down layer's dgrad epilogue -- the only separate
+            # bias-gradient pass left is the down layer's own
+            assert ran["bias_grad"]["calls"] == 1
             results[linked] = (y.detach().clone(), xa.grad.clone(), a_up.weight.rho.grad.clone(), a_up.bias.rho.grad.clone(),
                                a_down.weight.rho.grad.clone())
         finally:
