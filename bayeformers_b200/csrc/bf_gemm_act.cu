@@ -616,10 +616,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     s0 += __shfl_xor_sync(0xffffffffu, s0, 16), s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
                     const int64_t col = (int64_t)j0 + b * BOX_COLS + gw * 16 + wd * 2;
                     if (lane < 8 && col < p.J) {  // J % 8 == 0: the pair is inside or outside together
-                        float2* const dst = reinterpret_cast<float2*>(p.col_partial + ((int64_t)blockIdx.x * p.S + it.s) * p.J + col);
-                        float2 a = *dst;
-                        a.x += s0, a.y += s1;
-                        *dst = a;
+                        // fire-and-forget adds (a load + add + store would put an L2 round trip on the epilogue's critical
+                        // path); this thread is the only one that ever touches these two addresses and its adds to one
+                        // address are applied in program order, so the sum is still deterministic
+                        float* const dst = p.col_partial + ((int64_t)blockIdx.x * p.S + it.s) * p.J + col;
+                        atomicAdd(dst, s0);
+                        atomicAdd(dst + 1, s1);
                     }
                 }
             }
