@@ -66,7 +66,8 @@ def _is_exact_gelu(fn) -> bool:
 
 
 def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool = True,
-                     fuse_residual: bool = False, grad_sinks: bool = False, attention: bool = False) -> tnn.Module:
+                     fuse_residual: bool = False, grad_sinks: bool = False, attention: bool = False,
+                     attention_bias_grads: bool = False) -> tnn.Module:
     """Opt-in plumbing for the frequentist code AROUND the Bayesian layers of a host model.  In place; parameters,
     state_dict names and numerics (to rounding) are unchanged.
 
@@ -87,7 +88,11 @@ def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool 
                raises otherwise (runtime.GradSink).
     attention  transformers models: route self-attention over short sequences (bf16, no mask, T <= 128, head width 64)
                through the native whole-sequence kernels (nn/layers/attention.py); other cases keep torch's SDPA.  The
-               attention dropout mask then comes from the Philox counter stream."""
+               attention dropout mask then comes from the Philox counter stream.
+    attention_bias_grads  with `attention`: the T = 128 backward kernel also emits the bias gradients of the Bayesian query /
+               key / value projections (column sums of dq, dk, dv) and those layers skip their own pass.  Off by default:
+               measured at the bench shape the two store warps' extra instructions cost the backward kernel what the
+               three skipped passes save (attention_bwd 10.0 -> 13.2 ms against 3.0 ms of bias_grad per step)."""
     from .nn.layers.fused import fuse_output_block_, is_output_block
     from .nn.layers.layernorm import HostLayerNorm
     from .nn.layers.linear import Linear
@@ -96,7 +101,7 @@ def accelerate_host_(model: tnn.Module, layernorm: bool = True, fuse_gelu: bool 
         raise ValueError("grad_sinks=True needs fuse_residual=True")
     if attention:
         from .nn.layers.attention import use_native_attention_
-        use_native_attention_(model)
+        use_native_attention_(model, bias_grads=attention_bias_grads)
     if grad_sinks:
         runtime.enable_grad_sinks(True)  # process-wide; runtime.enable_grad_sinks(False) switches it off again
     if fuse_residual:

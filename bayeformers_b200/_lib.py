@@ -118,6 +118,10 @@ SIGNATURES = {
     "bf_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int64, c_int64, c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
+    "bf_attention_bias_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "bf_attention_bwd_bias": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                        c_int64, c_int64, c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "bf_attention_dropout_mask": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint32, c_uint32,
                                             c_void_p]),
 }

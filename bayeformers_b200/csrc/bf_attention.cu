@@ -490,7 +490,9 @@ int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64
                         cudaStream_t stream);
 int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides, const float* lse,
                         const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
-                        uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream);
+                        uint32_t site, void* dq, void* dk, void* dv, float* dbias, void* workspace, int64_t S,
+                        cudaStream_t stream);
+int64_t bf_attention_tc_bias_workspace_bytes(int64_t B, int64_t H, int64_t S);
 
 extern "C" int bf_attention_supported(int64_t T, int64_t head_dim) {
     return (head_dim == attn::D && T >= 16 && T <= attn::TMAX && T % 16 == 0) ? 1 : 0;
@@ -522,19 +524,22 @@ extern "C" int bf_attention_fwd(const void* q, const void* k, const void* v, con
     return 0;
 }
 
-extern "C" int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
+extern "C" int bf_attention_bwd_bias(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
                                 const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T,
                                 float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk,
-                                void* dv, void* stream) {
+                                void* dv, float* dbias, void* workspace, int64_t S, void* stream) {
     BF_CHECK_ARG(dout && q && k && v && strides && lse && dq && dk && dv, "null pointer");
     BF_ATTN_CHECK();
     for (int i = 0; i < 9; ++i) BF_CHECK_ARG(strides[i] % 8 == 0, "strides must be multiples of 8 elements (16 B)");
     BF_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                    reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
                    reinterpret_cast<uintptr_t>(dv)) & 15u) == 0, "buffers must be 16 B aligned");
-    if (T == attn::TMAX && bf_option(BF_OPT_ATTN_TC) && (keep || p_drop == 0.0f))
-        return bf_attention_tc_bwd(dout, q, k, v, strides, lse, keep, B, H, scale, p_drop, seed, step, site, dq, dk, dv,
-                                   reinterpret_cast<cudaStream_t>(stream));
+    const bool tc_path = T == attn::TMAX && bf_option(BF_OPT_ATTN_TC) && (keep || p_drop == 0.0f);
+    BF_CHECK_ARG(!dbias || (tc_path && workspace && S >= 1 && B % S == 0),
+                 "the fused q / k / v bias gradients need the tcgen05 path (T == 128, keep bits), a workspace and B % S == 0");
+    if (tc_path)
+        return bf_attention_tc_bwd(dout, q, k, v, strides, lse, keep, B, H, scale, p_drop, seed, step, site, dq, dk, dv, dbias,
+                                   workspace, S, reinterpret_cast<cudaStream_t>(stream));
     attn::Params p{};
     p.q = (const __nv_bfloat16*)q, p.k = (const __nv_bfloat16*)k, p.v = (const __nv_bfloat16*)v;
     p.o = (const __nv_bfloat16*)out, p.dout = (const __nv_bfloat16*)dout, p.lse = const_cast<float*>(lse);
@@ -549,6 +554,18 @@ extern "C" int bf_attention_bwd(const void* dout, const void* q, const void* k, 
     kernel<<<(int)(pairs < cap ? pairs : cap), attn::kBwdThreads, attn::BWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     BF_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
+                                const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T,
+                                float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk,
+                                void* dv, void* stream) {
+    return bf_attention_bwd_bias(dout, q, k, v, strides, out, lse, keep, B, H, T, scale, p_drop, seed, step, site, dq, dk, dv,
+                                 nullptr, nullptr, 1, stream);
+}
+
+extern "C" int64_t bf_attention_bias_workspace_bytes(int64_t B, int64_t H, int64_t S) {
+    return bf_attention_tc_bias_workspace_bytes(B < 1 ? 1 : B, H < 1 ? 1 : H, S < 1 ? 1 : S);
 }
 
 extern "C" int bf_attention_dropout_mask(uint8_t* out, int64_t B, int64_t H, int64_t T, float p_drop, uint64_t seed,

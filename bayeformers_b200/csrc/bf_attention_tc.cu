@@ -41,7 +41,7 @@ constexpr int TILE = TT * DD * 2;      // one [128][64] bf16 tile, 128 B rows, 1
 constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;   // 512 row workers
 constexpr int kThreads = kRowThreads + 64;    // + producer warp (16) + MMA warp (17)
-constexpr int kBwdThreads = kThreads + 32;    // backward: + store warp (18)
+constexpr int kBwdThreads = kThreads + 64;    // backward: + store / column-sum warps (18, 19)
 constexpr int kMaskThreads = 256;             // forward: + 8 mask warps (18..25), two threads per query row
 constexpr int kFwdThreads = kThreads + kMaskThreads;
 constexpr int KEEP_BYTES = 2 * TT * 16;       // forward: keep words of two pairs
@@ -59,6 +59,10 @@ struct Params {
     float* lse;       // [B, heads, 128] base-2 log-sum-exp of the scaled scores
     uint32_t* keep;   // [B, heads, 128, 4] keep bits of the 128 keys of a row (bit k % 32 of word k / 32), or null
     int H, total;     // heads, B * heads
+    // backward only: per-block partial column sums of dq, dk, dv -- the bias gradients of the q / k / v projections --
+    // [gridDim.x][3][S][heads * 64] fp32 (null: not wanted); seqs_per_sample = B / S (the batch is S samples folded)
+    float* col_partial;
+    int S, seqs_per_sample;
     float scale, scale_log2e, inv_keep;
     uint32_t thresh, k0, k1, step, site;
     const uint32_t* step_ptr;
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         tma_prefetch_desc(&map_dq), tma_prefetch_desc(&map_dk), tma_prefetch_desc(&map_dv);
         for (int b = 0; b < 2; ++b) mbar_init(full(b), 1), mbar_init(empty(b), 1);
         mbar_init(s_ready, 1), mbar_init(s_free, kRowThreads), mbar_init(p_ready, kRowThreads), mbar_init(o_ready, 1);
-        mbar_init(o_free, kRowThreads), mbar_init(staged, kRowThreads), mbar_init(stage_free, 1);
+        mbar_init(o_free, kRowThreads), mbar_init(staged, kRowThreads), mbar_init(stage_free, 2);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -418,21 +422,61 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
                 BF_STAMP(1, 6);
             }
         }
-    } else if (warp == kRowWarps + 2) {
-        // ===================== store warp: the staged gradient tiles (where P_d / dS were) -> global memory =====================
-        if (lane == 0) {
-            for (int i = 0; i < n_mine; ++i) {
-                const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
-                mbar_wait(staged, i & 1);
+    } else if (warp >= kRowWarps + 2) {
+        // ===================== store warps: the staged gradient tiles (where P_d / dS were) -> global memory; on the way
+        // (optional) their column sums = the bias gradients of the q / k / v projections: warp wb takes columns
+        // 32 wb .. +31 of the three tiles (lane: word l % 16, rows r and r + 4 by l / 16 -- conflict-free under the
+        // swizzle), adds them to this block's own partial row with fire-and-forget adds (one thread per address, adds in
+        // program order: deterministic); a second small pass adds the rows in block order.
+        const int wb = warp - (kRowWarps + 2);
+        // lane: 16 B chunk 4 wb + l % 4 (8 columns) of row 8 it + rsel; rows r and r + 4 share a quarter warp (their
+        // swizzled chunks fall into disjoint bank groups)
+        const int cl = lane & 3, rsel = ((lane >> 3) & 3) + 4 * ((lane >> 2) & 1);
+        const uint8_t* const tiles_gen = sm.gen + 2 * BWD_BUF;  // s_p as a generic pointer
+        const int64_t HD = (int64_t)p.H * DD;
+        for (int i = 0; i < n_mine; ++i) {
+            const int pair = blockIdx.x + i * gridDim.x, bb = pair / p.H, h = pair - bb * p.H;
+            mbar_wait(staged, i & 1);
+            if (wb == 0 && lane == 0) {
                 tma_store_4d(&map_dv, s_p, 0, 0, h, bb);
                 tma_store_4d(&map_dk, s_p + TILE, 0, 0, h, bb);
                 tma_store_4d(&map_dq, s_s, 0, 0, h, bb);
                 tma_store_commit();
-                tma_store_wait_read<0>();
-                mbar_arrive(stage_free);  // P_d / dS of the next pair may be written
             }
-            tma_store_wait_all();
+            if (p.col_partial) {
+                const int smp = bb / p.seqs_per_sample;
+#pragma unroll 1
+                for (int g = 0; g < 3; ++g) {  // staged order: dv, dk, dq -> rows 2, 1, 0 of [3][S][heads * 64]
+                    const uint8_t* const tile = tiles_gen + g * TILE;
+                    float a[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+                    for (int it = 0; it < 16; ++it) {
+                        const int r = 8 * it + rsel;
+                        const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + (((4 * wb + cl) ^ (r & 7)) << 4));
+                        a[0] += __uint_as_float(v.x << 16), a[1] += __uint_as_float(v.x & 0xffff0000u);
+                        a[2] += __uint_as_float(v.y << 16), a[3] += __uint_as_float(v.y & 0xffff0000u);
+                        a[4] += __uint_as_float(v.z << 16), a[5] += __uint_as_float(v.z & 0xffff0000u);
+                        a[6] += __uint_as_float(v.w << 16), a[7] += __uint_as_float(v.w & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {  // the 8 row classes of a column: lanes l, l ^ 4, l ^ 8, l ^ 16
+                        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 4);
+                        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+                        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+                    }
+                    if (lane < 4) {
+                        float* const dst = p.col_partial + (((int64_t)blockIdx.x * 3 + (2 - g)) * p.S + smp) * HD + (int64_t)h * DD +
+                                           32 * wb + 8 * cl;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e]);
+                    }
+                }
+            }
+            if (wb == 0 && lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stage_free);  // both warps: P_d / dS of the next pair may be written
         }
+        if (wb == 0 && lane == 0) tma_store_wait_all();
     } else if (warp < kRowWarps) {
         const int q = 32 * (warp & 3) + lane, cq = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -558,6 +602,16 @@ static int encode_pair_map(CUtensorMap* m, const void* base, int64_t B, int64_t 
     return 0;
 }
 
+// out[i] = sum over the per-block rows of the partial column sums, in block order (deterministic)
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int64_t n, int blocks) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.0f;
+    for (int c = 0; c < blocks; ++c) acc += partial[(int64_t)c * n + i];
+    out[i] = acc;
+}
+
 static void fill(Params& p, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site,
                  float* lse, uint32_t* keep) {
     p.lse = lse, p.keep = keep;
@@ -598,7 +652,8 @@ int bf_attention_tc_fwd(const void* q, const void* k, const void* v, const int64
 
 int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides, const float* lse,
                         const uint32_t* keep, int64_t B, int64_t H, float scale, float p_drop, uint64_t seed, uint32_t step,
-                        uint32_t site, void* dq, void* dk, void* dv, cudaStream_t stream) {
+                        uint32_t site, void* dq, void* dk, void* dv, float* dbias, void* workspace, int64_t S,
+                        cudaStream_t stream) {
     using namespace attn_tc;
     CUtensorMap mq, mk, mv, mdo, mdq, mdk, mdv;
     const int64_t osb = (int64_t)TT * H * DD, osh = DD, ost = H * DD;
@@ -615,7 +670,21 @@ int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const vo
     p.dq = (__nv_bfloat16*)dq, p.dk = (__nv_bfloat16*)dk, p.dv = (__nv_bfloat16*)dv;
     BF_CUDA_OK(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
+    const int64_t n_bias = 3 * S * H * DD;
+    if (dbias) {
+        p.col_partial = static_cast<float*>(workspace), p.S = (int)S, p.seqs_per_sample = (int)(B / S);
+        BF_CUDA_OK(cudaMemsetAsync(workspace, 0, (size_t)grid * n_bias * 4, stream));
+    }
     bwd_kernel<<<grid, kBwdThreads, BWD_SMEM, stream>>>(mq, mk, mv, mdo, mdq, mdk, mdv, p);
     BF_LAUNCH_OK();
+    if (dbias) {
+        colsum_reduce_kernel<<<(unsigned)((n_bias + 255) / 256), 256, 0, stream>>>(p.col_partial, dbias, n_bias, grid);
+        BF_LAUNCH_OK();
+    }
     return 0;
+}
+
+int64_t bf_attention_tc_bias_workspace_bytes(int64_t B, int64_t H, int64_t S) {
+    const int64_t total = B * H, grid = total < bf_num_sms() ? total : bf_num_sms();
+    return grid * 3 * S * H * attn_tc::DD * 4;
 }

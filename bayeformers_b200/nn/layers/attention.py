@@ -37,12 +37,27 @@ def attention_forward(module, query, key, value, attention_mask, dropout: float 
                            step=module._bf_calls & 0xFFFFFFFF)
     module._last_dropout = drop  # identity of this forward's mask (tests, debugging)
     scale = float(scaling) if scaling is not None else float(query.shape[-1]) ** -0.5
-    return ops.AttentionFn.apply(query, key, value, scale, drop), None
+    # the boxes the pre-hook below handed to this forward's q / k / v projections: the backward kernel fills them with
+    # the projections' bias gradients (column sums of dq, dk, dv per folded sample), consumed once
+    boxes, module._bf_qkv_boxes = getattr(module, "_bf_qkv_boxes", None), None
+    return ops.AttentionFn.apply(query, key, value, scale, drop, boxes, runtime.get_mc_samples()), None
 
 
-def use_native_attention_(model: torch.nn.Module) -> int:
+def _qkv_pre_hook(module, args):
+    """Before a self-attention block runs: give its Bayesian query / key / value projections a `bias_grad_box` each (see
+    ops.BayesLinear: a filled box replaces the layer's own pass over its output gradient)."""
+    boxes = []
+    for name in ("query", "key", "value"):
+        box = []
+        getattr(module, name)._bias_grad_box = box
+        boxes.append(box)
+    module._bf_qkv_boxes = boxes
+
+
+def use_native_attention_(model: torch.nn.Module, bias_grads: bool = False) -> int:
     """Point every transformers config found in `model` at the native attention function.  Returns how many configs
-    were switched (0: not a transformers model, nothing done)."""
+    were switched (0: not a transformers model, nothing done).  bias_grads: let the backward kernel emit the q / k / v
+    projections' bias gradients (see accelerate_host_)."""
     try:
         from transformers import AttentionInterface
     except Exception:  # pragma: no cover
@@ -69,7 +84,12 @@ def use_native_attention_(model: torch.nn.Module) -> int:
             cfg._attn_implementation = NAME
             n += 1
     # dropout sites get their stream ids now (same construction order on every rank)
+    from ..parameters.gaussian import Gaussian
+    from .linear import Linear as BayesLinearModule
     for mod in model.modules():
         if type(mod).__name__.endswith("SelfAttention") and not hasattr(mod, "_bf_site"):
             mod._bf_site, mod._bf_calls = runtime.next_tensor_id(), 0
+            qkv = [getattr(mod, name, None) for name in ("query", "key", "value")]
+            if bias_grads and all(isinstance(l, BayesLinearModule) and isinstance(l.bias, Gaussian) for l in qkv):
+                mod.register_forward_pre_hook(_qkv_pre_hook)
     return n

@@ -869,11 +869,15 @@ class AttentionFn(torch.autograd.Function):
     """O = dropout_p(softmax(q k^T * scale)) v for short sequences (`bf_attention_fwd` / `_bwd`): the host model's
     attention between the Bayesian projections.  q, k, v: bf16 [B, H, T, 64] views with unit inner stride (HF passes
     transposed views of the [B, T, H*64] projection outputs: read in place); returns [B, T, H, 64].  The keep mask is
-    regenerated in backward from (seed, site, step)."""
+    regenerated in backward from (seed, site, step).
+
+    `bias_boxes` (optional): three lists, the `bias_grad_box`es of the Bayesian q / k / v projections that produced the
+    inputs, and `S` the number of folded samples: at T == 128 the backward kernel then also emits the column sums of dq,
+    dk, dv per sample -- those layers' bias gradients -- and the layers skip their own pass over the gradients."""
 
     @staticmethod
     @_guarded
-    def forward(ctx, q, k, v, scale: float, drop: DropoutSpec):
+    def forward(ctx, q, k, v, scale: float, drop: DropoutSpec, bias_boxes=None, S: int = 1):
         _require_cuda(q, "query")
         lib = _lib.load()
         dev = q.device
@@ -893,7 +897,9 @@ class AttentionFn(torch.autograd.Function):
         _lib.check(rc, "bf_attention_fwd")
         stats["launches"] += 1
         ctx.save_for_backward(qc, kc, vc, lse, keep)
-        ctx.meta = (float(scale), drop, strides)
+        fused_bias = (bias_boxes is not None and T == 128 and (keep is not None or drop.p == 0.0) and S >= 1 and B % S == 0
+                      and bool(lib.bf_get_option(_lib.BF_OPT_ATTN_TC)))
+        ctx.meta = (float(scale), drop, strides, bias_boxes if fused_bias else None, int(S))
         return out
 
     @staticmethod
@@ -901,21 +907,32 @@ class AttentionFn(torch.autograd.Function):
     def backward(ctx, gout):
         lib = _lib.load()
         qc, kc, vc, lse, keep = ctx.saved_tensors
-        scale, drop, strides = ctx.meta
+        scale, drop, strides, bias_boxes, S = ctx.meta
         dev = qc.device
         B, H, T, Dh = qc.shape
         g = gout.to(torch.bfloat16).contiguous()
         dq = torch.empty((B, T, H, Dh), dtype=torch.bfloat16, device=dev)
         dk, dv = torch.empty_like(dq), torch.empty_like(dq)
         flops = 10.0 * B * H * T * T * Dh
-        rc = _timed("attention_bwd", flops, dev, lambda: lib.bf_attention_bwd(
+        dbias = ws = None
+        if bias_boxes is not None:
+            dbias = torch.empty((3, S, H * Dh), dtype=torch.float32, device=dev)
+            ws = _workspace("attention_colsum", dev, lib.bf_attention_bias_workspace_bytes(B, H, S))
+        rc = _timed("attention_bwd", flops, dev, lambda: lib.bf_attention_bwd_bias(
             _ptr(g), _ptr(qc), _ptr(kc), _ptr(vc), strides.data_ptr(), None, _ptr(lse), _ptr(keep), B, H, T, scale,
-            float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dq), _ptr(dk), _ptr(dv), _stream(dev)))
-        _lib.check(rc, "bf_attention_bwd")
+            float(drop.p), drop.seed, drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dbias),
+            _ptr(ws), S, _stream(dev)))
+        _lib.check(rc, "bf_attention_bwd_bias")
         stats["launches"] += 1
+        if bias_boxes is not None:
+            stats["launches"] += 1  # the fixed-order reduction of the per-block column sums
+            for i, box in enumerate(bias_boxes):  # q, k, v: picked up by the projections' backward (BayesLinear)
+                if box is not None:
+                    box.clear()
+                    box.append(dbias[i])
         # [B, T, H, D] buffers seen as [B, H, T, D]: the layout the inputs came in (views of [B, T, H*D] rows), so the
         # transposes / reshapes of the surrounding model stay free
-        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None, None
 
 
 def attention_supported(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:

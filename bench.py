@@ -83,6 +83,9 @@ def parse():
                     help="1 (default): the host model's short-sequence attention (T <= 128) runs on the native kernels "
                          "(tcgen05 at T = 128: 1.2 ms per BERT-base layer fwd+bwd against 2.2 ms of cuDNN's fused "
                          "attention); 0: torch SDPA")
+    ap.add_argument("--attention-bias-grads", type=int, default=0,
+                    help="1: q / k / v bias gradients from the attention backward kernel (no net gain measured: see "
+                         "bf.accelerate_host_)")
     ap.add_argument("--gelu-poly", type=int, default=1,
                     help="1 (default): the fused GELU / GELU' epilogues evaluate odd polynomials (|err| <= 1e-4 / 6e-4, "
                          "inside bf16 rounding); 0: the erf forms (bf_set_option(BF_OPT_GELU_POLY))")
@@ -412,7 +415,8 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
         # dropout + residual + LayerNorm of the output blocks in one pass each way (Philox dropout mask)
         bf.accelerate_host_(bm, layernorm=bool(args.host_ln), fuse_gelu=bool(args.fuse_gelu),
                             fuse_residual=bool(args.fuse_residual),
-                            grad_sinks=bool(args.grad_sinks and args.fuse_residual), attention=bool(args.attention))
+                            grad_sinks=bool(args.grad_sinks and args.fuse_residual), attention=bool(args.attention),
+                            attention_bias_grads=bool(args.attention_bias_grads))
     bm = bm.to(dev).train()
     if args.presample:
         bf.enable_presample(bm)

@@ -401,6 +401,15 @@ int bf_attention_fwd(const void* q, const void* k, const void* v, const int64_t*
 int bf_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
                      const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T, float scale,
                      float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk, void* dv, void* stream);
+/* bf_attention_bwd that also emits the bias gradients of the q / k / v projections, i.e. the column sums of dq, dk, dv
+ * over the rows of each of the S folded samples (B % S == 0; sample s = sequences [s*B/S, (s+1)*B/S)):
+ *   dbias  fp32 [3][S][H*64] (q, k, v), taken from the gradient tiles staged in shared memory (per-block partial rows in
+ *   `workspace`, added in block order by a second small pass: deterministic).  T == 128 / tcgen05 path only. */
+int64_t bf_attention_bias_workspace_bytes(int64_t B, int64_t H, int64_t S);
+int bf_attention_bwd_bias(const void* dout, const void* q, const void* k, const void* v, const int64_t* strides,
+                          const void* out, const float* lse, const uint32_t* keep, int64_t B, int64_t H, int64_t T,
+                          float scale, float p_drop, uint64_t seed, uint32_t step, uint32_t site, void* dq, void* dk,
+                          void* dv, float* dbias, void* workspace, int64_t S, void* stream);
 int bf_attention_dropout_mask(uint8_t* out, int64_t B, int64_t H, int64_t T, float p_drop, uint64_t seed, uint32_t step,
                               uint32_t site, void* stream);
 

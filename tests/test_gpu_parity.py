@@ -1388,6 +1388,20 @@ def test_attention_tcgen05_and_mma_sync_kernels_share_one_mask_and_agree():
     # the two families against each other
     assert rel_err(res[1][0].cpu().numpy(), res[0][0].cpu().numpy()) < 6e-3
     assert rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 1.5e-2
+    # the tcgen05 backward can also emit the q / k / v projections' bias gradients: column sums of dq, dk, dv per folded
+    # sample (S = 3 samples x 50 sequences), equal to the sums of the bf16 gradients it wrote, bit-identical run to run
+    S = 3
+    got = []
+    for rep in range(2):
+        boxes = [[], [], []]
+        fused.grad = None
+        ops.AttentionFn.apply(q, k, v, Dh ** -0.5, drop, boxes, S).backward(gout)
+        torch.cuda.synchronize()
+        assert all(len(b) == 1 and b[0].shape == (S, H * Dh) and b[0].dtype == torch.float32 for b in boxes)
+        got.append(torch.stack([b[0] for b in boxes]))
+        want = fused.grad.view(S, B // S * Tn, 3, H * Dh).double().sum(1).transpose(0, 1)  # [3, S, H * Dh]
+        assert rel_err(got[-1].cpu().numpy(), want.cpu().numpy()) < 1e-5
+    assert torch.equal(got[0], got[1])
 
 
 def test_attention_dropout_masks_are_independent_across_sites_and_steps():
@@ -1415,7 +1429,7 @@ def test_accelerate_host_native_attention_matches_sdpa():
     cfg = BertConfig(vocab_size=100, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
                      intermediate_size=512, max_position_embeddings=128, num_labels=2)
     base = bf.to_bayesian(BertForSequenceClassification(cfg), delta=0.05, freeze=True, gemm_dtype="bf16")
-    fast = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, attention=True)
+    fast = bf.accelerate_host_(copy.deepcopy(base), layernorm=False, fuse_gelu=False, attention=True, attention_bias_grads=True)
     truth = copy.deepcopy(base)  # fp32 everywhere: FFMA contractions, fp32 host model
     for l in truth.bayesian_children:
         l.gemm_dtype = torch.float32
@@ -1438,10 +1452,16 @@ def test_accelerate_host_native_attention_matches_sdpa():
                 logits = m(input_ids=ids.repeat(S, 1)).logits
             logits.float().square().sum().backward()
             torch.cuda.synchronize()
-            ran = set(ops.kernel_timing_summary())
+            summary = ops.kernel_timing_summary()
+            ran = set(summary)
         finally:
             ops.enable_kernel_timing(False)
         assert ({"attention_fwd", "attention_bwd"} <= ran) == (m is fast)
+        if m is not truth:
+            # 2 layers x (q, k, v, attention-output, FFN-up, FFN-down) + pooler + classifier = 14 Bayesian Linears; with
+            # the native attention the q / k / v bias gradients come out of its backward kernel
+            n_bias = summary["bias_grad"]["calls"]
+            assert n_bias == (14 - 6 if m is fast else 14), n_bias
         outs.append((logits.detach().float(), [l.weight.rho.grad.clone() for l in m.bayesian_children]))
     assert rel_err(outs[1][0].cpu().numpy(), outs[0][0].cpu().numpy()) < 2e-2
     e_sdpa = [rel_err(g.cpu().numpy(), t.cpu().numpy()) for g, t in zip(outs[0][1], outs[2][1])]
