@@ -6,7 +6,7 @@ import collections
 import csv
 import sys
 
-OURS = ("attn_tc::", "attn::", "bayes_gemm", "bayes_wgrad", "wgrad_reduce", "sample_kl", "layernorm_", "resln_", "bias_grad", "gemm_f32_kernel", "embedding_", "split_bf16x2",
+OURS = ("attn_tc::", "attn::", "colsum_reduce", "bayes_gemm", "bayes_wgrad", "wgrad_reduce", "sample_kl", "layernorm_", "resln_", "bias_grad", "gemm_f32_kernel", "embedding_", "split_bf16x2",
         "clip_adamw", "grad_sumsq", "gelu_bwd_bias_grad", "philox_normal", "dropout_mask_kernel")
 CONTRACTIONS = ("bayes_gemm", "bayes_wgrad_kernel")
 
