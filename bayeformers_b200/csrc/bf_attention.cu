@@ -143,6 +143,7 @@ __device__ __forceinline__ void scores(float (&s)[2 * NJP][4], const uint8_t* sA
 __device__ __forceinline__ void store_rows64(uint8_t* stage, int row0, const float (&o)[8][4], float r0, float r1,
                                              __nv_bfloat16* gbase, int64_t g_st, int lane) {
     const int g = lane >> 2, c = lane & 3;
+    __syncwarp();  // every lane's ldmatrix reads of these rows are done (they are, behind the mma.sync chain; this says so)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         *reinterpret_cast<uint32_t*>(stage + off64(row0 + g, 8 * j + 2 * c)) = pack_bf16(o[j][0] * r0, o[j][1] * r0);

@@ -29,6 +29,9 @@ for stage in "$@"; do
     ncu_attn)
       timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:"fwd_kernel|bwd_kernel|attention_fwd|attention_bwd|sdpa|cudnn" -c 40 -f -o gpurun_out/prof_attn python scripts/profile_attention.py > gpurun_out/ncu_attn.log 2>&1; echo "rc $?"; tail -2 gpurun_out/ncu_attn.log
       rm -f gpurun_out/r02_ncu_attention.md; python scripts/ncu_summary.py gpurun_out/prof_attn.ncu-rep gpurun_out/r02_ncu_attention.md; cut -c1-260 gpurun_out/r02_ncu_attention.md ;;
+    sanitize_colsum)
+      timeout -k 10 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "dgrad_gelu_kernel or tcgen05_and_mma_sync" > gpurun_out/sanitizer_colsum_memcheck.log 2>&1; echo "memcheck rc $?"; tail -4 gpurun_out/sanitizer_colsum_memcheck.log
+      timeout -k 10 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "dgrad_gelu_kernel and 2560 or tcgen05_and_mma_sync" > gpurun_out/sanitizer_colsum_racecheck.log 2>&1; echo "racecheck rc $?"; tail -4 gpurun_out/sanitizer_colsum_racecheck.log ;;
     sanitize_attn)
       timeout -k 10 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128 or attention_kernels and 150-2-128" > gpurun_out/sanitizer_attn_memcheck.log 2>&1; echo "memcheck rc $?"; tail -4 gpurun_out/sanitizer_attn_memcheck.log
       timeout -k 10 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128" > gpurun_out/sanitizer_attn_racecheck.log 2>&1; echo "racecheck rc $?"; tail -4 gpurun_out/sanitizer_attn_racecheck.log ;;
