@@ -34,7 +34,7 @@ int main() {
         bf_attention_tc_fwd(q, k, v, strides, B, H, 0.125f, 0.1f, 1, 2, 3, o, lse, keep, 0);
         cudaDeviceSynchronize();
         cudaMemcpyFromSymbol(t, attn_tc::g_trace, sizeof(t));
-        const char* fn[] = {"top", "s_ready", "max", "bar1", "drained(prev)", "philox+exp", "bar2", "staged P"};
+        const char* fn[] = {"top", "s_ready", "max", "bar1", "bar1'", "exp+sum", "bar2", "select+staged P (then the drain of the previous pair)"};
         printf("forward, ALU thread 0 (cycles since the pair's top)\n");
         for (int i = 1; i < 12; ++i) {
             printf("pair %2d: top+%6llu", i, t[i * 16] - t[(i - 1) * 16]);
