@@ -23,7 +23,7 @@ int main() {
     const int64_t strides[9] = {T * H * D, D, H * D, T * H * D, D, H * D, T * H * D, D, H * D};
     for (int rep = 0; rep < 3; ++rep) {
         int rc = bf_attention_tc_fwd(q, k, v, strides, B, H, 0.125f, 0.1f, 1, 2, 3, o, lse, keep, 0);
-        rc |= bf_attention_tc_bwd(dO, q, k, v, strides, lse, keep, B, H, 0.125f, 0.1f, 1, 2, 3, dq, dk, dv, 0);
+        rc |= bf_attention_tc_bwd(dO, q, k, v, strides, lse, keep, B, H, 0.125f, 0.1f, 1, 2, 3, dq, dk, dv, nullptr, nullptr, 1, 0);
         if (rc) { printf("rc %d\n", rc); return 1; }
     }
     cudaError_t e = cudaDeviceSynchronize();
