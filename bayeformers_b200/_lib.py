@@ -111,6 +111,12 @@ SIGNATURES = {
     "bf_resln_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "bf_resln_fwd_keep": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                    c_float, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    "bf_resln_bwd_keep": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "bf_dropout_mask": (c_int32, [c_void_p, c_int64, c_float, c_uint64, c_uint32, c_uint32, c_void_p]),
     "bf_attention_supported": (c_int32, [c_int64, c_int64]),
     "bf_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,

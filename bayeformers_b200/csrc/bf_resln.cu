@@ -111,6 +111,8 @@ struct DropSpec {
     uint32_t threshold;  // keep iff u16 >= threshold; 0 = dropout off
     float scale;         // 1 / (1 - p)
     const uint32_t* step_ptr;
+    uint8_t* keep;       // optional [rows][H / 8]: the keep bits of each octet, written by forward, read by backward
+                         // (the backward is issue-bound; regenerating the mask is half of its instructions)
 };
 
 // keep-multipliers (0 or scale) of the 8 elements of octet `oct` (= flat element index / 8)
@@ -122,6 +124,18 @@ __device__ __forceinline__ void drop_mult8(const DropSpec& d, uint32_t step, uin
         m[2 * i] = (w[i] & 0xffffu) >= d.threshold ? d.scale : 0.0f;
         m[2 * i + 1] = (w[i] >> 16) >= d.threshold ? d.scale : 0.0f;
     }
+}
+
+// the same from the stored keep byte of the octet (bit j = element j kept)
+__device__ __forceinline__ void drop_mult8_bits(const DropSpec& d, uint32_t bits, float (&m)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = (bits & (1u << j)) ? d.scale : 0.0f;
+}
+__device__ __forceinline__ uint32_t keep_byte(const float (&m)[8]) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b |= (m[j] != 0.0f ? 1u : 0u) << j;
+    return b;
 }
 
 // ------------------------------------------------------------------ forward
@@ -155,6 +169,7 @@ __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
                 if (drop.threshold) {
                     float mk[8];
                     drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
+                    if (drop.keep) drop.keep[(int64_t)row * (H / 8) + c * 32 + lane] = (uint8_t)keep_byte(mk);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) zv[j] = fmaf(hv[j], mk[j], rv[j]);
                 } else {
@@ -430,7 +445,8 @@ __global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
             Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
             if (kDrop) {
                 float mk[8];
-                drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
+                if (drop.keep) drop_mult8_bits(drop, __ldg(drop.keep + (int64_t)row * (H / 8) + c * 32 + lane), mk);
+                else drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] *= mk[j];
                 Pack8<T>::store(dh + row * H + c * 256 + lane * 8, o);
@@ -538,11 +554,26 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
     int st = 0;
     uint32_t parity = 0;
     float mean_n = 0.0f, rstd_n = 0.0f;  // row statistics: plain loads issued one iteration ahead
-    if (m_first < M) mean_n = __ldg(mean_in + row0 + m_first), rstd_n = __ldg(rstd_in + row0 + m_first);
+    uint32_t kb_n[C];                    // ... and, when forward stored them, the keep bytes of this lane's octets
+    const bool stored_mask = kDrop && drop.keep != nullptr;
+    auto fetch_keep = [&](int64_t r) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) kb_n[c] = __ldg(drop.keep + r * (H / 8) + c * 32 + lane);
+    };
+    if (m_first < M) {
+        mean_n = __ldg(mean_in + row0 + m_first), rstd_n = __ldg(rstd_in + row0 + m_first);
+        if (stored_mask) fetch_keep(row0 + m_first);
+    }
     for (int64_t m = m_first; m < M; m += m_step) {
         const int64_t row = row0 + m;
         const float mean = mean_n, rstd = rstd_n;
-        if (m + m_step < M) mean_n = __ldg(mean_in + row + m_step), rstd_n = __ldg(rstd_in + row + m_step);
+        uint32_t kb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) kb[c] = stored_mask ? kb_n[c] : 0u;
+        if (m + m_step < M) {
+            mean_n = __ldg(mean_in + row + m_step), rstd_n = __ldg(rstd_in + row + m_step);
+            if (stored_mask) fetch_keep(row + m_step);
+        }
         rl_mbar_wait(bars + st * 8, parity);
         const char* zr = ring + (st * 2) * kRowBytes;
         const char* gr = zr + kRowBytes;
@@ -602,7 +633,8 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
             Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
             if (kDrop) {
                 float mk[8];
-                drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
+                if (stored_mask) drop_mult8_bits(drop, kb[c], mk);
+                else drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     o2[j] = bf_mul2(o2[j], bf_pack2(mk[2 * j], mk[2 * j + 1]));
@@ -654,6 +686,7 @@ DropSpec make_drop(float p, uint64_t seed, uint32_t step, uint32_t site) {
     double t = (double)p * 65536.0 + 0.5;
     d.threshold = p <= 0.0f ? 0u : (uint32_t)(t > 65535.0 ? 65535.0 : t);
     d.scale = p <= 0.0f ? 1.0f : 1.0f / (1.0f - p);
+    d.keep = nullptr;
     return d;
 }
 
@@ -755,10 +788,21 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t n, DropSp
 
 extern "C" int bf_resln_supported(int64_t H) { return (H % 256 == 0 && H >= 256 && H <= 1024) ? 1 : 0; }
 
+extern "C" int bf_resln_fwd_keep(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
+                                 int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
+                                 uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
+                                 uint8_t* keep, void* stream);
 extern "C" int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
                             int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
                             uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
                             void* stream) {
+    return bf_resln_fwd_keep(h, r, dtype, gamma, beta, affine_stride, S, M, H, eps, p_drop, seed, step, site_id, z, y, mean,
+                             rstd, nullptr, stream);
+}
+extern "C" int bf_resln_fwd_keep(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
+                                 int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
+                                 uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
+                                 uint8_t* keep, void* stream) {
     BF_CHECK_ARG(h && r && gamma && z && y && mean && rstd, "null pointer");
     BF_CHECK_ARG(dtype == BF_F32 || dtype == BF_BF16, "bad dtype");
     BF_CHECK_ARG(S >= 1 && M >= 0 && S <= 65535, "bad S or M");
@@ -770,7 +814,8 @@ extern "C" int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const f
                  "h, r, z, y, gamma, beta must be 16-byte aligned (vector loads / stores)");
     if (M == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const DropSpec d = make_drop(p_drop, seed, step, site_id);
+    DropSpec d = make_drop(p_drop, seed, step, site_id);
+    d.keep = keep;
     if (dtype == BF_BF16) {
         BF_RESLN_DISPATCH(launch_fwd_c, __nv_bfloat16, h, r, gamma, beta, z, y, mean, rstd, S, M, affine_stride, eps, d, st);
     } else {
@@ -786,10 +831,21 @@ extern "C" int64_t bf_resln_bwd_workspace_bytes(int64_t S, int64_t M, int64_t H)
     return counters_bytes(S) + (S * nblk * 3 * H + S * 2 * H) * (int64_t)sizeof(float);
 }
 
+extern "C" int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
+                                 const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
+                                 uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
+                                 float* dbeta, float* dbias, void* workspace, const uint8_t* keep, void* stream);
 extern "C" int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
                             const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
                             uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
                             float* dbeta, float* dbias, void* workspace, void* stream) {
+    return bf_resln_bwd_keep(gy, z, dtype, gamma, affine_stride, mean, rstd, S, M, H, p_drop, seed, step, site_id, dz, dh, dgamma,
+                             dbeta, dbias, workspace, nullptr, stream);
+}
+extern "C" int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
+                                 const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
+                                 uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
+                                 float* dbeta, float* dbias, void* workspace, const uint8_t* keep, void* stream) {
     BF_CHECK_ARG(gy && z && gamma && mean && rstd && dz && dgamma && workspace, "null pointer");
     BF_CHECK_ARG(dtype == BF_F32 || dtype == BF_BF16, "bad dtype");
     BF_CHECK_ARG(S >= 1 && M >= 1 && S <= 65535, "bad S or M");
@@ -802,7 +858,8 @@ extern "C" int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const 
                      aligned16(dgamma) && (!dbeta || aligned16(dbeta)) && (!dbias || aligned16(dbias)) && aligned16(workspace),
                  "gy, z, dz, dh, gamma, dgamma, dbeta, dbias, workspace must be 16-byte aligned (vector / bulk copies)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const DropSpec d = make_drop(p_drop, seed, step, site_id);
+    DropSpec d = make_drop(p_drop, seed, step, site_id);
+    d.keep = const_cast<uint8_t*>(keep);
     if (dtype == BF_BF16) {
         BF_RESLN_DISPATCH(launch_bwd_c, __nv_bfloat16, gy, z, gamma, mean, rstd, dz, dh, dgamma, dbeta, dbias, workspace, S,
                           M, affine_stride, d, st);

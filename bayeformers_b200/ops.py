@@ -789,11 +789,16 @@ class DropoutSpec:
     step: int = 0
 
 
+# ResidualLayerNormFn: hand the dropout keep bits from forward to backward (True) or regenerate them there (False: A/B, tests)
+resln_keep_bits = {"on": True}
+
+
 class ResidualLayerNormFn(torch.autograd.Function):
     """y = layer_norm(dropout_p(h) + r) * gamma_s + beta_s in one pass each way
     (`bf_resln_fwd` / `bf_resln_bwd`): the code around a Bayesian Linear in a
     transformer output block.  gamma / beta: fp32 [S, H] (sampled, row A10) or [H]
-    (shared).  The dropout mask is regenerated from its Philox counter in backward.
+    (shared).  The dropout mask is a function of its Philox counter; its keep bits are handed to backward (H / 8
+    bytes per row) rather than regenerated there (`resln_keep_bits`).
     `bias_grad_box` (a list) receives sum_m dh[s][m][:] for the Linear that made h."""
 
     @staticmethod
@@ -819,12 +824,14 @@ class ResidualLayerNormFn(torch.autograd.Function):
         mean = torch.empty(rows, dtype=torch.float32, device=dev)
         rstd = torch.empty(rows, dtype=torch.float32, device=dev)
         nbytes = float(rows * H * hc.element_size() * 4)
-        rc = _timed("resln_fwd", nbytes, dev, lambda: lib.bf_resln_fwd(
+        # the keep bits of the dropout mask go to backward (H / 8 bytes per row) instead of being regenerated there
+        keep = torch.empty((rows, H // 8), dtype=torch.uint8, device=dev) if (drop.p > 0 and resln_keep_bits["on"]) else None
+        rc = _timed("resln_fwd", nbytes, dev, lambda: lib.bf_resln_fwd_keep(
             _ptr(hc), _ptr(rc_), _dt(hc.dtype), _ptr(g), _ptr(b), stride, S, M, H, float(eps), float(drop.p), drop.seed,
-            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), _stream(dev)))
-        _lib.check(rc, "bf_resln_fwd")
+            drop.step & 0xFFFFFFFF, drop.site_id, _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(keep), _stream(dev)))
+        _lib.check(rc, "bf_resln_fwd_keep")
         stats["launches"] += 1
-        ctx.save_for_backward(z, g, mean, rstd)
+        ctx.save_for_backward(z, g, mean, rstd, keep)
         ctx.meta = (S, M, H, stride, gamma.shape, gamma.dtype, None if beta is None else beta.dtype, drop, bias_grad_box,
                     sink)
         return y.view(h.shape)
@@ -833,7 +840,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
     @_guarded
     def backward(ctx, gy):
         lib = _lib.load()
-        z, g, mean, rstd = ctx.saved_tensors
+        z, g, mean, rstd, keep = ctx.saved_tensors
         S, M, H, stride, g_shape, g_dtype, b_dtype, drop, box, sink = ctx.meta
         dev = z.device
         gyc = _aligned(gy.to(z.dtype))
@@ -845,11 +852,11 @@ class ResidualLayerNormFn(torch.autograd.Function):
         dbias = torch.empty((S, H), dtype=torch.float32, device=dev) if box is not None else None
         ws = _workspace("resln_bwd", dev, lib.bf_resln_bwd_workspace_bytes(S, M, H))
         nbytes = float(z.numel() * z.element_size() * (4 if dh is not None else 3))
-        rc = _timed("resln_bwd", nbytes, dev, lambda: lib.bf_resln_bwd(
+        rc = _timed("resln_bwd", nbytes, dev, lambda: lib.bf_resln_bwd_keep(
             _ptr(gyc), _ptr(z), _dt(z.dtype), _ptr(g), stride, _ptr(mean), _ptr(rstd), S, M, H, float(drop.p), drop.seed,
             drop.step & 0xFFFFFFFF, drop.site_id, _ptr(dz), _ptr(dh), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(ws),
-            _stream(dev)))
-        _lib.check(rc, "bf_resln_bwd")
+            _ptr(keep), _stream(dev)))
+        _lib.check(rc, "bf_resln_bwd_keep")
         stats["launches"] += 1
         if box is not None:
             box.clear()

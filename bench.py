@@ -86,6 +86,9 @@ def parse():
     ap.add_argument("--attention-bias-grads", type=int, default=0,
                     help="1: q / k / v bias gradients from the attention backward kernel (no net gain measured: see "
                          "bf.accelerate_host_)")
+    ap.add_argument("--resln-keep-bits", type=int, default=1,
+                    help="1 (default): the fused dropout+residual+LayerNorm forward hands the mask's keep bits to its backward "
+                         "(H/8 bytes per row); 0: the backward regenerates them from the Philox counter")
     ap.add_argument("--gelu-poly", type=int, default=1,
                     help="1 (default): the fused GELU / GELU' epilogues evaluate odd polynomials (|err| <= 1e-4 / 6e-4, "
                          "inside bf16 rounding); 0: the erf forms (bf_set_option(BF_OPT_GELU_POLY))")
@@ -407,6 +410,7 @@ def measure(args, dev, world, rank, local, *, batch, gemm, steps, warmup, timing
     bf.runtime.enable_gelu_links(bool(args.gelu_links))
     from bayeformers_b200 import _lib as _bf_lib
     _bf_lib.load().bf_set_option(_bf_lib.BF_OPT_GELU_POLY, int(args.gelu_poly))
+    ops.resln_keep_bits["on"] = bool(args.resln_keep_bits)
     layers = bnn.TORCH2BAYE_ALL if args.config == "bert_large" else None
     bm = bf.to_bayesian(model, delta=0.05, freeze=(args.config != "mlp"), gemm_dtype=gemm, kl_grad=bool(args.kl_grad),
                         layers=layers)

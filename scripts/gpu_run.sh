@@ -35,6 +35,11 @@ for stage in "$@"; do
     sanitize_attn)
       timeout -k 10 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128 or attention_kernels and 150-2-128" > gpurun_out/sanitizer_attn_memcheck.log 2>&1; echo "memcheck rc $?"; tail -4 gpurun_out/sanitizer_attn_memcheck.log
       timeout -k 10 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "attention_kernels and 3-12-128" > gpurun_out/sanitizer_attn_racecheck.log 2>&1; echo "racecheck rc $?"; tail -4 gpurun_out/sanitizer_attn_racecheck.log ;;
+    ab_keep)
+      timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "resln or fuses_hf_output" 2>&1 | tail -3
+      for v in 0 1 0 1; do
+        timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --resln-keep-bits $v > gpurun_out/bench_keep$v.json 2> gpurun_out/bench_keep$v.err; echo "resln-keep-bits=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_keep$v.json 2>/dev/null | grep "^value\|resln"
+      done ;;
     ab_poly)
       for v in 0 1 0 1; do
         timeout -k 10 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --extras 0 --gelu-poly $v > gpurun_out/bench_poly$v.json 2> gpurun_out/bench_poly$v.err; echo "gelu-poly=$v rc $?"; python scripts/bench_kernels.py gpurun_out/bench_poly$v.json 2>/dev/null | head -1

@@ -1005,6 +1005,20 @@ def test_resln_vs_torch_fp64(S, M, H, shared, dtype, p):
     y2.backward(gy.to(DEV))
     assert torch.equal(y, y2) and torch.equal(hd.grad, hd2.grad) and torch.equal(rd.grad, rd2.grad)
     assert torch.equal(gd.grad, gd2.grad) and torch.equal(bd.grad, bd2.grad) and torch.equal(box[0], box2[0])
+    if p > 0:
+        # the backward normally LOADS the keep bits forward stored (H / 8 bytes per row); regenerating them from the Philox
+        # counter instead (ops.resln_keep_bits off) gives the same bits everywhere
+        ops.resln_keep_bits["on"] = False
+        try:
+            hd3, rd3 = h.to(DEV).requires_grad_(), r.to(DEV).requires_grad_()
+            gd3, bd3 = gamma.to(DEV).requires_grad_(), beta.to(DEV).requires_grad_()
+            box3 = []
+            y3 = ops.ResidualLayerNormFn.apply(hd3, rd3, gd3, bd3, S, 1e-12, spec, box3)
+            y3.backward(gy.to(DEV))
+        finally:
+            ops.resln_keep_bits["on"] = True
+        assert torch.equal(y, y3) and torch.equal(hd.grad, hd3.grad) and torch.equal(rd.grad, rd3.grad)
+        assert torch.equal(gd.grad, gd3.grad) and torch.equal(bd.grad, bd3.grad) and torch.equal(box[0], box3[0])
 
 
 @pytest.mark.parametrize("mode,bayes_ln,sinks", [("fp32", False, False), ("bf16", False, False), ("fp32", True, False),
