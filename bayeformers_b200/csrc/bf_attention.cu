@@ -9,17 +9,23 @@
 // thread block, so there is no online-softmax recurrence, no split of the key axis and no second pass for dq:
 //
 //   forward : S = q k^T (registers) -> row softmax -> Philox keep mask -> O = P_d v;  O and the base-2 log-sum-exp kept
-//   backward: S, P recomputed; dP = dO v^T; dS = P o (dP_d - rowsum(dO o O)) * scale; dq = dS k (registers);
-//             P_d and dS staged in shared memory, then dv = P_d^T dO and dk = dS^T q by the same block -- every output
-//             is written exactly once, nothing is accumulated with atomics, results are deterministic.
+//   backward: S, P recomputed; dP = dO v^T; dS = P o (dP_d - D) * scale with D = sum_k P_d dP_d (== rowsum(dO o O), so O
+//             is not read); P_d and dS staged in shared memory, then dv = P_d^T dO, dk = dS^T q and dq = dS k by the same
+//             block -- every output is written exactly once, nothing is accumulated with atomics: deterministic.
 //
 // q, k, v are read in place from the projection outputs ([B, T, heads*64] rows, any strides with a unit inner stride),
 // O and the gradients are written in the [B, T, heads, 64] layout the surrounding reshape expects, so no transposed
-// copies are made.  Matrix products use mma.sync m16n8k16 (bf16 in, fp32 accumulate) on fragments loaded with ldmatrix:
-// the op is bound by the q/k/v/o traffic and by its exponentials, not by tensor throughput, and whole-tile tcgen05
-// MMAs would leave nothing for the softmax between them to overlap with at this size.
+// copies are made.
 //
-// The dropout keep mask is never stored.  keep(b, h, q, k) = u16 >= round(p * 65536) with the u16 taken from
+// Two kernel families share this entry point and one keep mask.  T == 128 (BERT's GLUE configuration) runs on tcgen05
+// (bf_attention_tc.cu: TMA-loaded tiles, TMEM accumulators, one row per thread: 0.40 + 0.60 ms per BERT-base layer).
+// THIS file holds the kernels for the other lengths (16 <= T < 128) and the fallback (BF_OPT_ATTN_TC = 0): matrix
+// products with mma.sync m16n8k16 (bf16 in, fp32 accumulate) on fragments loaded with ldmatrix, tiles double buffered
+// with cp.async, a 16-warp backward (8 row groups x 2 key halves).  At T = 128 they take 0.67 + 1.60 ms: issue-bound
+// (a third of the instructions are Philox, and every two MMAs need an ldmatrix).
+//
+// The dropout keep mask is a pure function of its counter (these kernels regenerate it in backward; the tcgen05
+// forward also hands its keep bits to the tcgen05 backward).  keep(b, h, q, k) = u16 >= round(p * 65536) with the u16 taken from
 // Philox4x32-10(counter = (row, (k % 8) / 2 + 4 * (k / 32), 0x40000000 | site, step [+ device step counter]),
 // key = seed), row = (b * heads + h) * T + q: word (k / 8) % 4 of the result, low half for even k, high half for odd k
 // -- i.e. one call yields the 8 values one thread holds of a query row in the MMA accumulator layout.

@@ -382,3 +382,29 @@ def test_rng_state_round_trip_restores_stream_ids_and_counters():
     assert runtime.dropout_seed() == runtime.seed()
     with pytest.raises(KeyError):
         bf.load_rng_state(torch.nn.Sequential(torch.nn.Linear(2, 2)), state)
+
+
+def test_native_attention_glue_registers_and_hands_bias_boxes():
+    """accelerate_host_(attention=True) points a HuggingFace config at the native attention function and gives every
+    self-attention block its dropout stream id; attention_bias_grads=True additionally installs the pre-hook that hands
+    the Bayesian query / key / value projections a bias_grad_box each (host logic only: no kernel runs on CPU)."""
+    transformers = pytest.importorskip("transformers")
+    import bayeformers_b200 as bf
+    from bayeformers_b200.nn.layers import attention as A
+
+    cfg = transformers.BertConfig(vocab_size=50, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                  intermediate_size=256, max_position_embeddings=32, num_labels=2)
+    for flag in (False, True):
+        m = bf.to_bayesian(transformers.BertForSequenceClassification(cfg), delta=0.05, freeze=True)
+        m = bf.accelerate_host_(m, layernorm=False, fuse_gelu=False, attention=True, attention_bias_grads=flag)
+        blocks = [mod for mod in m.modules() if type(mod).__name__.endswith("SelfAttention")]
+        assert len(blocks) == 2 and all(hasattr(b, "_bf_site") for b in blocks)
+        assert len({b._bf_site for b in blocks}) == 2
+        assert all((len(b._forward_pre_hooks) == 1) == flag for b in blocks)
+        assert [c._attn_implementation for c in {id(x.config): x.config for x in m.modules() if hasattr(x, "config")}.values()] \
+            == [A.NAME]
+        if flag:
+            A._qkv_pre_hook(blocks[0], ())
+            boxes = blocks[0]._bf_qkv_boxes
+            assert [blocks[0].query._bias_grad_box, blocks[0].key._bias_grad_box, blocks[0].value._bias_grad_box] == boxes
+            assert all(b == [] for b in boxes) and boxes[0] is not boxes[1]
