@@ -111,8 +111,9 @@ struct DropSpec {
     uint32_t threshold;  // keep iff u16 >= threshold; 0 = dropout off
     float scale;         // 1 / (1 - p)
     const uint32_t* step_ptr;
-    uint8_t* keep;       // optional [rows][H / 8]: the keep bits of each octet, written by forward, read by backward
-                         // (the backward is issue-bound; regenerating the mask is half of its instructions)
+    uint32_t* keep;      // optional [rows][32]: per (row, lane) one word with the keep bytes of the lane's C octets (byte c =
+                         // octet c * 32 + lane), written by forward, read by backward (the backward is issue-bound;
+                         // regenerating the mask is half of its instructions)
 };
 
 // keep-multipliers (0 or scale) of the 8 elements of octet `oct` (= flat element index / 8)
@@ -126,18 +127,26 @@ __device__ __forceinline__ void drop_mult8(const DropSpec& d, uint32_t step, uin
     }
 }
 
+// multipliers and the keep byte (bit j = element j kept) from the same compares
+__device__ __forceinline__ uint32_t drop_mult8_byte(const DropSpec& d, uint32_t step, uint64_t oct, float (&m)[8]) {
+    const uint4 r = bf_philox4x32_10((uint32_t)oct, (uint32_t)(oct >> 32), d.site, step, d.k0, d.k1);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool k0 = (w[i] & 0xffffu) >= d.threshold, k1 = (w[i] >> 16) >= d.threshold;
+        m[2 * i] = k0 ? d.scale : 0.0f;
+        m[2 * i + 1] = k1 ? d.scale : 0.0f;
+        if (k0) bits |= 1u << (2 * i);
+        if (k1) bits |= 2u << (2 * i);
+    }
+    return bits;
+}
 // the same from the stored keep byte of the octet (bit j = element j kept)
 __device__ __forceinline__ void drop_mult8_bits(const DropSpec& d, uint32_t bits, float (&m)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = (bits & (1u << j)) ? d.scale : 0.0f;
 }
-__device__ __forceinline__ uint32_t keep_byte(const float (&m)[8]) {
-    uint32_t b = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b |= (m[j] != 0.0f ? 1u : 0u) << j;
-    return b;
-}
-
 // ------------------------------------------------------------------ forward
 template <typename T, int C>
 __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
     for (int64_t m = (int64_t)blockIdx.x * kFwdWarps + warp; m < M; m += (int64_t)gridDim.x * kFwdWarps) {
         const int64_t row = row0 + m;
         Pack8<T> pz[C];
+        uint32_t kw = 0;  // keep bytes of this lane's C octets
         {
             Pack8<T> ph[C], pr[C];
 #pragma unroll
@@ -168,8 +178,7 @@ __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
                 pr[c].get(rv);
                 if (drop.threshold) {
                     float mk[8];
-                    drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
-                    if (drop.keep) drop.keep[(int64_t)row * (H / 8) + c * 32 + lane] = (uint8_t)keep_byte(mk);
+                    kw |= drop_mult8_byte(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk) << (8 * c);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) zv[j] = fmaf(hv[j], mk[j], rv[j]);
                 } else {
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(kFwdThreads, kFwdBlocksPerSm)
                 pz[c].store(z + row * H + c * 256 + lane * 8);
             }
         }
+        if (drop.threshold && drop.keep) drop.keep[row * 32 + lane] = kw;  // one coalesced 128 B store per row
         float sum = 0.0f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(BwdCfg<C>::kThreads, 1)
             Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
             if (kDrop) {
                 float mk[8];
-                if (drop.keep) drop_mult8_bits(drop, __ldg(drop.keep + (int64_t)row * (H / 8) + c * 32 + lane), mk);
+                if (drop.keep) drop_mult8_bits(drop, (__ldg(drop.keep + row * 32 + lane) >> (8 * c)) & 0xffu, mk);
                 else drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] *= mk[j];
@@ -554,12 +564,9 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
     int st = 0;
     uint32_t parity = 0;
     float mean_n = 0.0f, rstd_n = 0.0f;  // row statistics: plain loads issued one iteration ahead
-    uint32_t kb_n[C];                    // ... and, when forward stored them, the keep bytes of this lane's octets
+    uint32_t kb_n = 0;                   // ... and, when forward stored it, the word with the keep bytes of this lane's octets
     const bool stored_mask = kDrop && drop.keep != nullptr;
-    auto fetch_keep = [&](int64_t r) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) kb_n[c] = __ldg(drop.keep + r * (H / 8) + c * 32 + lane);
-    };
+    auto fetch_keep = [&](int64_t r) { kb_n = __ldg(drop.keep + r * 32 + lane); };
     if (m_first < M) {
         mean_n = __ldg(mean_in + row0 + m_first), rstd_n = __ldg(rstd_in + row0 + m_first);
         if (stored_mask) fetch_keep(row0 + m_first);
@@ -567,9 +574,7 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
     for (int64_t m = m_first; m < M; m += m_step) {
         const int64_t row = row0 + m;
         const float mean = mean_n, rstd = rstd_n;
-        uint32_t kb[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) kb[c] = stored_mask ? kb_n[c] : 0u;
+        const uint32_t kb = kb_n;
         if (m + m_step < M) {
             mean_n = __ldg(mean_in + row + m_step), rstd_n = __ldg(rstd_in + row + m_step);
             if (stored_mask) fetch_keep(row + m_step);
@@ -633,7 +638,7 @@ __global__ void __launch_bounds__(StagedCfg<T, C>::kThreads, 1)
             Pack8<T>::store(dz + row * H + c * 256 + lane * 8, o);
             if (kDrop) {
                 float mk[8];
-                if (stored_mask) drop_mult8_bits(drop, kb[c], mk);
+                if (stored_mask) drop_mult8_bits(drop, (kb >> (8 * c)) & 0xffu, mk);
                 else drop_mult8(drop, step, (uint64_t)row * (H / 8) + c * 32 + lane, mk);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -791,7 +796,7 @@ extern "C" int bf_resln_supported(int64_t H) { return (H % 256 == 0 && H >= 256 
 extern "C" int bf_resln_fwd_keep(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
                                  int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
                                  uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
-                                 uint8_t* keep, void* stream);
+                                 uint32_t* keep, void* stream);
 extern "C" int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
                             int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
                             uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
@@ -802,7 +807,7 @@ extern "C" int bf_resln_fwd(const void* h, const void* r, int32_t dtype, const f
 extern "C" int bf_resln_fwd_keep(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
                                  int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop,
                                  uint64_t seed, uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd,
-                                 uint8_t* keep, void* stream) {
+                                 uint32_t* keep, void* stream) {
     BF_CHECK_ARG(h && r && gamma && z && y && mean && rstd, "null pointer");
     BF_CHECK_ARG(dtype == BF_F32 || dtype == BF_BF16, "bad dtype");
     BF_CHECK_ARG(S >= 1 && M >= 0 && S <= 65535, "bad S or M");
@@ -834,7 +839,7 @@ extern "C" int64_t bf_resln_bwd_workspace_bytes(int64_t S, int64_t M, int64_t H)
 extern "C" int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
                                  const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
                                  uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
-                                 float* dbeta, float* dbias, void* workspace, const uint8_t* keep, void* stream);
+                                 float* dbeta, float* dbias, void* workspace, const uint32_t* keep, void* stream);
 extern "C" int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
                             const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
                             uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
@@ -845,7 +850,7 @@ extern "C" int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const 
 extern "C" int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
                                  const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop,
                                  uint64_t seed, uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma,
-                                 float* dbeta, float* dbias, void* workspace, const uint8_t* keep, void* stream) {
+                                 float* dbeta, float* dbias, void* workspace, const uint32_t* keep, void* stream) {
     BF_CHECK_ARG(gy && z && gamma && mean && rstd && dz && dgamma && workspace, "null pointer");
     BF_CHECK_ARG(dtype == BF_F32 || dtype == BF_BF16, "bad dtype");
     BF_CHECK_ARG(S >= 1 && M >= 1 && S <= 65535, "bad S or M");
@@ -859,7 +864,7 @@ extern "C" int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, c
                  "gy, z, dz, dh, gamma, dgamma, dbeta, dbias, workspace must be 16-byte aligned (vector / bulk copies)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DropSpec d = make_drop(p_drop, seed, step, site_id);
-    d.keep = const_cast<uint8_t*>(keep);
+    d.keep = const_cast<uint32_t*>(keep);
     if (dtype == BF_BF16) {
         BF_RESLN_DISPATCH(launch_bwd_c, __nv_bfloat16, gy, z, gamma, mean, rstd, dz, dh, dgamma, dbeta, dbias, workspace, S,
                           M, affine_stride, d, st);

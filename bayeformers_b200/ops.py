@@ -824,8 +824,8 @@ class ResidualLayerNormFn(torch.autograd.Function):
         mean = torch.empty(rows, dtype=torch.float32, device=dev)
         rstd = torch.empty(rows, dtype=torch.float32, device=dev)
         nbytes = float(rows * H * hc.element_size() * 4)
-        # the keep bits of the dropout mask go to backward (H / 8 bytes per row) instead of being regenerated there
-        keep = torch.empty((rows, H // 8), dtype=torch.uint8, device=dev) if (drop.p > 0 and resln_keep_bits["on"]) else None
+        # the keep bits of the dropout mask go to backward (one word per lane and row: 128 B) instead of being regenerated there
+        keep = torch.empty((rows, 32), dtype=torch.int32, device=dev) if (drop.p > 0 and resln_keep_bits["on"]) else None
         rc = _timed("resln_fwd", nbytes, dev, lambda: lib.bf_resln_fwd_keep(
             _ptr(hc), _ptr(rc_), _dt(hc.dtype), _ptr(g), _ptr(b), stride, S, M, H, float(eps), float(drop.p), drop.seed,
             drop.step & 0xFFFFFFFF, drop.site_id, _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(keep), _stream(dev)))

@@ -368,17 +368,18 @@ int bf_resln_bwd(const void* gy, const void* z, int32_t dtype, const float* gamm
                  const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop, uint64_t seed,
                  uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma, float* dbeta, float* dbias,
                  void* workspace, void* stream);
-/* the same with the keep bits handed from forward to backward instead of regenerated: keep [S*M, H/8] bytes (bit j of
- * byte o = element 8*o + j kept), written by _fwd_keep, read by _bwd_keep -- the backward is issue-bound and the Philox
- * regeneration is half of its instructions; costs H/8 bytes per row each way.  keep == NULL: the plain functions. */
+/* the same with the keep bits handed from forward to backward instead of regenerated: keep [S*M, 32] uint32 -- word l
+ * of a row holds the keep bytes of the octets c*32 + l (byte c, c < H/256; bit j of a byte = element j of the octet kept)
+ * -- written by _fwd_keep, read by _bwd_keep: the backward is issue-bound and the Philox regeneration is half of its
+ * instructions; costs 128 bytes per row each way (one coalesced store / load per row).  keep == NULL: the plain functions. */
 int bf_resln_fwd_keep(const void* h, const void* r, int32_t dtype, const float* gamma, const float* beta,
                       int64_t affine_stride, int64_t S, int64_t M, int64_t H, float eps, float p_drop, uint64_t seed,
-                      uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd, uint8_t* keep,
+                      uint32_t step, uint32_t site_id, void* z, void* y, float* mean, float* rstd, uint32_t* keep,
                       void* stream);
 int bf_resln_bwd_keep(const void* gy, const void* z, int32_t dtype, const float* gamma, int64_t affine_stride,
                       const float* mean, const float* rstd, int64_t S, int64_t M, int64_t H, float p_drop, uint64_t seed,
                       uint32_t step, uint32_t site_id, void* dz, void* dh, float* dgamma, float* dbeta, float* dbias,
-                      void* workspace, const uint8_t* keep, void* stream);
+                      void* workspace, const uint32_t* keep, void* stream);
 int bf_dropout_mask(uint8_t* out, int64_t n, float p_drop, uint64_t seed, uint32_t step, uint32_t site_id,
                     void* stream);
 
