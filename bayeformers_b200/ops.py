@@ -797,7 +797,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
     """y = layer_norm(dropout_p(h) + r) * gamma_s + beta_s in one pass each way
     (`bf_resln_fwd` / `bf_resln_bwd`): the code around a Bayesian Linear in a
     transformer output block.  gamma / beta: fp32 [S, H] (sampled, row A10) or [H]
-    (shared).  The dropout mask is a function of its Philox counter; its keep bits are handed to backward (H / 8
+    (shared).  The dropout mask is a function of its Philox counter; its keep bits are handed to backward (128
     bytes per row) rather than regenerated there (`resln_keep_bits`).
     `bias_grad_box` (a list) receives sum_m dh[s][m][:] for the Linear that made h."""
 

@@ -88,7 +88,7 @@ def parse():
                          "bf.accelerate_host_)")
     ap.add_argument("--resln-keep-bits", type=int, default=1,
                     help="1 (default): the fused dropout+residual+LayerNorm forward hands the mask's keep bits to its backward "
-                         "(H/8 bytes per row); 0: the backward regenerates them from the Philox counter")
+                         "(128 bytes per row); 0: the backward regenerates them from the Philox counter")
     ap.add_argument("--gelu-poly", type=int, default=1,
                     help="1 (default): the fused GELU / GELU' epilogues evaluate odd polynomials (|err| <= 1e-4 / 6e-4, "
                          "inside bf16 rounding); 0: the erf forms (bf_set_option(BF_OPT_GELU_POLY))")

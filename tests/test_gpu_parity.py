@@ -1006,7 +1006,7 @@ def test_resln_vs_torch_fp64(S, M, H, shared, dtype, p):
     assert torch.equal(y, y2) and torch.equal(hd.grad, hd2.grad) and torch.equal(rd.grad, rd2.grad)
     assert torch.equal(gd.grad, gd2.grad) and torch.equal(bd.grad, bd2.grad) and torch.equal(box[0], box2[0])
     if p > 0:
-        # the backward normally LOADS the keep bits forward stored (H / 8 bytes per row); regenerating them from the Philox
+        # the backward normally LOADS the keep bits forward stored (128 bytes per row); regenerating them from the Philox
         # counter instead (ops.resln_keep_bits off) gives the same bits everywhere
         ops.resln_keep_bits["on"] = False
         try:
