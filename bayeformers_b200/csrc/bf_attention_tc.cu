@@ -10,8 +10,9 @@
 //   warp 17     MMA issuer (one thread)
 //   forward: warps 18..25 generate the Philox keep bits of the pairs ahead (they fill the issue slots the row workers
 //   leave idle; in the row workers the mask was 2/3 of all instructions); backward: warp 18 stores the gradient tiles
-// Outputs leave straight from registers: a thread holds 16 consecutive bf16 of an output row = one 32 B sector
-// (st.global.v8), so there is no staging tile, no store fence and no wait for a bulk store.
+// Forward outputs leave straight from registers: a thread holds 16 consecutive bf16 of an output row = one 32 B sector
+// (st.global.v8).  The backward stages its three gradient tiles where P_d / dS were and a store warp sends them off by
+// TMA while the next pair's second pass computes (direct stores of 48 KB per pair were LSU-bound).
 //
 // forward, per pair:   S = q k^T  (128x128x64, TMEM)        -> rows: max / exp2 / sum (four quarters exchanged through
 //                      shared memory), Philox keep bits (stored: 16 B per row, the backward does not regenerate them),
@@ -55,7 +56,8 @@ constexpr int BWD_SMEM = 1024 + 2 * BWD_BUF + 4 * TILE + XCH_BYTES + BAR_BYTES; 
 constexpr uint32_t TMEM_COLS = 512;
 
 struct Params {
-    __nv_bfloat16 *out, *dq, *dk, *dv;  // [B, 128, heads, 64]: written row quarter by row quarter (32 B per thread)
+    __nv_bfloat16* out;  // forward: [B, 128, heads, 64], written row quarter by row quarter (32 B per thread); the
+                         // backward's dq / dk / dv leave through TMA stores (tensor maps)
     float* lse;       // [B, heads, 128] base-2 log-sum-exp of the scaled scores
     uint32_t* keep;   // [B, heads, 128, 4] keep bits of the 128 keys of a row (bit k % 32 of word k / 32), or null
     int H, total;     // heads, B * heads
@@ -667,7 +669,6 @@ int bf_attention_tc_bwd(const void* dout, const void* q, const void* k, const vo
     if ((rc = encode_pair_map(&mdv, dv, B, H, osb, osh, ost))) return rc;
     Params p{};
     fill(p, B, H, scale, p_drop, seed, step, site, const_cast<float*>(lse), const_cast<uint32_t*>(keep));
-    p.dq = (__nv_bfloat16*)dq, p.dk = (__nv_bfloat16*)dk, p.dv = (__nv_bfloat16*)dv;
     BF_CUDA_OK(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     const int grid = p.total < bf_num_sms() ? p.total : bf_num_sms();
     const int64_t n_bias = 3 * S * H * DD;
