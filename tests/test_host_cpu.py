@@ -408,3 +408,46 @@ def test_native_attention_glue_registers_and_hands_bias_boxes():
             boxes = blocks[0]._bf_qkv_boxes
             assert [blocks[0].query._bias_grad_box, blocks[0].key._bias_grad_box, blocks[0].value._bias_grad_box] == boxes
             assert all(b == [] for b in boxes) and boxes[0] is not boxes[1]
+
+
+def test_gelu_epilogue_polynomials_meet_their_stated_error():
+    """The fused GELU / GELU' epilogues (csrc/bf_gemm_act.cu: gelu_poly2, gelu_grad_poly2) evaluate odd polynomials on
+    the argument clamped to [-4, 4].  Read the coefficients out of the CUDA source, evaluate them the way the kernel does
+    (float32 Horner in z^2), and check the error bounds the source and DESIGN.md state against the erf forms in float64."""
+    import math
+    import os
+    import re
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "bayeformers_b200", "csrc", "bf_gemm_act.cu")).read()
+
+    def coefficients(fn):
+        body = src[src.index(f"bf_f2 {fn}(bf_f2 z2)"):]
+        body = body[:body.index("\n}\n")]
+        vals = [float(v) for v in re.findall(r"bf_splat2\((-?[0-9.]+e[-+][0-9]+)f\)", body)]
+        return vals  # highest degree first, as the Horner chain lists them
+
+    erf = np.vectorize(math.erf)
+    z = np.linspace(-8.0, 8.0, 400001).astype(np.float32)
+    zc = np.clip(z, np.float32(-4.0), np.float32(4.0))
+    t = zc * zc
+    z64 = z.astype(np.float64)
+    phi = 0.5 * (1.0 + erf(z64 / math.sqrt(2.0)))
+    for fn, n_coef, truth, tol_inside, tol_all in (
+            ("gelu_poly2", 8, phi, 3e-5, 6e-5),
+            ("gelu_grad_poly2", 9, phi + z64 * np.exp(-0.5 * z64 * z64) / math.sqrt(2.0 * math.pi), 1e-4, 6e-4)):
+        c = coefficients(fn)
+        assert len(c) == n_coef, (fn, c)
+        acc = np.full_like(t, np.float32(c[0]))
+        for ck in c[1:]:
+            acc = acc * t + np.float32(ck)
+        got = (np.float32(0.5) + zc * acc).astype(np.float64)  # Phi(z) resp. gelu'(z)
+        err = np.abs(got - truth)
+        assert err[np.abs(z) <= 4.0].max() < tol_inside, (fn, err[np.abs(z) <= 4.0].max())
+        assert err.max() < tol_all, (fn, err.max())
+    # and the activation itself: z * Phi(z) against the exact GELU, relative to bf16's rounding step at that magnitude
+    c = coefficients("gelu_poly2")
+    acc = np.full_like(t, np.float32(c[0]))
+    for ck in c[1:]:
+        acc = acc * t + np.float32(ck)
+    y = (z * (np.float32(0.5) + zc * acc)).astype(np.float64)
+    assert np.abs(y - z64 * phi).max() < 4.5e-4  # worst at |z| = 8 (clamped tail); bf16 rounding of 8.0 is 3.1e-2
