@@ -109,3 +109,29 @@ def dropout_keep_mask(n: int, p: float, seed: int, step: int, site_id: int) -> n
         u[:, 2 * i] = r[i] & np.uint32(0xFFFF)
         u[:, 2 * i + 1] = r[i] >> np.uint32(16)
     return (u.reshape(-1)[:n] >= thr).astype(np.uint8)
+
+
+def attention_keep_mask(B: int, H: int, T: int, p: float, seed: int, step: int, site_id: int) -> np.ndarray:
+    """Keep mask (uint8 [B, H, T, T], 1 = kept) of the attention kernels (include/bayeformers_b200.h, bf_attention_fwd /
+    bf_attention_dropout_mask; both kernel families -- tcgen05 and mma.sync -- apply this one function).  The reference
+    leaves attention dropout to torch's generator inside the host model; this states the counter-based replacement.
+
+    Contract  (row = (b * H + h) * T + q, key k)
+        counter = (row, (k % 8) // 2 + 4 * (k // 32), 0x40000000 | site_id, step)
+        out     = philox4x32_10(counter, key = seed) -> (r0, r1, r2, r3)
+        u16     = r_{(k // 8) % 4} & 0xffff  for even k,  >> 16  for odd k
+        keep    = u16 >= min(round(p * 65536), 65535);  p <= 0 keeps everything
+    """
+    if p <= 0:
+        return np.ones((B, H, T, T), dtype=np.uint8)
+    thr = min(int(np.rint(np.float32(p).astype(np.float64) * 65536.0)), 65535)
+    rows = np.arange(B * H * T, dtype=np.uint64)[:, None]
+    k = np.arange(T, dtype=np.uint64)[None, :]
+    c1 = (k % np.uint64(8)) // np.uint64(2) + np.uint64(4) * (k // np.uint64(32))
+    r = philox4x32_10(np.broadcast_to(rows, (B * H * T, T)).copy(), np.broadcast_to(c1, (B * H * T, T)).copy(),
+                      0x40000000 | (site_id & 0x3FFFFFFF), step, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    word = ((k // np.uint64(8)) % np.uint64(4)).astype(np.int64)
+    words = np.stack([np.broadcast_to(x, (B * H * T, T)) for x in r], axis=0)  # [4, rows, T]
+    sel = np.take_along_axis(words, np.broadcast_to(word, (B * H * T, T))[None], axis=0)[0]
+    u16 = np.where((k % np.uint64(2)) == 0, sel & np.uint32(0xFFFF), sel >> np.uint32(16))
+    return (u16 >= thr).astype(np.uint8).reshape(B, H, T, T)

@@ -1418,6 +1418,16 @@ def test_attention_tcgen05_and_mma_sync_kernels_share_one_mask_and_agree():
     assert torch.equal(got[0], got[1])
 
 
+@pytest.mark.parametrize("B,H,Tn,p,seed,step,site", [(2, 3, 128, 0.1, 0x1234567, 5, 7), (1, 2, 64, 0.5, 0xDEADBEEFCAFEF00D, 9, 77),
+                                                      (3, 1, 16, 0.25, 3, 0, 1)])
+def test_attention_dropout_mask_matches_oracle_contract(B, H, Tn, p, seed, step, site):
+    """The keep mask of the attention kernels against its CPU restatement (oracle/philox_oracle.attention_keep_mask):
+    integer work, bit-exact.  (The tcgen05 forward's stored keep bits are tied to this mask kernel bit for bit in
+    test_attention_tcgen05_and_mma_sync_kernels_share_one_mask_and_agree.)"""
+    got = ops.attention_dropout_mask(B, H, Tn, ops.DropoutSpec(p, seed, site, step), DEV).cpu().numpy()
+    assert np.array_equal(got, P.attention_keep_mask(B, H, Tn, p, seed, step, site))
+
+
 def test_attention_dropout_masks_are_independent_across_sites_and_steps():
     B, H, Tn = 4, 12, 128
     base = ops.DropoutSpec(p=0.1, seed=11, site_id=3, step=5)

@@ -221,3 +221,18 @@ def test_oracle_convert_matches_live_reference():
     assert torch.equal(ref(x), ora(x))
     assert torch.equal(ref.log_prior(), O.model_log_prior(ora))
     assert torch.equal(ref.log_variational_posterior(), O.model_log_variational_posterior(ora))
+
+
+def test_attention_keep_mask_oracle_rate_and_determinism():
+    """oracle.attention_keep_mask (the contract the attention kernels are checked against on the GPU): keep rate of the
+    quantised threshold, determinism, independence of consecutive steps, everything kept at p = 0."""
+    from oracle import philox_oracle as P
+    m = P.attention_keep_mask(4, 3, 128, 0.1, 11, 5, 3)
+    thr = round(0.1 * 65536)
+    n = m.size
+    assert m.shape == (4, 3, 128, 128) and m.dtype == np.uint8
+    assert abs(m.mean() - (1 - thr / 65536)) < 5 * np.sqrt(0.09 / n)
+    assert np.array_equal(m, P.attention_keep_mask(4, 3, 128, 0.1, 11, 5, 3))
+    m2 = P.attention_keep_mask(4, 3, 128, 0.1, 11, 6, 3).astype(np.float64)
+    assert abs(np.corrcoef(m.reshape(-1).astype(np.float64), m2.reshape(-1))[0, 1]) < 5 / np.sqrt(n)
+    assert P.attention_keep_mask(1, 1, 16, 0.0, 1, 1, 1).all()
